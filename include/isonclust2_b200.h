@@ -1,0 +1,115 @@
+/* isonclust2_b200 — C ABI of the B200 (sm_100a) implementation of isONclust2's
+ * data-parallel clustering hot path.
+ *
+ * The reference (nanoporetech/isONclust2) has no plugin / FFI surface: every
+ * function of the path is an internal C++ free function linked into one
+ * binary.  This header is the boundary a maintainer would bind instead of
+ * those functions; each entry point names the reference function(s) it
+ * replaces (paths relative to the reference tree).  INTEGRATION.md shows the
+ * call sites on the reference side.
+ *
+ * Conventions: plain pointers and sizes only; every function returns ICB_OK
+ * (0) or a negative ICB_ERR_* code and never throws; a context owns one CUDA
+ * device and one stream and is not shared between host threads concurrently
+ * (create one context per thread); host pointers may be pageable or pinned
+ * (pinned makes the copies asynchronous).  Reads are passed "flat": one byte
+ * string of concatenated sequences, one of concatenated Phred+33 qualities
+ * and offs[n_reads+1] (int64) with read i = [offs[i], offs[i+1]).
+ */
+#ifndef ISONCLUST2_B200_H
+#define ISONCLUST2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICB_OK 0
+#define ICB_ERR_CUDA -1		/* a CUDA runtime call failed; see icb_last_error */
+#define ICB_ERR_ARG -2		/* invalid argument */
+#define ICB_ERR_INVALID_BASE -3 /* a sketched read holds a base outside ACGT (reference: RevComp throws, util.cpp:31-33) */
+#define ICB_ERR_NO_PEMP -4	/* no empirical p_shared row for this (k, w, e1, e2) (reference: GetPMinShared throws, p_emp_prob.cpp:88) */
+#define ICB_ERR_STATE -5	/* call order violated (e.g. download before compute) */
+#define ICB_ERR_NOMEM -6
+
+typedef struct icb_ctx icb_ctx;
+typedef struct icb_readset icb_readset;
+
+/* {Min, Pos, Index}: byte-identical to the reference's Minimizer (minimizer.h:20-29) */
+typedef struct {
+    uint32_t Min, Pos, Index;
+} icb_minimizer;
+
+/* ------------------------------------------------------------------ context */
+int icb_device_count(void);
+int icb_ctx_create(int device, icb_ctx** ctx);
+void icb_ctx_destroy(icb_ctx* ctx);
+int icb_ctx_sync(icb_ctx* ctx);
+/* the context's cudaStream_t, so a caller can bracket work with its own CUDA events */
+void* icb_ctx_stream(icb_ctx* ctx);
+const char* icb_last_error(icb_ctx* ctx);
+const char* icb_strerror(int code);
+
+/* Per-kernel device timing (CUDA events on the context's stream).  When enabled every kernel launch is
+ * bracketed by an event pair; icb_ctx_kernel_time returns the number of launches and the summed
+ * milliseconds recorded for the kernel called `name` since the last reset (synchronises the stream). */
+int icb_ctx_timing(icb_ctx* ctx, int enable);
+int icb_ctx_timing_reset(icb_ctx* ctx);
+int icb_ctx_kernel_time(icb_ctx* ctx, const char* name, int64_t* launches, double* total_ms);
+/* total kernel launches issued by this context since creation (always counted) */
+int64_t icb_ctx_launch_count(icb_ctx* ctx);
+
+/* ------------------------------------------------------------------ host-side helpers (no device work)
+ * The three expressions of the path the reference evaluates with the HOST libm / libstdc++; they stay on the
+ * host so results are bit-identical:
+ *   icb_init_qual_tab    InitQualTab (nomin=0) / InitQualTabNomin (nomin=1), qualscore.cpp:156-180
+ *   icb_quality_filter   filtered[i] = (-10*log10(err[i])) <= min_qual, qualscore.cpp:56 and cluster.cpp:157
+ *   icb_sort_by_score    SortByQualScores, qualscore.cpp:138-145: stable, descending; order[slot] = read index */
+void icb_init_qual_tab(double tab[129], int nomin);
+int icb_quality_filter(const double* err, int64_t n, double min_qual, uint8_t* filtered);
+int icb_sort_by_score(const double* score, int64_t n, int32_t* order);
+
+/* ------------------------------------------------------------------ read set
+ * Uploads the flat reads to the device (the only copy of the inputs the device stages need). */
+int icb_readset_create(icb_ctx* ctx, const char* seq, const char* qual, const int64_t* offs, int64_t n_reads,
+		       icb_readset** rs);
+void icb_readset_destroy(icb_readset* rs);
+int64_t icb_readset_n_reads(const icb_readset* rs);
+int64_t icb_readset_n_bases(const icb_readset* rs);
+
+/* ------------------------------------------------------------------ stage 1a: quality scores
+ * Replaces FillQualScores (qualscore.cpp:14-37) = CalcQualScore (:107-136) + CalcErrorRate (:147-154) for
+ * every read.  qualtab / qualtab_nomin are InitQualTab() / InitQualTabNomin() (:156-180) computed by the
+ * HOST libm (129 doubles each) — the device never evaluates pow().  Results stay on the device
+ * (the sketch and cluster stages read them) until downloaded. */
+int icb_score_reads(icb_readset* rs, int kmer_size, const double qualtab[129], const double qualtab_nomin[129]);
+int icb_scores_download(icb_readset* rs, double* score, double* err);
+
+/* ------------------------------------------------------------------ stage 1b: sketches
+ * Replaces the per-read body of PrepareSortedBatch (qualscore.cpp:62-96): HomopolymerCompress (hpc.cpp:4-32),
+ * CalcErrorRate on the compressed qualities, KmerEncodeSeq (kmer_index.cpp:5-17) of the compressed read and of
+ * its RevComp (util.cpp:13-38), GetKmerMinimizers (minimizer.cpp:78-123) on both.
+ *
+ * skip (may be NULL): n_reads bytes, non-zero = the host's quality filter (qualscore.cpp:56, needs host
+ * log10) rejected the read -> status 0, nothing computed.
+ * status per read: 0 skipped by `skip`; 1 sketched; 2 raw read too short to compress (kept without sketch,
+ * qualscore.cpp:91-96); 3 compressed read shorter than 2k or w (dropped, qualscore.cpp:65-73).
+ * Returns ICB_ERR_INVALID_BASE if a read that reaches the RevComp step holds a non-ACGT base. */
+int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const double qualtab_nomin[129],
+		     const uint8_t* skip);
+/* totals, to size the download buffers */
+int icb_sketch_sizes(icb_readset* rs, int64_t* n_minimizers, int64_t* n_rev_minimizers);
+/* Any pointer may be NULL to skip that array.
+ *   status[n], hpc_len[n], hpc_err[n]
+ *   hpc_seq / hpc_qual: n_bases bytes each; the compressed read i occupies [offs[i], offs[i]+hpc_len[i])
+ *       — the SAME offsets as the raw read (compression never grows a read), the rest of the slot is unspecified
+ *   mins: n_minimizers entries, read i = [min_offs[i], min_offs[i+1]) ; rev_mins likewise with rev_offs */
+int icb_sketch_download(icb_readset* rs, int32_t* status, int32_t* hpc_len, double* hpc_err, char* hpc_seq,
+			char* hpc_qual, icb_minimizer* mins, int64_t* min_offs, icb_minimizer* rev_mins,
+			int64_t* rev_offs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

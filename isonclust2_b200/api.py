@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference's hot-path interface on top of the C ABI.
+
+Names follow the reference (FillQualScores / SortByQualScores / PrepareSortedBatch, qualscore.h:14-24) so the
+parity tests read like the reference's own.  Everything numeric happens in libisonclust2_b200.so; this module
+only marshals numpy buffers, evaluates the two host-libm expressions the reference evaluates on the host
+(InitQualTab's pow, the -10*log10(err) quality filter) and orders reads.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import lib as _lib
+
+MIN_DT = np.dtype([("Min", "<u4"), ("Pos", "<u4"), ("Index", "<u4")])
+
+
+class IcbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+def init_qual_tab():
+    """InitQualTab (qualscore.cpp:156-169): host libm pow, capped at 0.79433."""
+    t = np.zeros(129)
+    _lib.load().icb_init_qual_tab(t.ctypes.data, 0)
+    return t
+
+
+def init_qual_tab_nomin():
+    """InitQualTabNomin (qualscore.cpp:171-180)."""
+    t = np.zeros(129)
+    _lib.load().icb_init_qual_tab(t.ctypes.data, 1)
+    return t
+
+
+def quality_filtered(err, min_qual):
+    """(-10*log10(err)) <= minQual with the host libm, like qualscore.cpp:56 / cluster.cpp:157."""
+    err = np.ascontiguousarray(err, dtype=np.float64)
+    out = np.zeros(len(err), dtype=np.uint8)
+    rc = _lib.load().icb_quality_filter(err.ctypes.data, len(err), float(min_qual), out.ctypes.data)
+    if rc:
+        raise IcbError(rc, "icb_quality_filter")
+    return out
+
+
+quality_filtered_fast = quality_filtered
+
+
+def sort_by_qual_scores(score):
+    """SortByQualScores (qualscore.cpp:138-145): std::stable_sort, descending."""
+    score = np.ascontiguousarray(score, dtype=np.float64)
+    order = np.empty(len(score), dtype=np.int32)
+    rc = _lib.load().icb_sort_by_score(score.ctypes.data, len(score), order.ctypes.data)
+    if rc:
+        raise IcbError(rc, "icb_sort_by_score")
+    return order
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        rc = self.L.icb_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise IcbError(rc, self.L.icb_strerror(rc).decode() + " (icb_ctx_create; is a CUDA device visible?)")
+        self.h = h
+        self.device = device
+        self.qualtab = init_qual_tab()
+        self.qualtab_nomin = init_qual_tab_nomin()
+
+    def check(self, rc):
+        if rc != 0:
+            raise IcbError(rc, self.L.icb_last_error(self.h).decode() or self.L.icb_strerror(rc).decode())
+
+    def close(self):
+        if self.h:
+            self.L.icb_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        self.check(self.L.icb_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.L.icb_ctx_stream(self.h)
+
+    def timing(self, enable=True):
+        self.check(self.L.icb_ctx_timing(self.h, 1 if enable else 0))
+
+    def timing_reset(self):
+        self.check(self.L.icb_ctx_timing_reset(self.h))
+
+    def kernel_time(self, name):
+        n, ms = C.c_int64(), C.c_double()
+        self.check(self.L.icb_ctx_kernel_time(self.h, name.encode(), C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def launch_count(self):
+        return self.L.icb_ctx_launch_count(self.h)
+
+    def upload(self, seq, qual, offs):
+        return ReadSet(self, seq, qual, offs)
+
+
+class ReadSet:
+    """Device-resident flat reads + their scores and sketches."""
+
+    def __init__(self, ctx, seq, qual, offs):
+        self.ctx = ctx
+        L = ctx.L
+        seq = np.ascontiguousarray(seq, dtype=np.uint8) if not isinstance(seq, np.ndarray) else seq
+        qual = np.ascontiguousarray(qual, dtype=np.uint8) if not isinstance(qual, np.ndarray) else qual
+        self.offs = np.ascontiguousarray(offs, dtype=np.int64)
+        self.n = len(self.offs) - 1
+        self.n_bases = int(self.offs[-1])
+        h = C.c_void_p()
+        ctx.check(L.icb_readset_create(ctx.h, seq.ctypes.data, qual.ctypes.data, self.offs.ctypes.data, self.n, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.L.icb_readset_destroy(self.h)
+            self.h = None
+
+    # FillQualScores
+    def score_async(self, k):
+        c = self.ctx
+        c.check(c.L.icb_score_reads(self.h, k, c.qualtab.ctypes.data, c.qualtab_nomin.ctypes.data))
+
+    def scores(self, score=None, err=None):
+        c = self.ctx
+        score = np.empty(self.n) if score is None else score
+        err = np.empty(self.n) if err is None else err
+        c.check(c.L.icb_scores_download(self.h, score.ctypes.data, err.ctypes.data))
+        return score, err
+
+    def score(self, k):
+        self.score_async(k)
+        return self.scores()
+
+    # PrepareSortedBatch body
+    def sketch_async(self, k, w, skip=None):
+        c = self.ctx
+        if skip is not None:
+            skip = np.ascontiguousarray(skip, dtype=np.uint8)
+        c.check(c.L.icb_sketch_reads(self.h, k, w, c.qualtab_nomin.ctypes.data, skip.ctypes.data if skip is not None else None))
+
+    def sketch_sizes(self):
+        a, b = C.c_int64(), C.c_int64()
+        self.ctx.check(self.ctx.L.icb_sketch_sizes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def sketch_download(self, hpc=True):
+        c = self.ctx
+        nf, nr = self.sketch_sizes()
+        n = self.n
+        status, hpc_len = np.empty(n, np.int32), np.empty(n, np.int32)
+        hpc_err = np.empty(n)
+        hs = np.empty(self.n_bases, np.uint8) if hpc else None
+        hq = np.empty(self.n_bases, np.uint8) if hpc else None
+        mins, rmins = np.empty(nf, MIN_DT), np.empty(nr, MIN_DT)
+        mo, ro = np.empty(n + 1, np.int64), np.empty(n + 1, np.int64)
+        c.check(c.L.icb_sketch_download(self.h, status.ctypes.data, hpc_len.ctypes.data, hpc_err.ctypes.data,
+                                        hs.ctypes.data if hpc else None, hq.ctypes.data if hpc else None,
+                                        mins.ctypes.data, mo.ctypes.data, rmins.ctypes.data, ro.ctypes.data))
+        return dict(status=status, hpc_len=hpc_len, hpc_err=hpc_err, hpc_seq=hs, hpc_qual=hq, mins=mins, min_offs=mo,
+                    rev_mins=rmins, rev_offs=ro)
+
+    def sketch(self, k, w, skip=None, hpc=True):
+        self.sketch_async(k, w, skip)
+        return self.sketch_download(hpc=hpc)

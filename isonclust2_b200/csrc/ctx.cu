@@ -1,0 +1,235 @@
+// Context, error reporting, kernel timers and the device-resident read set.
+#include <cstdio>
+#include <cstring>
+
+#include "icb_common.cuh"
+
+int icb_ctx::fail_cuda(cudaError_t e, const char* what, const char* file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", int(e), cudaGetErrorString(e), what, file, line);
+    last_error = buf;
+    return ICB_ERR_CUDA;
+}
+
+int icb_ctx::fail(int code, const std::string& msg)
+{
+    last_error = msg;
+    return code;
+}
+
+cudaEvent_t icb_ctx::get_event()
+{
+    if (!event_pool.empty()) {
+	cudaEvent_t e = event_pool.back();
+	event_pool.pop_back();
+	return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void icb_ctx::timer_begin(const char* name)
+{
+    auto& t = timers[name];
+    cudaEvent_t a = get_event(), b = get_event();
+    cudaEventRecord(a, stream);
+    t.pending.emplace_back(a, b);
+}
+
+void icb_ctx::timer_end(const char* name)
+{
+    auto& t = timers[name];
+    cudaEventRecord(t.pending.back().second, stream);
+}
+
+void icb_ctx::timers_collect()
+{
+    cudaStreamSynchronize(stream);
+    for (auto& kv : timers) {
+	for (auto& p : kv.second.pending) {
+	    float ms = 0.f;
+	    cudaEventElapsedTime(&ms, p.first, p.second);
+	    kv.second.launches++;
+	    kv.second.total_ms += ms;
+	    event_pool.push_back(p.first);
+	    event_pool.push_back(p.second);
+	}
+	kv.second.pending.clear();
+    }
+}
+
+extern "C" {
+
+int icb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int icb_ctx_create(int device, icb_ctx** out)
+{
+    if (!out) return ICB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return ICB_ERR_CUDA;  // no CPU fallback: fail loudly
+    if (device < 0 || device >= n) return ICB_ERR_ARG;
+    auto ctx = new icb_ctx;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+	delete ctx;
+	return ICB_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return ICB_OK;
+}
+
+void icb_ctx_destroy(icb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->timers_collect();
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int icb_ctx_sync(icb_ctx* ctx)
+{
+    ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ICB_OK;
+}
+
+void* icb_ctx_stream(icb_ctx* ctx) { return (void*)ctx->stream; }
+const char* icb_last_error(icb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+const char* icb_strerror(int code)
+{
+    switch (code) {
+	case ICB_OK: return "ok";
+	case ICB_ERR_CUDA: return "CUDA runtime error (no usable GPU or a failed call)";
+	case ICB_ERR_ARG: return "invalid argument";
+	case ICB_ERR_INVALID_BASE: return "Invalid base encountered";
+	case ICB_ERR_NO_PEMP: return "Empirical probability lookup failure!";
+	case ICB_ERR_STATE: return "call order violated";
+	case ICB_ERR_NOMEM: return "out of memory";
+    }
+    return "unknown error";
+}
+
+int icb_ctx_timing(icb_ctx* ctx, int enable)
+{
+    ctx->timers_collect();
+    ctx->timing = enable != 0;
+    return ICB_OK;
+}
+
+int icb_ctx_timing_reset(icb_ctx* ctx)
+{
+    ctx->timers_collect();
+    ctx->timers.clear();
+    return ICB_OK;
+}
+
+int icb_ctx_kernel_time(icb_ctx* ctx, const char* name, int64_t* launches, double* total_ms)
+{
+    ctx->timers_collect();
+    auto it = ctx->timers.find(name);
+    if (it == ctx->timers.end()) {
+	if (launches) *launches = 0;
+	if (total_ms) *total_ms = 0.0;
+	return ICB_OK;
+    }
+    if (launches) *launches = it->second.launches;
+    if (total_ms) *total_ms = it->second.total_ms;
+    return ICB_OK;
+}
+
+int64_t icb_ctx_launch_count(icb_ctx* ctx) { return ctx->launch_count; }
+
+// ---------------------------------------------------------------- read set
+
+static const int64_t PAD = 256;	 // slack after the byte buffers so 16-byte tile loads may overrun
+
+int icb_readset_create(icb_ctx* ctx, const char* seq, const char* qual, const int64_t* offs, int64_t n_reads,
+		       icb_readset** out)
+{
+    if (!ctx || !out || n_reads < 0 || (n_reads > 0 && (!seq || !qual || !offs))) return ICB_ERR_ARG;
+    *out = nullptr;
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto rs = new icb_readset;
+    rs->ctx = ctx;
+    rs->n_reads = n_reads;
+    rs->h_offs.assign(offs, offs + n_reads + 1);
+    if (n_reads == 0) rs->h_offs.assign(1, 0);
+    for (int64_t i = 0; i < n_reads; i++) {
+	int64_t l = offs[i + 1] - offs[i];
+	if (l < 0 || l > 0x7fffff00LL) {
+	    delete rs;
+	    return ctx->fail(ICB_ERR_ARG, "offsets must be non-decreasing and reads shorter than 2^31");
+	}
+	if (l > rs->max_len) rs->max_len = l;
+    }
+    rs->n_bases = rs->h_offs[n_reads] - rs->h_offs[0];
+    if (rs->h_offs[0] != 0) {
+	delete rs;
+	return ctx->fail(ICB_ERR_ARG, "offs[0] must be 0");
+    }
+    int64_t nb = rs->n_bases;
+    cudaError_t e;
+#define RS_ALLOC(ptr, bytes)                                           \
+    if ((e = cudaMalloc((void**)&(ptr), (size_t)(bytes))) != cudaSuccess) { \
+	icb_readset_destroy(rs);                                       \
+	return ctx->fail_cuda(e, "cudaMalloc " #ptr, __FILE__, __LINE__);  \
+    }
+    RS_ALLOC(rs->d_seq, nb + PAD);
+    RS_ALLOC(rs->d_qual, nb + PAD);
+    RS_ALLOC(rs->d_offs, sizeof(int64_t) * (n_reads + 1));
+    RS_ALLOC(rs->d_score, sizeof(double) * (n_reads + 1));
+    RS_ALLOC(rs->d_err, sizeof(double) * (n_reads + 1));
+    RS_ALLOC(rs->d_counters, sizeof(unsigned long long) * 8);
+#undef RS_ALLOC
+    ICB_CUDA(ctx, cudaMemsetAsync(rs->d_seq + nb, 0, PAD, ctx->stream));
+    ICB_CUDA(ctx, cudaMemsetAsync(rs->d_qual + nb, 0, PAD, ctx->stream));
+    if (nb > 0) {
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_seq, seq, nb, cudaMemcpyHostToDevice, ctx->stream));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_qual, qual, nb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_offs, rs->h_offs.data(), sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice,
+				  ctx->stream));
+    *out = rs;
+    return ICB_OK;
+}
+
+void icb_readset_destroy(icb_readset* rs)
+{
+    if (!rs) return;
+    cudaSetDevice(rs->ctx->device);
+    cudaStreamSynchronize(rs->ctx->stream);
+    cudaFree(rs->d_seq);
+    cudaFree(rs->d_qual);
+    cudaFree(rs->d_offs);
+    cudaFree(rs->d_score);
+    cudaFree(rs->d_err);
+    cudaFree(rs->d_status);
+    cudaFree(rs->d_hpc_len);
+    cudaFree(rs->d_hpc_err);
+    cudaFree(rs->d_hpc_seq);
+    cudaFree(rs->d_hpc_qual);
+    cudaFree(rs->d_mins);
+    cudaFree(rs->d_min_off);
+    cudaFree(rs->d_nf);
+    cudaFree(rs->d_nr);
+    cudaFree(rs->d_counters);
+    cudaFree(rs->d_long_list);
+    cudaFree(rs->d_long_scratch);
+    delete rs;
+}
+
+int64_t icb_readset_n_reads(const icb_readset* rs) { return rs->n_reads; }
+int64_t icb_readset_n_bases(const icb_readset* rs) { return rs->n_bases; }
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Internal definitions shared by the CUDA translation units of libisonclust2_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "isonclust2_b200.h"
+
+#define ICB_SM_COUNT_FALLBACK 148
+
+struct icb_kernel_timer {
+    int64_t launches = 0;
+    double total_ms = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct icb_ctx {
+    int device = 0;
+    int sm_count = ICB_SM_COUNT_FALLBACK;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    bool timing = false;
+    int64_t launch_count = 0;
+    std::map<std::string, icb_kernel_timer> timers;
+    std::vector<cudaEvent_t> event_pool;
+
+    int fail_cuda(cudaError_t e, const char* what, const char* file, int line);
+    int fail(int code, const std::string& msg);
+    cudaEvent_t get_event();
+    void timer_begin(const char* name);
+    void timer_end(const char* name);
+    void timers_collect();
+};
+
+#define ICB_CUDA(ctx, call)                                                   \
+    do {                                                                      \
+	cudaError_t e__ = (call);                                             \
+	if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// RAII-free launch bracket: ICB_LAUNCH(ctx, "name", kernel<<<...>>>(...));
+#define ICB_LAUNCH(ctx, name, ...)                                            \
+    do {                                                                      \
+	(ctx)->launch_count++;                                                \
+	if ((ctx)->timing) (ctx)->timer_begin(name);                          \
+	__VA_ARGS__;                                                          \
+	if ((ctx)->timing) (ctx)->timer_end(name);                            \
+	ICB_CUDA(ctx, cudaGetLastError());                                    \
+    } while (0)
+
+struct icb_readset {
+    icb_ctx* ctx = nullptr;
+    int64_t n_reads = 0;
+    int64_t n_bases = 0;
+    int64_t max_len = 0;
+    std::vector<int64_t> h_offs;  // host copy of the offsets
+    // inputs
+    uint8_t* d_seq = nullptr;
+    uint8_t* d_qual = nullptr;
+    int64_t* d_offs = nullptr;
+    // stage 1a
+    bool scored = false;
+    double* d_score = nullptr;
+    double* d_err = nullptr;
+    // stage 1b
+    bool sketched = false;
+    int sk_k = 0, sk_w = 0;
+    int32_t* d_status = nullptr;
+    int32_t* d_hpc_len = nullptr;
+    double* d_hpc_err = nullptr;
+    uint8_t* d_hpc_seq = nullptr;
+    uint8_t* d_hpc_qual = nullptr;
+    icb_minimizer* d_mins = nullptr;  // arena: per read fwd then rev, located by d_min_off
+    int64_t mins_capacity = 0;
+    int64_t* d_min_off = nullptr;  // arena offset of read i (fwd minimizers first)
+    int32_t* d_nf = nullptr;	   // forward count
+    int32_t* d_nr = nullptr;	   // reverse count
+    unsigned long long* d_counters = nullptr;  // [0] arena cursor, [1] error flags, [2] long-read list cursor
+    int32_t* d_long_list = nullptr;
+    uint8_t* d_long_scratch = nullptr;
+    int64_t total_f = 0, total_r = 0;
+};
+
+// stage launchers (defined in score.cu / sketch.cu)
+int icb_launch_score(icb_readset* rs, int k, const double* tab, const double* tab_nomin);
+int icb_launch_error_rate(icb_readset* rs, const uint8_t* d_qual, const int64_t* d_offs, const int32_t* d_len,
+			  const int32_t* d_status, const double* tab_nomin, double* d_out);
+int icb_launch_sketch(icb_readset* rs, int k, int w, const uint8_t* d_skip);

@@ -1,0 +1,68 @@
+"""ctypes binding of libisonclust2_b200.so (the C ABI declared in include/isonclust2_b200.h).
+
+There is no fallback: if the library is missing or a symbol the header declares is absent, load() raises.
+"""
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisonclust2_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "isonclust2_b200.h")
+
+_lib = None
+_p, _i64, _i32, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+
+
+def header_symbols():
+    """Every function name include/isonclust2_b200.h declares."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(icb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing — build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+                           "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    missing = [s for s in header_symbols() if not hasattr(L, s)]
+    if missing:
+        raise RuntimeError(f"{LIB_PATH} does not export: {missing}")
+    L.icb_device_count.restype = _i32
+    L.icb_ctx_create.argtypes = [_i32, C.POINTER(_p)]
+    L.icb_ctx_destroy.argtypes = [_p]
+    L.icb_ctx_destroy.restype = None
+    L.icb_ctx_sync.argtypes = [_p]
+    L.icb_ctx_stream.argtypes = [_p]
+    L.icb_ctx_stream.restype = _p
+    L.icb_last_error.argtypes = [_p]
+    L.icb_last_error.restype = C.c_char_p
+    L.icb_strerror.argtypes = [_i32]
+    L.icb_strerror.restype = C.c_char_p
+    L.icb_ctx_timing.argtypes = [_p, _i32]
+    L.icb_ctx_timing_reset.argtypes = [_p]
+    L.icb_ctx_kernel_time.argtypes = [_p, C.c_char_p, C.POINTER(_i64), C.POINTER(_dbl)]
+    L.icb_ctx_launch_count.argtypes = [_p]
+    L.icb_ctx_launch_count.restype = _i64
+    L.icb_readset_create.argtypes = [_p, _p, _p, _p, _i64, C.POINTER(_p)]
+    L.icb_readset_destroy.argtypes = [_p]
+    L.icb_readset_destroy.restype = None
+    L.icb_readset_n_reads.argtypes = [_p]
+    L.icb_readset_n_reads.restype = _i64
+    L.icb_readset_n_bases.argtypes = [_p]
+    L.icb_readset_n_bases.restype = _i64
+    L.icb_score_reads.argtypes = [_p, _i32, _p, _p]
+    L.icb_scores_download.argtypes = [_p, _p, _p]
+    L.icb_sketch_reads.argtypes = [_p, _i32, _i32, _p, _p]
+    L.icb_sketch_sizes.argtypes = [_p, C.POINTER(_i64), C.POINTER(_i64)]
+    L.icb_sketch_download.argtypes = [_p] * 10
+    L.icb_init_qual_tab.argtypes = [_p, _i32]
+    L.icb_init_qual_tab.restype = None
+    L.icb_quality_filter.argtypes = [_p, _i64, _dbl, _p]
+    L.icb_sort_by_score.argtypes = [_p, _i64, _p]
+    _lib = L
+    return L

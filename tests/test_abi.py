@@ -1,0 +1,31 @@
+"""CPU: the C-ABI library loads and exports every symbol include/isonclust2_b200.h declares (no compute calls)."""
+import os
+
+from isonclust2_b200 import lib, pemp
+
+
+def test_library_exports_header_symbols():
+    L = lib.load()
+    syms = lib.header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(L, s), s
+
+
+def test_no_cpu_fallback_without_gpu():
+    L = lib.load()
+    if L.icb_device_count() > 0:
+        return
+    import ctypes as C
+    import pytest
+    from isonclust2_b200 import api
+    h = C.c_void_p()
+    assert L.icb_ctx_create(0, C.byref(h)) != 0  # fails loudly, no fallback
+    with pytest.raises(api.IcbError):
+        api.Context(0)
+
+
+def test_pemp_table_shipped():
+    t = pemp.load_p_shared(11, 15)
+    assert t.shape == (15, 15) and (t == t.T).all() and (t > 0).all() and (t < 1).all()
+    assert os.path.getsize(pemp._DATA) == 12 + 41880 * 12
