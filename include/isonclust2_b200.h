@@ -109,6 +109,23 @@ int icb_sketch_download(icb_readset* rs, int32_t* status, int32_t* hpc_len, doub
 			char* hpc_qual, icb_minimizer* mins, int64_t* min_offs, icb_minimizer* rev_mins,
 			int64_t* rev_offs);
 
+/* ------------------------------------------------------------------ stage 3: alignment verification
+ * Replaces, per candidate pair of getBestClusterAln (cluster.cpp:461-515): ParasailAlign (cluster.cpp:408-423,
+ * parasail_sg_trace_scan_16 with the _32 rerun on saturation), parasail_result_get_traceback
+ * (traceback_template.c:13-190) and the window count of getAlnRatio (cluster.cpp:442-459).
+ * read / rep index the read set (raw sequences); strand -1 aligns against RevComp(rep) (cluster.cpp:488-490).
+ * gap_open = setGapOpen(e1+e2) (cluster.cpp:425-440) and limit = floor((1-(e1+e2))*k) (cluster.cpp:446) are
+ * evaluated by the host (doubles); gap extend is 1, match +2, mismatch -2 (cluster.cpp:473-479).
+ * aligned = number of k-column windows of the traceback's comparison string (all but the last one) holding at
+ * least `limit` matches; the caller forms aligned / read_length >= AlignedThreshold (cluster.cpp:458, 503). */
+typedef struct {
+    int32_t read, rep, strand, gap_open, limit;
+} icb_pair;
+typedef struct {
+    int32_t aligned, score, end_query, end_ref, comp_len;
+} icb_align_result;
+int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size, icb_align_result* results);
+
 #ifdef __cplusplus
 }
 #endif

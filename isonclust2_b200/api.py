@@ -13,6 +13,18 @@ import numpy as np
 from . import lib as _lib
 
 MIN_DT = np.dtype([("Min", "<u4"), ("Pos", "<u4"), ("Index", "<u4")])
+PAIR_DT = np.dtype([("read", "<i4"), ("rep", "<i4"), ("strand", "<i4"), ("gap_open", "<i4"), ("limit", "<i4")])
+ALN_DT = np.dtype([("aligned", "<i4"), ("score", "<i4"), ("end_query", "<i4"), ("end_ref", "<i4"), ("comp_len", "<i4")])
+
+
+def set_gap_open(e):
+    """setGapOpen (cluster.cpp:425-440)."""
+    return 5 if e <= 0.01 else 4 if e <= 0.04 else 3 if e <= 0.1 else 2
+
+
+def aln_limit(e, k):
+    """floor((1.0 - e) * kmerSize) of getAlnRatio (cluster.cpp:446), as the integer the device compares with."""
+    return int(max(-1, min(k + 1, math.floor((1.0 - e) * k))))
 
 
 class IcbError(RuntimeError):
@@ -173,6 +185,14 @@ class ReadSet:
                                         mins.ctypes.data, mo.ctypes.data, rmins.ctypes.data, ro.ctypes.data))
         return dict(status=status, hpc_len=hpc_len, hpc_err=hpc_err, hpc_seq=hs, hpc_qual=hq, mins=mins, min_offs=mo,
                     rev_mins=rmins, rev_offs=ro)
+
+    def align_pairs(self, pairs, k):
+        """pairs: PAIR_DT array (indices into this read set).  Returns ALN_DT array."""
+        c = self.ctx
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DT)
+        out = np.zeros(len(pairs), ALN_DT)
+        c.check(c.L.icb_align_pairs(self.h, pairs.ctypes.data, len(pairs), k, out.ctypes.data))
+        return out
 
     def sketch(self, k, w, skip=None, hpc=True):
         self.sketch_async(k, w, skip)

@@ -1,0 +1,456 @@
+// Stage 3 — batched semi-global alignment verification of (read, representative) pairs.
+//
+// Replaces, per pair, ParasailAlign (reference cluster.cpp:408-423 -> parasail_sg_trace_scan_16/_32),
+// parasail_result_get_traceback (vendor/parasail/src/traceback_template.c:13-190) and getAlnRatio's
+// window count (cluster.cpp:442-459).  The arithmetic is parasail's semi-global (all four ends free)
+// affine-gap DP with match +2 / mismatch -2 (anything outside ACGT scores 0, case-insensitive,
+// memory.c:336-413), gap open o in {2..5}, extend 1, its trace-bit tie-breaks (sg_trace.c:137-152), its
+// end-cell rule (sg_trace_scan_avx2_256_16.c:355-395) and its traceback walk.  All DP values are int32,
+// which equals parasail's 16-bit result whenever that does not saturate and its 32-bit rerun otherwise.
+//
+// Design (B200): nothing here is a contraction — integer max/add on the INT pipe (DPX viaddmax / vimax3).
+//   icb_k_align_dp      one warp per pair.  The matrix is cut into strips of 256 query rows; lane t owns 8
+//                       consecutive rows in registers and sweeps the columns one step behind lane t-1
+//                       (systolic wavefront, 3 shuffles per step).  Strip boundary rows live in an
+//                       L2-resident global line.  4 trace bits per cell are accumulated with funnel
+//                       shifts of sign bits and stored as full 32-byte sectors, one per 8x8 cell tile.
+//   icb_k_align_trace   one thread per pair walks the 8x8 tiles back from the end cell, feeding a k-bit
+//                       shift register whose popcount gives the per-window match count.
+// Roofline class: integer ALU (GCUPS); trace traffic is 0.5 B/cell.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "icb_common.cuh"
+
+namespace {
+
+constexpr int AL_WARPS = 4;
+constexpr int AL_THREADS = AL_WARPS * 32;
+constexpr int ROWS = 8;		     // rows per lane
+constexpr int STRIP = 32 * ROWS;     // rows per strip
+constexpr int NEG = -(1 << 29);
+
+struct PairDesc {
+    int64_t q_off, r_off;   // byte offsets of read / representative in the sequence buffer
+    int32_t n, m;	    // lengths (query rows, reference columns)
+    int32_t rc;		    // representative is taken reverse-complemented
+    int32_t open;	    // gap open
+    int32_t limit;	    // window counts if matches >= limit
+    int32_t out;	    // slot in the result array
+    int64_t trace_off;	    // in 32-byte sectors
+    int64_t line_off;	    // in ints: boundary line (2*m), last row (m), last column (n rounded to 8)
+};
+
+// A,C,G,T (either case) -> 0..3, anything else -> 4
+__device__ __forceinline__ int base_code(uint32_t c)
+{
+    c &= 0xdfu;	 // upper-case
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+}
+// upper-cased character of the reference string as parasail sees it (RevComp applied when rc)
+__device__ __forceinline__ uint32_t ref_char(const uint8_t* __restrict__ seq, const PairDesc& d, int j)
+{
+    if (!d.rc) return seq[d.r_off + j];
+    uint32_t c = seq[d.r_off + (d.m - 1 - j)];
+    return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;  // util.cpp:13-38 (ACGT only reaches here)
+}
+
+__device__ __forceinline__ uint32_t up_char(uint32_t c) { return (c >= 'a' && c <= 'z') ? c - 32u : c; }
+
+__device__ __forceinline__ uint32_t shf_in(uint32_t acc, int signsrc)
+{
+    // acc = (acc << 1) | (signsrc < 0)
+    return __funnelshift_l(uint32_t(signsrc), acc, 1);
+}
+
+__global__ void __launch_bounds__(AL_THREADS)
+icb_k_align_dp(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ descs, int n_pairs, uint4* __restrict__ trace,
+	       int* __restrict__ lines, int4* __restrict__ ends /* score, end_query, end_ref, pad */,
+	       unsigned long long* __restrict__ ticket)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+	int p = 0;
+	if (lane == 0) p = int(atomicAdd(ticket, 1ull));
+	p = __shfl_sync(0xffffffffu, p, 0);
+	if (p >= n_pairs) break;
+	const PairDesc d = descs[p];
+	const int n = d.n, m = d.m, o = d.open;
+	int* bound = lines + d.line_off;	   // (H,F) of the strip's bottom row per column
+	int* lastrow = bound + 2 * m;		   // H[n-1][j]
+	int* lastcol = lastrow + m;		   // H[i][m-1]
+	const int ncg = (m + 7) >> 3;
+	uint4* tr = trace + d.trace_off * 2;
+	const int nstrips = (n + STRIP - 1) / STRIP;
+	const int tstar = ((n - 1) % STRIP) / ROWS, rstar = (n - 1) % ROWS;
+
+	for (int strip = 0; strip < nstrips; strip++) {
+	    const int i0 = strip * STRIP + lane * ROWS;	 // first row of this lane
+	    const bool lastStrip = strip == nstrips - 1;
+	    int a[ROWS];
+	    uint32_t qother = 0;
+#pragma unroll
+	    for (int r = 0; r < ROWS; r++) {
+		int c = (i0 + r < n) ? base_code(seq[d.q_off + i0 + r]) : 4;
+		a[r] = c;
+		qother |= uint32_t(c > 3) << r;
+	    }
+	    int Hl[ROWS], El[ROWS];
+	    uint32_t T[ROWS];
+#pragma unroll
+	    for (int r = 0; r < ROWS; r++) {
+		Hl[r] = 0;
+		El[r] = NEG;
+		T[r] = 0;
+	    }
+	    int hup_prev = 0;		      // H[i0-1][j-1]
+	    int hb = 0, fb = NEG;	      // this lane's bottom-row (H,F) of its previous column
+	    int bcode = 0;		      // this lane's previous column's reference code
+	    int pre_h = 0, pre_f = NEG, pre_b = 0;  // lane l holds column s0+l of the top boundary / reference
+	    const int rowgroup = strip * 32 + lane;
+	    const int nsteps = m + 31;
+	    for (int s = 0; s < nsteps; s++) {
+		if ((s & 31) == 0) {
+		    int jj = s + lane;
+		    if (jj < m) {
+			pre_b = base_code(ref_char(seq, d, jj));
+			if (strip > 0) {
+			    pre_h = bound[2 * jj];
+			    pre_f = bound[2 * jj + 1];
+			}
+		    }
+		}
+		// inputs of this step: from the lane above (its previous step), lane 0 from the boundary line
+		int hup = __shfl_up_sync(0xffffffffu, hb, 1);
+		int fup = __shfl_up_sync(0xffffffffu, fb, 1);
+		int b = __shfl_up_sync(0xffffffffu, bcode, 1);
+		int h0 = __shfl_sync(0xffffffffu, pre_h, s & 31);
+		int f0 = __shfl_sync(0xffffffffu, pre_f, s & 31);
+		int b0 = __shfl_sync(0xffffffffu, pre_b, s & 31);
+		if (lane == 0) {
+		    hup = h0;
+		    fup = f0;
+		    b = b0;
+		}
+		const int j = s - lane;
+		if (j >= 0 && j < m) {
+		    int hdiag = hup_prev;
+		    hup_prev = hup;
+		    const int mat = b > 3 ? 0 : 2, mis = b > 3 ? 0 : -2;
+		    if (qother == 0) {
+#pragma unroll
+			for (int r = 0; r < ROWS; r++) {
+			    int f_ext = fup - 1;
+			    int F = __viaddmax_s32(hup, -o, f_ext);
+			    int e_ext = El[r] - 1;
+			    int E = __viaddmax_s32(Hl[r], -o, e_ext);
+			    int dd = hdiag + (a[r] == b ? mat : mis);
+			    int H = __vimax3_s32(dd, E, F);
+			    uint32_t t = T[r];
+			    t = shf_in(t, dd - H);	  // 1: H != diagonal
+			    t = shf_in(t, F - H);	  // 1: H != F
+			    t = shf_in(t, e_ext - E);	  // 1: E opened here (DIAG_E)
+			    t = shf_in(t, f_ext - F);	  // 1: F opened here (DIAG_F)
+			    T[r] = t;
+			    hdiag = Hl[r];
+			    Hl[r] = H;
+			    El[r] = E;
+			    hup = H;
+			    fup = F;
+			}
+		    }
+		    else {
+#pragma unroll
+			for (int r = 0; r < ROWS; r++) {
+			    int f_ext = fup - 1;
+			    int F = __viaddmax_s32(hup, -o, f_ext);
+			    int e_ext = El[r] - 1;
+			    int E = __viaddmax_s32(Hl[r], -o, e_ext);
+			    int sc = (a[r] > 3) ? 0 : (a[r] == b ? mat : mis);
+			    int dd = hdiag + sc;
+			    int H = __vimax3_s32(dd, E, F);
+			    uint32_t t = T[r];
+			    t = shf_in(t, dd - H);
+			    t = shf_in(t, F - H);
+			    t = shf_in(t, e_ext - E);
+			    t = shf_in(t, f_ext - F);
+			    T[r] = t;
+			    hdiag = Hl[r];
+			    Hl[r] = H;
+			    El[r] = E;
+			    hup = H;
+			    fup = F;
+			}
+		    }
+		    hb = hup;
+		    fb = fup;
+		    bcode = b;
+		    if (lane == 31 && !lastStrip) {
+			bound[2 * j] = hb;
+			bound[2 * j + 1] = fb;
+		    }
+		    if (lastStrip && lane == tstar) {
+			int hsel = Hl[0];
+#pragma unroll
+			for (int r = 1; r < ROWS; r++) hsel = (r == rstar) ? Hl[r] : hsel;
+			lastrow[j] = hsel;
+		    }
+		    if (j == m - 1) {
+#pragma unroll
+			for (int r = 0; r < ROWS; r++)
+			    if (i0 + r < n) lastcol[i0 + r] = Hl[r];
+		    }
+		    if (((j & 7) == 7 || j == m - 1) && i0 < n) {
+			const int sh = 4 * (7 - (j & 7));
+			uint4* dst = tr + (int64_t(rowgroup) * ncg + (j >> 3)) * 2;
+			dst[0] = make_uint4(T[0] << sh, T[1] << sh, T[2] << sh, T[3] << sh);
+			dst[1] = make_uint4(T[4] << sh, T[5] << sh, T[6] << sh, T[7] << sh);
+		    }
+		}
+	    }
+	    __syncwarp();
+	}
+	// ---- end cell (sg_trace_scan_avx2_256_16.c:355-395): first maximum of the last row, then the last
+	// column: strictly larger wins, the smallest row among equals; a tie with the row maximum only moves
+	// the end if that maximum sits in the corner.
+	__syncwarp();
+	int best = NEG * 2, bj = m - 1;
+	for (int j = lane; j < m; j += 32) {
+	    int v = lastrow[j];
+	    if (v > best) {
+		best = v;
+		bj = j;
+	    }
+	}
+#pragma unroll
+	for (int dlt = 16; dlt; dlt >>= 1) {
+	    int ov = __shfl_xor_sync(0xffffffffu, best, dlt), oj = __shfl_xor_sync(0xffffffffu, bj, dlt);
+	    if (ov > best || (ov == best && oj < bj)) {
+		best = ov;
+		bj = oj;
+	    }
+	}
+	int cbest = NEG * 2, ci = n - 1;
+	for (int i = lane; i < n; i += 32) {
+	    int v = lastcol[i];
+	    if (v > cbest) {
+		cbest = v;
+		ci = i;
+	    }
+	}
+#pragma unroll
+	for (int dlt = 16; dlt; dlt >>= 1) {
+	    int ov = __shfl_xor_sync(0xffffffffu, cbest, dlt), oi = __shfl_xor_sync(0xffffffffu, ci, dlt);
+	    if (ov > cbest || (ov == cbest && oi < ci)) {
+		cbest = ov;
+		ci = oi;
+	    }
+	}
+	if (lane == 0) {
+	    int score = best, ei = n - 1, ej = bj;
+	    if (cbest > best || (cbest == best && bj == m - 1)) {
+		score = cbest;
+		ei = ci;
+		ej = m - 1;
+	    }
+	    ends[d.out] = make_int4(score, ei, ej, 0);
+	}
+    }
+}
+
+struct TraceState {
+    uint32_t reg, mask;
+    int k, limit;
+    long long pushed;
+    int aligned;
+    __device__ __forceinline__ void push(uint32_t bit)
+    {
+	reg = ((reg << 1) | bit) & mask;
+	// windows are counted from the (k+1)-th pushed column on: the reference never tests the last window
+	if (pushed >= k && __popc(reg) >= limit) aligned++;
+	pushed++;
+    }
+    __device__ void push_zeros(long long g)
+    {
+	long long first = g < k ? g : k;
+	for (long long t = 0; t < first; t++) push(0);
+	long long rest = g - first;
+	if (rest > 0) {
+	    // register is all zero now; every further column closes an all-blank window
+	    long long counted = rest;
+	    if (pushed < k) counted -= (k - pushed);
+	    if (counted > 0 && 0 >= limit) aligned += int(counted);
+	    pushed += rest;
+	}
+    }
+};
+
+__global__ void __launch_bounds__(64)
+icb_k_align_trace(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ descs, int n_pairs, const uint4* __restrict__ trace,
+		  const int4* __restrict__ ends, int k, icb_align_result* __restrict__ out)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const PairDesc d = descs[p];
+    const int n = d.n, m = d.m;
+    const int4 e = ends[d.out];
+    const int ncg = (m + 7) >> 3;
+    const uint4* tr = trace + d.trace_off * 2;
+    TraceState st;
+    st.reg = 0;
+    st.mask = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+    st.k = k;
+    st.limit = d.limit;
+    st.pushed = 0;
+    st.aligned = 0;
+    int i = e.y, j = e.z;
+    // free tail (traceback_template.c:72-94)
+    if (i + 1 == n) st.push_zeros(m - 1 - j);
+    else st.push_zeros(n - 1 - i);
+    int where = 0;  // 0 diag, 1 ins (consumes reference), 2 del (consumes query)
+    long long tile = -1;
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    while (i >= 0 || j >= 0) {
+	if (i < 0) {
+	    st.push_zeros(j + 1);
+	    break;
+	}
+	if (j < 0) {
+	    st.push_zeros(i + 1);
+	    break;
+	}
+	long long t = (long long)(i >> 3) * ncg + (j >> 3);
+	if (t != tile) {
+	    uint4 x = tr[t * 2], y = tr[t * 2 + 1];
+	    w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+	    w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+	    tile = t;
+	}
+	uint32_t word = w[0];
+#pragma unroll
+	for (int r = 1; r < 8; r++) word = ((i & 7) == r) ? w[r] : word;
+	uint32_t nib = (word >> (4 * (7 - (j & 7)))) & 15u;
+	// nib bits: 8 = H != diagonal, 4 = H != F, 2 = DIAG_E, 1 = DIAG_F
+	if (where == 0) {
+	    if (!(nib & 8u)) {
+		uint32_t a = up_char(seq[d.q_off + i]), b = up_char(ref_char(seq, d, j));  // traceback.c match_char, case-insensitive
+		st.push(a == b ? 1u : 0u);
+		i--;
+		j--;
+	    }
+	    else if (nib & 4u) where = 1;  // neither diagonal nor F: INS (traceback_template.c:118-120)
+	    else where = 2;
+	}
+	else if (where == 1) {
+	    st.push(0);
+	    j--;
+	    where = (nib & 2u) ? 0 : 1;
+	}
+	else {
+	    st.push(0);
+	    i--;
+	    where = (nib & 1u) ? 0 : 2;
+	}
+    }
+    icb_align_result r;
+    r.aligned = st.pushed >= k ? st.aligned : 0;
+    r.score = e.x;
+    r.end_query = e.y;
+    r.end_ref = e.z;
+    r.comp_len = int(st.pushed);
+    out[d.out] = r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size, icb_align_result* results)
+{
+    if (!rs || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results))) return ICB_ERR_ARG;
+    icb_ctx* ctx = rs->ctx;
+    if (kmer_size < 1 || kmer_size > 32) return ctx->fail(ICB_ERR_ARG, "kmer_size must be in [1,32]");
+    if (n_pairs == 0) return ICB_OK;
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // descriptors, largest matrices first (longest-processing-time order over the persistent warps)
+    std::vector<PairDesc> descs(n_pairs);
+    const int64_t budget_sectors = (int64_t(6) << 30) / 32;  // trace arena per launch: 6 GiB
+    std::vector<int64_t> order(n_pairs);
+    std::iota(order.begin(), order.end(), 0);
+    for (int64_t p = 0; p < n_pairs; p++) {
+	const icb_pair& q = pairs[p];
+	if (q.read < 0 || q.read >= rs->n_reads || q.rep < 0 || q.rep >= rs->n_reads)
+	    return ctx->fail(ICB_ERR_ARG, "pair index outside the read set");
+	PairDesc& d = descs[p];
+	d.q_off = rs->h_offs[q.read];
+	d.r_off = rs->h_offs[q.rep];
+	d.n = int32_t(rs->h_offs[q.read + 1] - rs->h_offs[q.read]);
+	d.m = int32_t(rs->h_offs[q.rep + 1] - rs->h_offs[q.rep]);
+	if (d.n < 1 || d.m < 1) return ctx->fail(ICB_ERR_ARG, "empty sequence in an alignment pair");
+	d.rc = q.strand == -1;
+	d.open = q.gap_open;
+	d.limit = q.limit;
+	d.out = int32_t(p);
+    }
+    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+	return int64_t(descs[x].n) * descs[x].m > int64_t(descs[y].n) * descs[y].m;
+    });
+    int64_t done = 0;
+    while (done < n_pairs) {
+	// take as many pairs as fit the trace budget
+	int64_t sectors = 0, ints = 0, cnt = 0;
+	std::vector<PairDesc> batch;
+	while (done + cnt < n_pairs) {
+	    PairDesc d = descs[order[done + cnt]];
+	    int64_t s = int64_t((d.n + 7) / 8) * ((d.m + 7) / 8);
+	    if (cnt > 0 && sectors + s > budget_sectors) break;
+	    d.trace_off = sectors;
+	    d.line_off = ints;
+	    sectors += s;
+	    ints += 3 * int64_t(d.m) + ((d.n + 7) & ~7) + 8;
+	    batch.push_back(d);
+	    cnt++;
+	}
+	uint4* d_trace = nullptr;
+	int* d_lines = nullptr;
+	int4* d_ends = nullptr;
+	PairDesc* d_descs = nullptr;
+	icb_align_result* d_out = nullptr;
+	unsigned long long* d_ticket = nullptr;
+	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_trace, size_t(sectors) * 32 + 64, st));
+	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_lines, size_t(ints) * 4 + 64, st));
+	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_ends, sizeof(int4) * n_pairs, st));
+	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_descs, sizeof(PairDesc) * cnt, st));
+	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_out, sizeof(icb_align_result) * n_pairs, st));
+	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_ticket, 8, st));
+	ICB_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, 8, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_descs, batch.data(), sizeof(PairDesc) * cnt, cudaMemcpyHostToDevice, st));
+	int64_t warps = cnt;
+	int64_t maxw = int64_t(ctx->sm_count) * 16;
+	if (warps > maxw) warps = maxw;
+	unsigned grid = unsigned((warps + AL_WARPS - 1) / AL_WARPS);
+	ICB_LAUNCH(ctx, "align_dp",
+		   icb_k_align_dp<<<grid, AL_THREADS, 0, st>>>(rs->d_seq, d_descs, int(cnt), d_trace, d_lines, d_ends, d_ticket));
+	ICB_LAUNCH(ctx, "align_trace",
+		   icb_k_align_trace<<<unsigned((cnt + 63) / 64), 64, 0, st>>>(rs->d_seq, d_descs, int(cnt), d_trace, d_ends,
+									      kmer_size, d_out));
+	// results are indexed by the caller's pair index (d.out); copy the touched range pair by pair is wasteful,
+	// so stage the whole array once per launch and pick this launch's slots
+	std::vector<icb_align_result> tmp(n_pairs);
+	ICB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_out, sizeof(icb_align_result) * n_pairs, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+	for (auto& d : batch) results[d.out] = tmp[d.out];
+	ICB_CUDA(ctx, cudaFreeAsync(d_trace, st));
+	ICB_CUDA(ctx, cudaFreeAsync(d_lines, st));
+	ICB_CUDA(ctx, cudaFreeAsync(d_ends, st));
+	ICB_CUDA(ctx, cudaFreeAsync(d_descs, st));
+	ICB_CUDA(ctx, cudaFreeAsync(d_out, st));
+	ICB_CUDA(ctx, cudaFreeAsync(d_ticket, st));
+	done += cnt;
+    }
+    return ICB_OK;
+}
+
+}  // extern "C"
