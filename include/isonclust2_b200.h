@@ -126,6 +126,46 @@ typedef struct {
 } icb_align_result;
 int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size, icb_align_result* results);
 
+/* ------------------------------------------------------------------ stage 2 + the greedy loop: clustering
+ * Replaces ClusterSortedReads for an initial clustering (cluster.cpp:67-322 with consensus off, the default):
+ * per read getBestCluster (cluster.cpp:530-568) = GetMinimizerHits (minimizer.cpp:44-76) + SortMinimizerHits
+ * (cluster.cpp:622-636) + getBestClusterMapping / getMappedRatio (cluster.cpp:324-406) + getBestClusterAln
+ * (cluster.cpp:461-515), then AddMinimizers (minimizer.cpp:31-42) for a new cluster.  The device keeps the
+ * minimizer -> cluster index and scores chunks of reads against it; the host walks the reads in order.
+ *
+ * p_shared: the 15x15 grid InitMinSharedMap(k, w) builds (p_emp_prob.cpp:22-47), index [c1*15+c2] with error class
+ * c = round(e*100)-1 (0.01..0.15); NaN = no row (-> ICB_ERR_NO_PEMP, where the reference throws).  It ships as
+ * isonclust2_b200/data/p_emp_prob.bin.  The other fields are CmdArgs' (args.h:9-37). */
+typedef struct {
+    int32_t kmer_size, window_size;
+    int32_t mode; /* 0 sahlin, 1 fast, 2 furious (args.h:7) */
+    int32_t min_shared;
+    double mapped_threshold, aligned_threshold, min_fraction, min_prob_no_hits, min_qual;
+    double p_shared[225];
+    int32_t chunk_size; /* reads scored per device round trip; 0 = default */
+} icb_cluster_params;
+
+typedef struct {
+    int64_t chunks, rounds, reads_queried;
+    int64_t aln_invoked;   /* the reference's ALN_INVOKED counter (cluster.cpp:21, 563) */
+    int64_t pairs_aligned; /* DP problems solved (>= what the reference solves: speculative pairs included) */
+    int64_t cells_aligned;
+    int64_t tie_fallbacks; /* reads whose outcome depended on the reference's candidate order */
+} icb_cluster_stats;
+
+typedef struct icb_clusterer icb_clusterer;
+/* rs must be scored and sketched with the same k / w */
+int icb_clusterer_create(icb_readset* rs, const icb_cluster_params* params, icb_clusterer** cl);
+void icb_clusterer_destroy(icb_clusterer* cl);
+/* order[n]: read ids in sorted (greedy) order.  cluster_of[slot] = cluster the read of that slot ends in (a founder
+ * gets the id of the cluster it founds), -1 if the read is skipped (cluster.cpp:116-160); strand_of[slot] = +1 / -1
+ * (MatchStrand after cluster.cpp:235-246), 0 if skipped.  May be called repeatedly; later calls continue on the
+ * clusters founded so far. */
+int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_t* cluster_of, int32_t* strand_of);
+int64_t icb_clusterer_n_clusters(const icb_clusterer* cl);
+int icb_clusterer_founders(const icb_clusterer* cl, int32_t* founder_read);
+int icb_clusterer_stats(const icb_clusterer* cl, icb_cluster_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,66 @@ def sort_by_qual_scores(score):
     return order
 
 
+class ClusterParams(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("window_size", C.c_int32), ("mode", C.c_int32), ("min_shared", C.c_int32),
+                ("mapped_threshold", C.c_double), ("aligned_threshold", C.c_double), ("min_fraction", C.c_double),
+                ("min_prob_no_hits", C.c_double), ("min_qual", C.c_double), ("p_shared", C.c_double * 225),
+                ("chunk_size", C.c_int32)]
+
+
+class ClusterStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("chunks", "rounds", "reads_queried", "aln_invoked", "pairs_aligned", "cells_aligned",
+                                         "tie_fallbacks")]
+
+
+MODES = {"sahlin": 0, "fast": 1, "furious": 2}
+
+
+class Clusterer:
+    """ClusterSortedReads (cluster.cpp:67-322) for an initial clustering; CmdArgs defaults of args.h:13-28."""
+
+    def __init__(self, rs, k, w, mode="sahlin", min_shared=5, mapped_threshold=0.65, aligned_threshold=0.2, min_fraction=0.8,
+                 min_prob_no_hits=0.1, min_qual=7.0, chunk_size=0, p_shared=None):
+        from . import pemp
+        self.rs = rs
+        c = rs.ctx
+        P = ClusterParams(kmer_size=k, window_size=w, mode=MODES.get(mode, mode), min_shared=min_shared,
+                          mapped_threshold=mapped_threshold, aligned_threshold=aligned_threshold, min_fraction=min_fraction,
+                          min_prob_no_hits=min_prob_no_hits, min_qual=min_qual, chunk_size=chunk_size)
+        ps = np.ascontiguousarray(pemp.load_p_shared(k, w) if p_shared is None else p_shared, dtype=np.float64).reshape(225)
+        for i in range(225):
+            P.p_shared[i] = ps[i]
+        h = C.c_void_p()
+        c.check(c.L.icb_clusterer_create(rs.h, C.byref(P), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.rs.ctx.L.icb_clusterer_destroy(self.h)
+            self.h = None
+
+    def cluster(self, order):
+        c = self.rs.ctx
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        cl, st = np.empty(len(order), np.int32), np.empty(len(order), np.int32)
+        c.check(c.L.icb_cluster_reads(self.h, order.ctypes.data, len(order), cl.ctypes.data, st.ctypes.data))
+        return cl, st
+
+    @property
+    def n_clusters(self):
+        return self.rs.ctx.L.icb_clusterer_n_clusters(self.h)
+
+    def founders(self):
+        f = np.empty(self.n_clusters, np.int32)
+        self.rs.ctx.check(self.rs.ctx.L.icb_clusterer_founders(self.h, f.ctypes.data))
+        return f
+
+    def stats(self):
+        s = ClusterStats()
+        self.rs.ctx.check(self.rs.ctx.L.icb_clusterer_stats(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in ClusterStats._fields_}
+
+
 class Context:
     def __init__(self, device=0):
         self.L = _lib.load()

@@ -1,0 +1,638 @@
+// The greedy, order-dependent assignment loop (host) on top of the stage-2 and stage-3 kernels.
+//
+// Mirrors ClusterSortedReads (reference cluster.cpp:67-322, consensus off — the default, args.h:19) and
+// getBestCluster / getBestClusterMapping / getBestClusterAln (cluster.cpp:355-406, 461-515, 530-568).  The
+// host keeps exactly what is sequential in the reference: walking the sorted reads in order, deciding
+// join-or-found, and — for the rare reads where two equally scored candidates both pass — the candidate
+// ORDER, which the reference defines through libstdc++ (iteration order of an unordered_map with
+// StrandedClsHash and 20*(|mins|+|revMins|) buckets, minimizer.cpp:48, minimizer.h:53-58, followed by an
+// unstable std::sort, cluster.cpp:622-636); the same two library facilities are used here on the device's
+// (cluster, strand, count, first-hit) records.  Everything data-parallel — hit counting, mapped lengths,
+// alignments — is computed on the device per CHUNK of reads, speculatively where the sequential dependency
+// demands it (see index.cu), and consumed here in order.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+
+#include "index.cuh"
+
+namespace {
+
+struct PairHash {  // minimizer.h:53-58 StrandedClsHash
+    std::size_t operator()(const std::pair<int, int>& u) const { return std::size_t(int(u.first * u.second)); }
+};
+struct SortedCand {
+    unsigned Size;
+    unsigned Cls;
+    int Strand;
+};
+
+struct AlnKey {
+    int pos, id, strand;
+    bool operator<(const AlnKey& o) const
+    {
+	if (pos != o.pos) return pos < o.pos;
+	if (id != o.id) return id < o.id;
+	return strand < o.strand;
+    }
+};
+
+enum Outcome { OUT_JOIN, OUT_NEW, OUT_NEED };
+
+}  // namespace
+
+struct icb_clusterer {
+    icb_ctx* ctx = nullptr;
+    icb_readset* rs = nullptr;
+    icb_cluster_params P{};
+    int32_t nmax[225];
+    // host copies of per-read scalars
+    std::vector<int32_t> status, hpc_len, nf, nr;
+    std::vector<double> score, raw_err;
+    // clusters
+    std::vector<int32_t> founder;  // cluster id -> founder read
+    // device state
+    IcbIndex main_idx, chunk_idx;
+    uint8_t* d_class = nullptr;
+    int32_t* d_nmax = nullptr;
+    int32_t* d_cls_founder = nullptr;
+    int64_t cls_founder_cap = 0;
+    int32_t* d_chunk_reads = nullptr;
+    int32_t* d_list = nullptr;
+    int32_t* d_ids = nullptr;
+    IcbQueryHeader* d_hdr = nullptr;
+    IcbCand* d_cands = nullptr;
+    int64_t cands_cap = 0;
+    int64_t* d_full_off = nullptr;
+    uint32_t* d_scratch = nullptr;
+    int64_t scratch_words = 0;
+    int chunk_cap = 0;
+    int max_m = 0;
+    icb_cluster_stats stats{};
+
+    int ensure_scratch(int64_t words);
+    int ensure_cands(int64_t n);
+    int query(const std::vector<int32_t>& chunk, int C0, const std::vector<int32_t>* list, int mode, int cap,
+	      std::vector<IcbQueryHeader>& hdr, std::vector<IcbCand>& cands, std::vector<int64_t>* full_off);
+    int process_chunk(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of, int32_t* strand_of);
+};
+
+int icb_clusterer::ensure_scratch(int64_t words)
+{
+    if (words <= scratch_words) return ICB_OK;
+    cudaFree(d_scratch);
+    d_scratch = nullptr;
+    scratch_words = 0;
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_scratch, size_t(words) * 4));
+    scratch_words = words;
+    return ICB_OK;
+}
+
+int icb_clusterer::ensure_cands(int64_t n)
+{
+    if (n <= cands_cap) return ICB_OK;
+    cudaFree(d_cands);
+    d_cands = nullptr;
+    cands_cap = 0;
+    int64_t want = std::max<int64_t>(n, 1 << 16);
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_cands, size_t(want) * sizeof(IcbCand)));
+    cands_cap = want;
+    return ICB_OK;
+}
+
+// one query launch over (a subset of) the chunk; results copied to the host
+int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::vector<int32_t>* list, int mode, int cap,
+			 std::vector<IcbQueryHeader>& hdr, std::vector<IcbCand>& cands, std::vector<int64_t>* full_off)
+{
+    cudaStream_t st = ctx->stream;
+    const int n_chunk = int(chunk.size());
+    const int n_items = list ? int(list->size()) : n_chunk;
+    if (n_items == 0) return ICB_OK;
+    const int Ctot = C0 + n_chunk;
+    IcbQueryArgs a{};
+    a.arena = rs->d_mins;
+    a.min_off = rs->d_min_off;
+    a.nf = rs->d_nf;
+    a.nr = rs->d_nr;
+    a.hpc_len = rs->d_hpc_len;
+    a.read_class = d_class;
+    a.chunk_reads = d_chunk_reads;
+    a.n_chunk = n_chunk;
+    a.list = nullptr;
+    a.n_list = 0;
+    if (list) {
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_list, list->data(), sizeof(int32_t) * n_items, cudaMemcpyHostToDevice, st));
+	a.list = d_list;
+	a.n_list = n_items;
+    }
+    a.main_idx = main_idx.v;
+    a.chunk_idx = chunk_idx.v;
+    a.C0 = C0;
+    a.cls_founder = d_cls_founder;
+    a.nmax = d_nmax;
+    a.min_shared = P.min_shared;
+    a.min_frac = P.min_fraction;
+    a.cap = cap;
+    a.mode = mode;
+    a.hdr = d_hdr;
+    a.full_off = nullptr;
+    int64_t n_records;
+    std::vector<int64_t> foff;
+    if (mode == 1) {
+	foff.resize(n_items + 1);
+	for (int i = 0; i <= n_items; i++) foff[i] = int64_t(i) * 2 * Ctot;
+	n_records = foff[n_items];
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_full_off, foff.data(), sizeof(int64_t) * n_items, cudaMemcpyHostToDevice, st));
+	a.full_off = d_full_off;
+    }
+    else
+	n_records = int64_t(n_items) * cap;
+    int rc = ensure_cands(n_records);
+    if (rc) return rc;
+    a.cands = d_cands;
+    // shared memory plan: dense counters (Ctot words) + candidate list (2*cap) + bitmaps
+    const int bw = (max_m + 31) / 32;
+    const int bmWords = std::max(bw, 1024);
+    int64_t words_smem = int64_t(Ctot) + 2 * cap + bmWords;
+    const int64_t smem_limit_words = (200 * 1024) / 4;
+    int n_blocks = std::min(n_items, ctx->sm_count * 8);
+    a.smem_cnt = words_smem <= smem_limit_words;
+    int64_t stride = 0;
+    if (!a.smem_cnt) {
+	words_smem = 2 * cap + bmWords;
+	stride += Ctot;
+    }
+    if (mode == 1) stride += 2 * int64_t(Ctot);
+    if (words_smem > smem_limit_words) return ctx->fail(ICB_ERR_ARG, "a read has too many minimizers for the candidate query");
+    a.smem_words = int32_t(words_smem);
+    a.g_stride = stride;
+    a.g_scratch = nullptr;
+    if (stride > 0) {
+	rc = ensure_scratch(stride * n_blocks);
+	if (rc) return rc;
+	a.g_scratch = d_scratch;
+    }
+    rc = icb_query_launch(ctx, a, n_blocks, size_t(words_smem) * 4);
+    if (rc) return rc;
+    hdr.resize(n_items);
+    ICB_CUDA(ctx, cudaMemcpyAsync(hdr.data(), d_hdr, sizeof(IcbQueryHeader) * n_items, cudaMemcpyDeviceToHost, st));
+    cands.resize(n_records);
+    ICB_CUDA(ctx, cudaMemcpyAsync(cands.data(), d_cands, sizeof(IcbCand) * n_records, cudaMemcpyDeviceToHost, st));
+    ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (full_off) *full_off = foff;
+    return ICB_OK;
+}
+
+int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of,
+				 int32_t* strand_of)
+{
+    cudaStream_t st = ctx->stream;
+    const int N = int(chunk.size());
+    const int C0 = int(founder.size());
+    const int k = P.kmer_size;
+    const int CAP = 64;
+    stats.chunks++;
+    // ---- chunk index: every read of the chunk as a provisional founder (id = C0 + position)
+    ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, chunk.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    {
+	std::vector<int32_t> ids(N);
+	int64_t tot = 0;
+	for (int i = 0; i < N; i++) {
+	    ids[i] = C0 + i;
+	    tot += nf[chunk[i]];
+	}
+	int rc = chunk_idx.clear();
+	if (rc) return rc;
+	rc = chunk_idx.reserve(tot);
+	if (rc) return rc;
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, ids.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+	rc = icb_index_insert(ctx, chunk_idx, rs, d_chunk_reads, d_ids, N);
+	if (rc) return rc;
+	chunk_idx.nodes_upper = tot;
+    }
+    // ---- candidates of every read against snapshot + provisional founders
+    std::vector<IcbQueryHeader> hdr;
+    std::vector<IcbCand> cands;
+    int rc = query(chunk, C0, nullptr, 0, CAP, hdr, cands, nullptr);
+    if (rc) return rc;
+    stats.reads_queried += N;
+    // per-read candidate lists (reads whose list overflowed are re-queried with room for every key)
+    std::vector<std::vector<IcbCand>> cl(N);
+    std::vector<int32_t> over;
+    for (int i = 0; i < N; i++) {
+	if (hdr[i].overflow) over.push_back(i);
+	else cl[i].assign(cands.begin() + int64_t(i) * CAP, cands.begin() + int64_t(i) * CAP + hdr[i].n_cand);
+    }
+    if (!over.empty()) {
+	std::vector<IcbQueryHeader> h2;
+	std::vector<IcbCand> c2;
+	const int cap2 = 2 * (C0 + N);
+	rc = query(chunk, C0, &over, 0, cap2, h2, c2, nullptr);
+	if (rc) return rc;
+	for (size_t t = 0; t < over.size(); t++)
+	    cl[over[t]].assign(c2.begin() + int64_t(t) * cap2, c2.begin() + int64_t(t) * cap2 + h2[t].n_cand);
+    }
+
+    std::vector<int> founder_cls(N, -1);  // provisional founder -> real cluster id once committed
+    std::vector<char> committed(N, 0);
+    std::map<AlnKey, int> aln;		   // alignment results (aligned window count)
+    std::map<int, std::vector<IcbCand>> full;  // full candidate lists for tie reads
+    int nextCls = C0;
+    int commit_pos = 0;
+
+    auto real_id = [&](int id) { return id < C0 ? id : founder_cls[id - C0]; };
+    auto rep_read = [&](int id) { return id < C0 ? founder[id] : chunk[id - C0]; };
+
+    // exact candidate order of the reference for one read, restricted to real clusters
+    auto reference_order = [&](int pos, const std::vector<IcbCand>& all) {
+	std::vector<IcbCand> v;
+	for (auto& c : all) {
+	    int rid = real_id(c.id);
+	    if (rid < 0) continue;
+	    IcbCand d = c;
+	    d.id = rid;
+	    v.push_back(d);
+	}
+	// insertion order of GetMinimizerHits: forward strand first, keys by (first hit rank, cluster id)
+	std::sort(v.begin(), v.end(), [](const IcbCand& a, const IcbCand& b) {
+	    if (a.strand != b.strand) return a.strand > b.strand;
+	    if (a.tmapped != b.tmapped) return a.tmapped < b.tmapped;
+	    return a.id < b.id;
+	});
+	const int r = chunk[pos];
+	std::unordered_map<std::pair<int, int>, unsigned, PairHash> m(20 * (size_t(nf[r]) + size_t(nr[r])));
+	for (auto& c : v) m[std::make_pair(c.id, c.strand)] = unsigned(c.count);
+	std::vector<SortedCand> order;
+	order.reserve(m.size());
+	for (auto& kv : m) order.push_back(SortedCand{kv.second, unsigned(kv.first.first), kv.first.second});
+	std::sort(order.begin(), order.end(), [](const SortedCand& a, const SortedCand& b) { return a.Size > b.Size; });
+	return order;
+    };
+
+    // decision for the read at `pos` given the founders committed so far.  Returns OUT_NEED when device work is
+    // missing (alignment pairs appended to needPairs, tie reads to needFull).
+    auto decide = [&](int pos, int& outCls, int& outStrand, std::vector<AlnKey>& needPairs, std::vector<int32_t>& needFull,
+		      bool countStats) -> Outcome {
+	const int r = chunk[pos];
+	std::vector<IcbCand> v;
+	int top = hdr[pos].top_snap;
+	for (auto& c : cl[pos]) {
+	    if (c.id >= C0 && founder_cls[c.id - C0] < 0) continue;  // provisional founder that is no founder (yet)
+	    v.push_back(c);
+	    top = std::max(top, c.count);
+	}
+	outCls = -1;
+	outStrand = 0;
+	if (top == 0) return OUT_NEW;  // no hits at all (cluster.cpp:541-543)
+	const bool mappingMode = P.mode == 0 || P.mode == 1;
+	if (mappingMode && !(unsigned(top) < unsigned(P.min_shared))) {
+	    const int thr = int(double(unsigned(top)) * P.min_fraction);  // cluster.cpp:387
+	    // groups of equal count, best first
+	    std::vector<IcbCand> cs;
+	    for (auto& c : v)
+		if (!(c.count < thr)) cs.push_back(c);
+	    std::sort(cs.begin(), cs.end(), [](const IcbCand& a, const IcbCand& b) { return a.count > b.count; });
+	    size_t g = 0;
+	    while (g < cs.size()) {
+		size_t e = g;
+		std::vector<const IcbCand*> pass;
+		while (e < cs.size() && cs[e].count == cs[g].count) {
+		    float mr = float(double(cs[e].tmapped) / double(size_t(hpc_len[r])));  // cluster.cpp:351,390
+		    if (mr >= P.mapped_threshold) pass.push_back(&cs[e]);
+		    e++;
+		}
+		if (pass.size() == 1) {
+		    outCls = real_id(pass[0]->id);
+		    outStrand = pass[0]->strand;
+		    return OUT_JOIN;
+		}
+		if (pass.size() > 1) {
+		    // several equally scored candidates pass: the reference takes the first in ITS order
+		    auto it = full.find(pos);
+		    if (it == full.end()) {
+			needFull.push_back(pos);
+			return OUT_NEED;
+		    }
+		    if (countStats) stats.tie_fallbacks++;
+		    auto order = reference_order(pos, it->second);
+		    for (auto& o : order) {
+			for (auto* p : pass)
+			    if (unsigned(real_id(p->id)) == o.Cls && p->strand == o.Strand) {
+				outCls = int(o.Cls);
+				outStrand = o.Strand;
+				return OUT_JOIN;
+			    }
+		    }
+		    return OUT_NEW;  // unreachable
+		}
+		g = e;
+	    }
+	}
+	if (unsigned(top) < unsigned(P.min_shared)) return OUT_NEW;  // cluster.cpp:553-556
+	if (P.mode == 1) return OUT_NEW;			      // fast: minimizers only
+	// getBestClusterAln: candidates tied with the top count, in order, first passing wins
+	std::vector<const IcbCand*> tied;
+	for (auto& c : v)
+	    if (c.count == top) tied.push_back(&c);
+	bool missing = false;
+	for (auto* c : tied) {
+	    AlnKey key{pos, c->id, c->strand};
+	    if (aln.find(key) == aln.end()) {
+		needPairs.push_back(key);
+		missing = true;
+	    }
+	}
+	if (missing) return OUT_NEED;
+	if (countStats) stats.aln_invoked++;
+	const unsigned readLen = unsigned(rs->h_offs[r + 1] - rs->h_offs[r]);
+	std::vector<const IcbCand*> pass;
+	for (auto* c : tied) {
+	    double ratio = double(aln[AlnKey{pos, c->id, c->strand}]) / readLen;  // cluster.cpp:458
+	    if (ratio >= P.aligned_threshold) pass.push_back(c);
+	}
+	if (pass.empty()) return OUT_NEW;
+	if (pass.size() == 1 || tied.size() == 1) {
+	    outCls = real_id(pass[0]->id);
+	    outStrand = pass[0]->strand;
+	    return OUT_JOIN;
+	}
+	auto it = full.find(pos);
+	if (it == full.end()) {
+	    needFull.push_back(pos);
+	    return OUT_NEED;
+	}
+	if (countStats) stats.tie_fallbacks++;
+	auto order = reference_order(pos, it->second);
+	for (auto& o : order) {
+	    for (auto* p : pass)
+		if (unsigned(real_id(p->id)) == o.Cls && p->strand == o.Strand) {
+		    outCls = int(o.Cls);
+		    outStrand = o.Strand;
+		    return OUT_JOIN;
+		}
+	}
+	return OUT_NEW;	 // unreachable
+    };
+
+    while (commit_pos < N) {
+	stats.rounds++;
+	std::vector<AlnKey> needPairs;
+	std::vector<int32_t> needFull;
+	bool speculative = false;
+	for (int pos = commit_pos; pos < N; pos++) {
+	    int c, s;
+	    std::vector<AlnKey> np;
+	    std::vector<int32_t> nfull;
+	    Outcome o = decide(pos, c, s, np, nfull, !speculative);
+	    if (o == OUT_NEED) {
+		speculative = true;  // later reads are only scanned for the device work they will need
+		needPairs.insert(needPairs.end(), np.begin(), np.end());
+		needFull.insert(needFull.end(), nfull.begin(), nfull.end());
+		continue;
+	    }
+	    if (speculative) continue;
+	    // commit in order
+	    if (o == OUT_NEW) {
+		founder_cls[pos] = nextCls;
+		founder.push_back(chunk[pos]);
+		cluster_of[slots[pos]] = nextCls;
+		strand_of[slots[pos]] = 1;
+		nextCls++;
+	    }
+	    else {
+		cluster_of[slots[pos]] = c;
+		strand_of[slots[pos]] = s;
+	    }
+	    committed[pos] = 1;
+	    commit_pos = pos + 1;
+	}
+	if (commit_pos >= N) break;
+	if (needPairs.empty() && needFull.empty()) return ctx->fail(ICB_ERR_STATE, "greedy loop made no progress");
+	if (!needFull.empty()) {
+	    std::sort(needFull.begin(), needFull.end());
+	    needFull.erase(std::unique(needFull.begin(), needFull.end()), needFull.end());
+	    std::vector<IcbQueryHeader> h2;
+	    std::vector<IcbCand> c2;
+	    std::vector<int64_t> foff;
+	    rc = query(chunk, C0, &needFull, 1, 0, h2, c2, &foff);
+	    if (rc) return rc;
+	    for (size_t t = 0; t < needFull.size(); t++)
+		full[needFull[t]].assign(c2.begin() + foff[t], c2.begin() + foff[t] + h2[t].n_cand);
+	}
+	if (!needPairs.empty()) {
+	    std::sort(needPairs.begin(), needPairs.end());
+	    needPairs.erase(std::unique(needPairs.begin(), needPairs.end(), [](const AlnKey& a, const AlnKey& b) {
+				return a.pos == b.pos && a.id == b.id && a.strand == b.strand;
+			    }),
+			    needPairs.end());
+	    std::vector<icb_pair> pairs(needPairs.size());
+	    for (size_t t = 0; t < needPairs.size(); t++) {
+		const AlnKey& key = needPairs[t];
+		const int r = chunk[key.pos], rep = rep_read(key.id);
+		const double e = raw_err[r] + raw_err[rep];  // cluster.cpp:494-496: e1 (read) + e2 (representative)
+		icb_pair& p = pairs[t];
+		p.read = r;
+		p.rep = rep;
+		p.strand = key.strand;
+		p.gap_open = e <= 0.01 ? 5 : (e <= 0.04 ? 4 : (e <= 0.1 ? 3 : 2));  // setGapOpen, cluster.cpp:425-440
+		double lim = std::floor((1.0 - e) * unsigned(k));		     // getAlnRatio, cluster.cpp:446
+		p.limit = lim < -1.0 ? -1 : (lim > double(k + 1) ? k + 1 : int(lim));
+	    }
+	    std::vector<icb_align_result> res(pairs.size());
+	    rc = icb_align_pairs(rs, pairs.data(), int64_t(pairs.size()), k, res.data());
+	    if (rc) return rc;
+	    stats.pairs_aligned += int64_t(pairs.size());
+	    for (size_t t = 0; t < needPairs.size(); t++) {
+		aln[needPairs[t]] = res[t].aligned;
+		stats.cells_aligned += int64_t(rs->h_offs[pairs[t].read + 1] - rs->h_offs[pairs[t].read]) *
+				       int64_t(rs->h_offs[pairs[t].rep + 1] - rs->h_offs[pairs[t].rep]);
+	    }
+	}
+    }
+    // ---- AddMinimizers for the clusters founded in this chunk (cluster.cpp:178-180)
+    std::vector<int32_t> fr, fi;
+    int64_t tot = 0;
+    for (int i = 0; i < N; i++)
+	if (founder_cls[i] >= 0) {
+	    fr.push_back(chunk[i]);
+	    fi.push_back(founder_cls[i]);
+	    tot += nf[chunk[i]];
+	}
+    if (!fr.empty()) {
+	rc = main_idx.reserve(tot);
+	if (rc) return rc;
+	if (int64_t(founder.size()) > cls_founder_cap) {
+	    int64_t ncap = std::max<int64_t>(cls_founder_cap * 2, int64_t(founder.size()) + 1024);
+	    int32_t* nd = nullptr;
+	    ICB_CUDA(ctx, cudaMalloc((void**)&nd, sizeof(int32_t) * ncap));
+	    if (C0 > 0) ICB_CUDA(ctx, cudaMemcpyAsync(nd, d_cls_founder, sizeof(int32_t) * C0, cudaMemcpyDeviceToDevice, st));
+	    ICB_CUDA(ctx, cudaStreamSynchronize(st));
+	    cudaFree(d_cls_founder);
+	    d_cls_founder = nd;
+	    cls_founder_cap = ncap;
+	}
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_cls_founder + C0, founder.data() + C0, sizeof(int32_t) * (founder.size() - C0),
+				      cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, fr.data(), sizeof(int32_t) * fr.size(), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, fi.data(), sizeof(int32_t) * fi.size(), cudaMemcpyHostToDevice, st));
+	rc = icb_index_insert(ctx, main_idx, rs, d_chunk_reads, d_ids, int(fr.size()));
+	if (rc) return rc;
+	main_idx.nodes_upper += tot;
+	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return ICB_OK;
+}
+
+extern "C" {
+
+int icb_clusterer_create(icb_readset* rs, const icb_cluster_params* p, icb_clusterer** out)
+{
+    if (!rs || !p || !out) return ICB_ERR_ARG;
+    *out = nullptr;
+    icb_ctx* ctx = rs->ctx;
+    if (!rs->scored || !rs->sketched) return ctx->fail(ICB_ERR_STATE, "icb_clusterer_create needs scored and sketched reads");
+    if (p->kmer_size != rs->sk_k || p->window_size != rs->sk_w)
+	return ctx->fail(ICB_ERR_ARG, "k / w differ from the ones the reads were sketched with");
+    if (p->mode < 0 || p->mode > 2) return ctx->fail(ICB_ERR_ARG, "mode must be 0 (sahlin), 1 (fast) or 2 (furious)");
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto cl = new icb_clusterer;
+    cl->ctx = ctx;
+    cl->rs = rs;
+    cl->P = *p;
+    if (cl->P.chunk_size <= 0) cl->P.chunk_size = 256;
+    // n_max table (cluster.cpp:335-349: pow(pError, n) >= minProbNoHits with the HOST libm; monotone in n)
+    if (p->mode != 2) {
+	for (int c = 0; c < 225; c++) {
+	    double ps = p->p_shared[c];
+	    if (!(ps == ps)) {
+		delete cl;
+		return ctx->fail(ICB_ERR_NO_PEMP, "Empirical probability lookup failure!");
+	    }
+	    double pe = 1.0 - ps;
+	    int32_t n = -1;
+	    for (int32_t t = 0; t < (1 << 20); t++) {
+		if (std::pow(pe, double(t)) >= p->min_prob_no_hits) n = t;
+		else break;
+	    }
+	    cl->nmax[c] = n;
+	}
+    }
+    else
+	for (int c = 0; c < 225; c++) cl->nmax[c] = 0;
+    const int64_t n = rs->n_reads;
+    cl->status.resize(n);
+    cl->hpc_len.resize(n);
+    cl->nf.resize(n);
+    cl->nr.resize(n);
+    cl->score.resize(n);
+    cl->raw_err.resize(n);
+    cudaStream_t st = ctx->stream;
+    if (n) {
+	ICB_CUDA(ctx, cudaMemcpyAsync(cl->status.data(), rs->d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(cl->hpc_len.data(), rs->d_hpc_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(cl->nf.data(), rs->d_nf, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(cl->nr.data(), rs->d_nr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(cl->score.data(), rs->d_score, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(cl->raw_err.data(), rs->d_err, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    }
+    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_class, n + 16));
+    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_nmax, sizeof(int32_t) * 225));
+    ICB_CUDA(ctx, cudaMemcpyAsync(cl->d_nmax, cl->nmax, sizeof(int32_t) * 225, cudaMemcpyHostToDevice, st));
+    int rc = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, cl->d_class);
+    if (rc) return rc;
+    ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n; i++) cl->max_m = std::max(cl->max_m, std::max(cl->nf[i], cl->nr[i]));
+    if (cl->max_m >= 32768) {
+	delete cl;
+	return ctx->fail(ICB_ERR_ARG, "a read has 32768 or more minimizers per strand");
+    }
+    const int cs = cl->P.chunk_size;
+    cl->chunk_cap = cs;
+    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_chunk_reads, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_list, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_ids, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_hdr, sizeof(IcbQueryHeader) * cs));
+    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_full_off, sizeof(int64_t) * (cs + 1)));
+    rc = cl->main_idx.create(ctx, 1u << 16, 1 << 16);
+    if (rc) return rc;
+    rc = cl->chunk_idx.create(ctx, 1u << 16, 1 << 16);
+    if (rc) return rc;
+    *out = cl;
+    return ICB_OK;
+}
+
+void icb_clusterer_destroy(icb_clusterer* cl)
+{
+    if (!cl) return;
+    cudaSetDevice(cl->ctx->device);
+    cudaStreamSynchronize(cl->ctx->stream);
+    cl->main_idx.destroy();
+    cl->chunk_idx.destroy();
+    cudaFree(cl->d_class);
+    cudaFree(cl->d_nmax);
+    cudaFree(cl->d_cls_founder);
+    cudaFree(cl->d_chunk_reads);
+    cudaFree(cl->d_list);
+    cudaFree(cl->d_ids);
+    cudaFree(cl->d_hdr);
+    cudaFree(cl->d_cands);
+    cudaFree(cl->d_full_off);
+    cudaFree(cl->d_scratch);
+    delete cl;
+}
+
+int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_t* cluster_of, int32_t* strand_of)
+{
+    if (!cl || n < 0 || (n > 0 && (!order || !cluster_of || !strand_of))) return ICB_ERR_ARG;
+    icb_ctx* ctx = cl->ctx;
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const icb_cluster_params& P = cl->P;
+    std::vector<int32_t> chunk;
+    std::vector<int64_t> slots;
+    for (int64_t s = 0; s < n; s++) {
+	cluster_of[s] = -1;
+	strand_of[s] = 0;
+	const int32_t r = order[s];
+	if (r < 0 || r >= cl->rs->n_reads) return ctx->fail(ICB_ERR_ARG, "read index outside the read set");
+	// the skips of ClusterSortedReads (cluster.cpp:116-160)
+	if (cl->status[r] != 1) continue;
+	if (cl->score[r] < 0) continue;
+	const int64_t L = cl->rs->h_offs[r + 1] - cl->rs->h_offs[r];
+	if (uint64_t(L) < uint64_t(unsigned(2 * P.kmer_size))) continue;
+	if (uint64_t(cl->hpc_len[r]) < uint64_t(unsigned(2 * P.kmer_size))) continue;
+	if ((-10 * std::log10(cl->raw_err[r])) <= P.min_qual) continue;
+	chunk.push_back(r);
+	slots.push_back(s);
+	if (int(chunk.size()) == cl->chunk_cap) {
+	    int rc = cl->process_chunk(chunk, slots, cluster_of, strand_of);
+	    if (rc) return rc;
+	    chunk.clear();
+	    slots.clear();
+	}
+    }
+    if (!chunk.empty()) {
+	int rc = cl->process_chunk(chunk, slots, cluster_of, strand_of);
+	if (rc) return rc;
+    }
+    return ICB_OK;
+}
+
+int64_t icb_clusterer_n_clusters(const icb_clusterer* cl) { return cl ? int64_t(cl->founder.size()) : 0; }
+
+int icb_clusterer_founders(const icb_clusterer* cl, int32_t* founder_read)
+{
+    if (!cl || !founder_read) return ICB_ERR_ARG;
+    memcpy(founder_read, cl->founder.data(), sizeof(int32_t) * cl->founder.size());
+    return ICB_OK;
+}
+
+int icb_clusterer_stats(const icb_clusterer* cl, icb_cluster_stats* out)
+{
+    if (!cl || !out) return ICB_ERR_ARG;
+    *out = cl->stats;
+    return ICB_OK;
+}
+
+}  // extern "C"

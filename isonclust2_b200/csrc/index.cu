@@ -1,0 +1,430 @@
+// Stage 2 kernels — index build (AddMinimizers, reference minimizer.cpp:31-42) and the per-chunk candidate
+// query that replaces GetMinimizerHits / ConsolidateMinimizerHits (minimizer.cpp:44-76, cluster.cpp:609-615),
+// the hit counts of SortMinimizerHits (cluster.cpp:622-636) and the integer part of getMappedRatio
+// (cluster.cpp:324-353) for the candidates getBestClusterMapping can reach (cluster.cpp:355-406).
+//
+// Exactness across the greedy loop's sequential dependency: a chunk of sorted reads is scored against the
+// index SNAPSHOT at chunk start (clusters < C0) plus a CHUNK index that holds every read of the chunk as a
+// provisional founder (id = C0 + position); a read only sees provisional founders that precede it.  The host
+// loop keeps the ones that really became founders.  Hits against a cluster are independent of all other
+// clusters, so dropping provisional ones is exact.
+//
+// One 128-thread CTA per read.  Shared-minimizer counts are dense 16-bit counters in shared memory (one
+// 32-bit word per cluster: low half forward strand, high half reverse), bumped with shared-memory atomics
+// while threads walk the posting chains of the read's minimizers.  The mapped length needs each candidate's
+// hits in minimizer order: a bitmap over the read's minimizer ranks per relevant candidate, filled in a second
+// walk, then scanned by one thread per candidate.  Roofline class: L2/HBM latency-bound gathers (posting
+// chains), reported as hits/s; bytes per read = 12(M_f+M_r) + 8(M_f+M_r) + 8H + 16C.
+#include "index.cuh"
+
+namespace {
+
+constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t NIL = 0xFFFFFFFFu;
+constexpr int Q_THREADS = 128;
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x)
+{
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t find_slot(const IcbIndexView& ix, uint32_t key)
+{
+    if (key == EMPTY) return ix.mask + 1;
+    uint32_t s = hash32(key) & ix.mask;
+    for (;;) {
+	uint32_t k = ix.keys[s];
+	if (k == key) return s;
+	if (k == EMPTY) return NIL;
+	s = (s + 1) & ix.mask;
+    }
+}
+
+__device__ __forceinline__ uint32_t claim_slot(const IcbIndexView& ix, uint32_t key)
+{
+    if (key == EMPTY) return ix.mask + 1;
+    uint32_t s = hash32(key) & ix.mask;
+    for (;;) {
+	uint32_t prev = atomicCAS(&ix.keys[s], EMPTY, key);
+	if (prev == EMPTY || prev == key) return s;
+	s = (s + 1) & ix.mask;
+    }
+}
+
+template <class F>
+__device__ __forceinline__ void for_each_posting(const IcbIndexView& ix, uint32_t key, F f)
+{
+    uint32_t s = find_slot(ix, key);
+    if (s == NIL) return;
+    uint32_t n = ix.heads[s];
+    while (n != NIL) {
+	uint2 nd = ix.nodes[n];
+	f(nd.x);
+	n = nd.y;
+    }
+}
+
+// one CTA per founder: one node per DISTINCT forward minimizer value (the reference's `cls > back()` test keeps
+// a cluster once per posting list)
+__global__ void __launch_bounds__(Q_THREADS)
+icb_k_index_insert(IcbIndexView ix, const icb_minimizer* __restrict__ arena, const int64_t* __restrict__ min_off,
+		   const int32_t* __restrict__ nf, const int32_t* __restrict__ reads, const int32_t* __restrict__ ids, int n)
+{
+    int b = blockIdx.x;
+    if (b >= n) return;
+    const int r = reads[b];
+    const uint32_t id = uint32_t(ids[b]);
+    const int M = nf[r];
+    const icb_minimizer* m = arena + min_off[r];
+    for (int i = threadIdx.x; i < M; i += Q_THREADS) {
+	const uint32_t v = m[i].Min;
+	bool dup = false;
+	for (int j = 0; j < i; j++)
+	    if (m[j].Min == v) {
+		dup = true;
+		break;
+	    }
+	if (dup) continue;
+	uint32_t s = claim_slot(ix, v);
+	uint32_t nid = atomicAdd(ix.node_count, 1u);
+	uint32_t old = atomicExch(&ix.heads[s], nid);
+	ix.nodes[nid] = make_uint2(id, old);
+    }
+}
+
+__global__ void icb_k_index_rehash(IcbIndexView oldv, IcbIndexView newv)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > oldv.mask + 1) return;
+    uint32_t k = s == oldv.mask + 1 ? EMPTY : oldv.keys[s];
+    uint32_t h = oldv.heads[s];
+    if (s <= oldv.mask && k == EMPTY) return;
+    if (h == NIL) return;
+    uint32_t t = claim_slot(newv, k);
+    newv.heads[t] = h;
+}
+
+__global__ void icb_k_fill_u32(uint32_t* p, uint32_t v, int64_t n)
+{
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// error class of p_emp_prob.cpp:66-94: round(e, 2) (util.cpp:6-10) clamped to [0.01, 0.15] -> 0..14
+__global__ void icb_k_classify(const double* __restrict__ err, const int32_t* __restrict__ status, int64_t n, uint8_t* __restrict__ cls)
+{
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = 0;
+    if (status[i] == 1) {
+	double r = round(__dmul_rn(err[i], 100.0));  // std::round: half away from zero
+	c = r > 15.0 ? 15 : (r < 1.0 ? 1 : int(r));
+	c -= 1;
+    }
+    cls[i] = uint8_t(c);
+}
+
+template <bool SMEM_CNT>
+__global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
+{
+    extern __shared__ uint32_t sm[];
+    __shared__ int s_red[Q_THREADS / 32];
+    __shared__ int s_red2[Q_THREADS / 32];
+    __shared__ int s_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Ctot = a.C0 + a.n_chunk;
+    uint32_t* cnt = SMEM_CNT ? sm : a.g_scratch + int64_t(blockIdx.x) * a.g_stride;
+    uint32_t* list = SMEM_CNT ? sm + Ctot : sm;		 // 2 words per record: (id<<1|half), count
+    uint32_t* bm = list + 2 * a.cap;
+    const int bmWords = a.smem_words - (SMEM_CNT ? Ctot : 0) - 2 * a.cap;
+    uint32_t* first = a.g_scratch + int64_t(blockIdx.x) * a.g_stride + (SMEM_CNT ? 0 : Ctot);  // mode 1 only
+
+    const int n_items = a.list ? a.n_list : a.n_chunk;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+	const int pos = a.list ? a.list[item] : item;
+	const int r = a.chunk_reads[pos];
+	const int nf = a.nf[r], nr = a.nr[r];
+	const icb_minimizer* mins = a.arena + a.min_off[r];
+	__syncthreads();
+	for (int i = tid; i < Ctot; i += Q_THREADS) cnt[i] = 0;
+	if (a.mode == 1)
+	    for (int i = tid; i < 2 * Ctot; i += Q_THREADS) first[i] = 0xFFFFFFFFu;
+	if (tid == 0) s_n = 0;
+	__syncthreads();
+	// ---- walk 1: shared-minimizer counts per (cluster, strand)
+	for (int t = tid; t < nf + nr; t += Q_THREADS) {
+	    const icb_minimizer m = mins[t];
+	    const int half = t >= nf;
+	    const uint32_t inc = 1u << (16 * half);
+	    for_each_posting(a.main_idx, m.Min, [&](uint32_t id) {
+		atomicAdd(&cnt[id], inc);
+		if (a.mode == 1) atomicMin(&first[2 * id + half], m.Index);
+	    });
+	    for_each_posting(a.chunk_idx, m.Min, [&](uint32_t id) {
+		if (int(id) - a.C0 < pos) {
+		    atomicAdd(&cnt[id], inc);
+		    if (a.mode == 1) atomicMin(&first[2 * id + half], m.Index);
+		}
+	    });
+	}
+	__syncthreads();
+	// ---- top count among snapshot clusters, number of live keys
+	int top = 0, live = 0;
+	for (int i = tid; i < Ctot; i += Q_THREADS) {
+	    uint32_t v = cnt[i];
+	    int lo = v & 0xffff, hi = v >> 16;
+	    live += (lo > 0) + (hi > 0);
+	    if (i < a.C0) top = max(top, max(lo, hi));
+	}
+#pragma unroll
+	for (int d = 16; d; d >>= 1) {
+	    top = max(top, __shfl_xor_sync(0xffffffffu, top, d));
+	    live += __shfl_xor_sync(0xffffffffu, live, d);
+	}
+	if (lane == 0) {
+	    s_red[warp] = top;
+	    s_red2[warp] = live;
+	}
+	__syncthreads();
+	top = 0;
+	live = 0;
+	for (int i = 0; i < Q_THREADS / 32; i++) {
+	    top = max(top, s_red[i]);
+	    live += s_red2[i];
+	}
+	IcbQueryHeader* hdr = a.hdr + item;
+	if (a.mode == 1) {
+	    IcbCand* out = a.cands + a.full_off[item];
+	    for (int i = tid; i < Ctot; i += Q_THREADS) {
+		uint32_t v = cnt[i];
+		for (int half = 0; half < 2; half++) {
+		    int c = half ? int(v >> 16) : int(v & 0xffff);
+		    if (c > 0) {
+			int slot = atomicAdd(&s_n, 1);
+			IcbCand cd;
+			cd.id = i;
+			cd.strand = half ? -1 : 1;
+			cd.count = c;
+			cd.tmapped = int(first[2 * i + half]);
+			out[slot] = cd;
+		    }
+		}
+	    }
+	    __syncthreads();
+	    if (tid == 0) {
+		hdr->top_snap = top;
+		hdr->n_cand = s_n;
+		hdr->overflow = 0;
+		hdr->n_total = live;
+	    }
+	    continue;
+	}
+	// ---- mode 0: candidates the mapping / alignment tests can reach.  The real top count may still be raised
+	// by a provisional founder, never lowered, so int(max(top, minShared) * minFraction) is a safe lower bound
+	// of the cut getBestClusterMapping applies (cluster.cpp:387).
+	const int tbase = max(top, a.min_shared);
+	int thr = __double2int_rz(__dmul_rn(double(tbase), a.min_frac));
+	if (thr < 1) thr = 1;
+	for (int i = tid; i < Ctot; i += Q_THREADS) {
+	    uint32_t v = cnt[i];
+	    uint32_t nv = v;
+	    for (int half = 0; half < 2; half++) {
+		int c = half ? int(v >> 16) : int(v & 0xffff);
+		if (c >= thr) {
+		    int slot = atomicAdd(&s_n, 1);
+		    if (slot < a.cap) {
+			list[2 * slot] = uint32_t(i) << 1 | uint32_t(half);
+			list[2 * slot + 1] = uint32_t(c);
+			uint32_t tag = 0x8000u | uint32_t(slot);
+			nv = half ? ((nv & 0x0000ffffu) | (tag << 16)) : ((nv & 0xffff0000u) | tag);
+		    }
+		}
+	    }
+	    if (nv != v) cnt[i] = nv;
+	}
+	__syncthreads();
+	const int nRelAll = s_n;
+	const int nRel = min(nRelAll, a.cap);
+	const int bw = (max(nf, nr) + 31) >> 5;
+	const int perRound = max(1, bmWords / max(bw, 1));
+	const int myClass = a.read_class[r];
+	const int Lh = a.hpc_len[r];
+	for (int base = 0; base < nRel; base += perRound) {
+	    const int cntRound = min(perRound, nRel - base);
+	    for (int i = tid; i < cntRound * bw; i += Q_THREADS) bm[i] = 0;
+	    __syncthreads();
+	    // ---- walk 2: which of the read's minimizers hit each relevant candidate
+	    for (int t = tid; t < nf + nr; t += Q_THREADS) {
+		const icb_minimizer m = mins[t];
+		const int half = t >= nf;
+		auto mark = [&](uint32_t id) {
+		    uint32_t v = cnt[id];
+		    uint32_t h = half ? (v >> 16) : (v & 0xffffu);
+		    if (h & 0x8000u) {
+			int slot = int(h & 0x7fffu) - base;
+			if (slot >= 0 && slot < cntRound) atomicOr(&bm[slot * bw + (m.Index >> 5)], 1u << (m.Index & 31));
+		    }
+		};
+		for_each_posting(a.main_idx, m.Min, mark);
+		for_each_posting(a.chunk_idx, m.Min, [&](uint32_t id) {
+		    if (int(id) - a.C0 < pos) mark(id);
+		});
+	    }
+	    __syncthreads();
+	    // ---- totalMapped (cluster.cpp:333-351) in integers: a gap of g missed minimizers is bridged iff
+	    // pow(pError, g) >= minProbNoHits  <=>  g <= nmax[class(rep), class(read)]
+	    if (tid < cntRound) {
+		const int slot = base + tid;
+		const uint32_t e = list[2 * slot];
+		const int id = int(e >> 1), half = int(e & 1);
+		const int M = half ? nr : nf;
+		const icb_minimizer* mm = mins + (half ? nf : 0);
+		const int repRead = id < a.C0 ? a.cls_founder[id] : a.chunk_reads[id - a.C0];
+		const int nm = a.nmax[int(a.read_class[repRead]) * 15 + myClass];
+		const uint32_t* b = bm + tid * bw;
+		long long T = 0;
+		int prev = -1;
+		for (int wd = 0; wd < bw; wd++) {
+		    uint32_t x = b[wd];
+		    while (x) {
+			int bit = __ffs(x) - 1;
+			x &= x - 1;
+			int idx = wd * 32 + bit;
+			if (prev < 0) {
+			    if (idx <= nm) T += mm[idx].Pos;
+			}
+			else if (idx - prev - 1 <= nm) T += (long long)mm[idx].Pos - mm[prev].Pos;
+			prev = idx;
+		    }
+		}
+		if (prev >= 0 && M - prev - 1 <= nm) T += (long long)Lh - mm[prev].Pos;
+		IcbCand cd;
+		cd.id = id;
+		cd.strand = half ? -1 : 1;
+		cd.count = int(list[2 * slot + 1]);
+		cd.tmapped = int(T);
+		a.cands[int64_t(item) * a.cap + slot] = cd;
+	    }
+	    __syncthreads();
+	}
+	if (tid == 0) {
+	    hdr->top_snap = top;
+	    hdr->n_cand = nRel;
+	    hdr->overflow = nRelAll > a.cap;
+	    hdr->n_total = live;
+	}
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host side of the index
+
+static int fill_u32(icb_ctx* ctx, uint32_t* p, uint32_t v, int64_t n)
+{
+    if (n <= 0) return ICB_OK;
+    ICB_LAUNCH(ctx, "fill_u32", icb_k_fill_u32<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(p, v, n));
+    return ICB_OK;
+}
+
+int IcbIndex::create(icb_ctx* c, uint32_t cap_pow2, int64_t node_cap)
+{
+    ctx = c;
+    capacity = cap_pow2;
+    node_capacity = node_cap;
+    nodes_upper = 0;
+    ICB_CUDA(ctx, cudaMalloc((void**)&v.keys, sizeof(uint32_t) * (size_t(capacity) + 1)));
+    ICB_CUDA(ctx, cudaMalloc((void**)&v.heads, sizeof(uint32_t) * (size_t(capacity) + 1)));
+    ICB_CUDA(ctx, cudaMalloc((void**)&v.nodes, sizeof(uint2) * size_t(node_capacity)));
+    ICB_CUDA(ctx, cudaMalloc((void**)&v.node_count, sizeof(uint32_t) * 2));
+    v.mask = capacity - 1;
+    return clear();
+}
+
+int IcbIndex::clear()
+{
+    nodes_upper = 0;
+    ICB_CUDA(ctx, cudaMemsetAsync(v.keys, 0xff, sizeof(uint32_t) * (size_t(capacity) + 1), ctx->stream));
+    ICB_CUDA(ctx, cudaMemsetAsync(v.heads, 0xff, sizeof(uint32_t) * (size_t(capacity) + 1), ctx->stream));
+    ICB_CUDA(ctx, cudaMemsetAsync(v.node_count, 0, sizeof(uint32_t) * 2, ctx->stream));
+    return ICB_OK;
+}
+
+int IcbIndex::reserve(int64_t extra)
+{
+    const int64_t need = nodes_upper + extra;
+    if (need > node_capacity) {
+	int64_t nc = node_capacity;
+	while (nc < need) nc *= 2;
+	uint2* nn = nullptr;
+	ICB_CUDA(ctx, cudaMalloc((void**)&nn, sizeof(uint2) * size_t(nc)));
+	ICB_CUDA(ctx, cudaMemcpyAsync(nn, v.nodes, sizeof(uint2) * size_t(nodes_upper), cudaMemcpyDeviceToDevice, ctx->stream));
+	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(v.nodes);
+	v.nodes = nn;
+	node_capacity = nc;
+    }
+    if (need * 2 > int64_t(capacity)) {	 // distinct keys <= nodes: keep the load factor under one half
+	uint64_t ncap = capacity;
+	while (int64_t(ncap) < need * 2) ncap *= 2;
+	if (ncap > (1ull << 31)) return ctx->fail(ICB_ERR_NOMEM, "minimizer index too large");
+	IcbIndexView nv = v;
+	nv.mask = uint32_t(ncap - 1);
+	ICB_CUDA(ctx, cudaMalloc((void**)&nv.keys, sizeof(uint32_t) * (size_t(ncap) + 1)));
+	ICB_CUDA(ctx, cudaMalloc((void**)&nv.heads, sizeof(uint32_t) * (size_t(ncap) + 1)));
+	ICB_CUDA(ctx, cudaMemsetAsync(nv.keys, 0xff, sizeof(uint32_t) * (size_t(ncap) + 1), ctx->stream));
+	ICB_CUDA(ctx, cudaMemsetAsync(nv.heads, 0xff, sizeof(uint32_t) * (size_t(ncap) + 1), ctx->stream));
+	ICB_LAUNCH(ctx, "index_rehash", icb_k_index_rehash<<<unsigned((size_t(capacity) + 1 + 255) / 256), 256, 0, ctx->stream>>>(v, nv));
+	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(v.keys);
+	cudaFree(v.heads);
+	v = nv;
+	capacity = uint32_t(ncap);
+    }
+    return ICB_OK;
+}
+
+void IcbIndex::destroy()
+{
+    cudaFree(v.keys);
+    cudaFree(v.heads);
+    cudaFree(v.nodes);
+    cudaFree(v.node_count);
+    v = IcbIndexView{};
+}
+
+int icb_index_insert(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, const int32_t* d_reads, const int32_t* d_ids, int n)
+{
+    if (n <= 0) return ICB_OK;
+    ICB_LAUNCH(ctx, "index_insert",
+	       icb_k_index_insert<<<n, Q_THREADS, 0, ctx->stream>>>(idx.v, rs->d_mins, rs->d_min_off, rs->d_nf, d_reads, d_ids, n));
+    return ICB_OK;
+}
+
+int icb_query_launch(icb_ctx* ctx, const IcbQueryArgs& a, int n_blocks, size_t smem_bytes)
+{
+    if (n_blocks <= 0) return ICB_OK;
+    if (a.smem_cnt) {
+	ICB_CUDA(ctx, cudaFuncSetAttribute(icb_k_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+	ICB_LAUNCH(ctx, a.mode ? "index_query_full" : "index_query",
+		   icb_k_query<true><<<n_blocks, Q_THREADS, smem_bytes, ctx->stream>>>(a));
+    }
+    else {
+	ICB_CUDA(ctx, cudaFuncSetAttribute(icb_k_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+	ICB_LAUNCH(ctx, a.mode ? "index_query_full" : "index_query",
+		   icb_k_query<false><<<n_blocks, Q_THREADS, smem_bytes, ctx->stream>>>(a));
+    }
+    return ICB_OK;
+}
+
+int icb_classify_errors(icb_ctx* ctx, const double* d_err, const int32_t* d_status, int64_t n, uint8_t* d_class)
+{
+    if (n <= 0) return ICB_OK;
+    ICB_LAUNCH(ctx, "classify_errors", icb_k_classify<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(d_err, d_status, n, d_class));
+    return ICB_OK;
+}

@@ -61,6 +61,14 @@ def load():
     L.icb_sketch_sizes.argtypes = [_p, C.POINTER(_i64), C.POINTER(_i64)]
     L.icb_sketch_download.argtypes = [_p] * 10
     L.icb_align_pairs.argtypes = [_p, _p, _i64, _i32, _p]
+    L.icb_clusterer_create.argtypes = [_p, _p, C.POINTER(_p)]
+    L.icb_clusterer_destroy.argtypes = [_p]
+    L.icb_clusterer_destroy.restype = None
+    L.icb_cluster_reads.argtypes = [_p, _p, _i64, _p, _p]
+    L.icb_clusterer_n_clusters.argtypes = [_p]
+    L.icb_clusterer_n_clusters.restype = _i64
+    L.icb_clusterer_founders.argtypes = [_p, _p]
+    L.icb_clusterer_stats.argtypes = [_p, _p]
     L.icb_init_qual_tab.argtypes = [_p, _i32]
     L.icb_init_qual_tab.restype = None
     L.icb_quality_filter.argtypes = [_p, _i64, _dbl, _p]

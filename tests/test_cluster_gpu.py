@@ -1,0 +1,116 @@
+"""GPU parity: stage 2 (device index + candidate query) and the host greedy loop vs the oracle — identical cluster
+assignment, strands, founders and alignment-invocation counts, in all three modes and for every chunk size."""
+import numpy as np
+import pytest
+
+from isonclust2_b200 import api, pemp, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_cluster(ctx, seq, qual, offs, k, w, mode, chunk_size, **kw):
+    rs = ctx.upload(seq, qual, offs)
+    try:
+        score, err = rs.score(k)
+        skip = api.quality_filtered(err, kw.get("min_qual", 7.0))
+        rs.sketch_async(k, w, skip=skip)
+        order = api.sort_by_qual_scores(score)
+        cl = api.Clusterer(rs, k, w, mode=mode, chunk_size=chunk_size, **kw)
+        try:
+            c, s = cl.cluster(order)
+            return dict(order=order, cluster=c, strand=s, founders=cl.founders(), stats=cl.stats(), n_clusters=cl.n_clusters)
+        finally:
+            cl.close()
+    finally:
+        rs.close()
+
+
+def _port_cluster(port, seq, qual, offs, k, w, mode, **kw):
+    score, err = port.fill_scores(qual, offs, k)
+    order = port.sort_order(score)
+    sk = port.sketch_batch(seq, qual, offs, k, w)
+    status = sk["status"].copy()
+    for i in range(len(err)):
+        if port.L.orc_quality_filtered(err[i], kw.get("min_qual", 7.0)):
+            status[i] = 0
+    pc = port.cluster(seq, offs, sk, score, err, order, k, w, mode, pemp.load_p_shared(k, w), status=status, **kw)
+    pc["order"] = order
+    return pc
+
+
+def _same(g, p):
+    assert (g["order"] == p["order"]).all()
+    assert g["n_clusters"] == p["n_clusters"]
+    assert (g["cluster"] == p["cluster"]).all(), np.flatnonzero(g["cluster"] != p["cluster"])[:10]
+    assert (g["strand"] == p["strand"]).all()
+    # founders: the oracle reports sorted-slot indices, the product read ids
+    assert (g["founders"] == g["order"][p["founder"]]).all()
+    assert g["stats"]["aln_invoked"] == p["n_aligned"]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("chunk_size", [1, 7, 64, 256])
+def test_cluster_matches_oracle(port, ctx, mode, chunk_size):
+    k, w = 11, 15
+    seq, qual, offs = synth.make_reads(220, seed=51, reads_per_gene=11, min_len=300, max_len=800)
+    p = _port_cluster(port, seq, qual, offs, k, w, mode)
+    g = _gpu_cluster(ctx, seq, qual, offs, k, w, mode, chunk_size)
+    _same(g, p)
+
+
+@pytest.mark.parametrize("mode,name", [(0, "sahlin"), (1, "fast"), (2, "furious")])
+def test_cluster_golden(ctx, golden, mode, name):
+    """Fixtures produced by the unmodified reference (tests/golden/make_golden.py)."""
+    seq, qual, offs = golden["seq"], golden["qual"], golden["offs"]
+    k, w = int(golden["k"]), int(golden["w"])
+    g = _gpu_cluster(ctx, seq, qual, offs, k, w, mode, 32)
+    sizes, ids, strands = golden[f"cl_{name}_sizes"], golden[f"cl_{name}_ids"], golden[f"cl_{name}_strands"]
+    ra, pos = {}, 0
+    for c, sz in enumerate(sizes):
+        for j in range(1, sz):
+            ra[int(ids[pos + j])] = (c, int(strands[pos + j]))
+        pos += sz
+    ga = {int(g["order"][s]): (int(g["cluster"][s]), int(g["strand"][s])) for s in range(len(g["order"])) if g["cluster"][s] >= 0}
+    assert ga == ra
+    assert g["stats"]["aln_invoked"] == int(golden[f"cl_{name}_n_aligned"])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cluster_vs_reference_batch(ref, ctx, mode):
+    """A 1500-read batch against the UNMODIFIED reference's ClusterSortedReads (ties, many clusters in fast mode)."""
+    k, w = 11, 15
+    seq, qual, offs = synth.make_reads(1500, seed=52 + mode)
+    rb = ref.sort_and_sketch(seq, qual, offs, k, w)
+    _, _, order = rb.scores()
+    rc = rb.cluster(mode)
+    g = _gpu_cluster(ctx, seq, qual, offs, k, w, mode, 256)
+    assert (g["order"] == order).all()
+    ra, pos = {}, 0
+    for c, sz in enumerate(rc["sizes"]):
+        for j in range(1, sz):
+            ra[int(rc["ids"][pos + j])] = (c, int(rc["strands"][pos + j]))
+        pos += sz
+    ga = {int(g["order"][s]): (int(g["cluster"][s]), int(g["strand"][s])) for s in range(len(order)) if g["cluster"][s] >= 0}
+    assert ga == ra
+    assert g["n_clusters"] == rc["n_clusters"] and g["stats"]["aln_invoked"] == rc["n_aligned"]
+
+
+def test_cluster_params_variants(port, ctx):
+    k, w = 13, 20
+    seq, qual, offs = synth.make_reads(150, seed=54, reads_per_gene=10, min_len=300, max_len=700)
+    for kw in (dict(min_shared=3, min_fraction=0.5), dict(mapped_th=0.9, aligned_th=0.4), dict(min_prob_no_hits=0.3, min_qual=12.0)):
+        p = _port_cluster(port, seq, qual, offs, k, w, 0, **kw)
+        gk = {{"mapped_th": "mapped_threshold", "aligned_th": "aligned_threshold"}.get(a, a): b for a, b in kw.items()}
+        g = _gpu_cluster(ctx, seq, qual, offs, k, w, 0, 48, **gk)
+        _same(g, p)
+
+
+def test_cluster_no_pemp_row(ctx):
+    seq, qual, offs = synth.make_reads(20, seed=55, min_len=300, max_len=400)
+    rs = ctx.upload(seq, qual, offs)
+    rs.score(12)
+    rs.sketch_async(12, 47)  # no (k=12, w=47+-2) row in the empirical table
+    with pytest.raises(api.IcbError) as ei:
+        api.Clusterer(rs, 12, 47, mode="sahlin")
+    assert ei.value.code == -4
+    rs.close()
