@@ -98,9 +98,10 @@ def test_cluster_vs_reference_batch(ref, ctx, mode):
 def test_cluster_params_variants(port, ctx):
     k, w = 13, 20
     seq, qual, offs = synth.make_reads(150, seed=54, reads_per_gene=10, min_len=300, max_len=700)
-    for kw in (dict(min_shared=3, min_fraction=0.5), dict(mapped_th=0.9, aligned_th=0.4), dict(min_prob_no_hits=0.3, min_qual=12.0)):
+    for kw in (dict(min_shared=3, min_frac=0.5), dict(mapped_th=0.9, aligned_th=0.4), dict(min_prob_no_hits=0.3, min_qual=12.0)):
         p = _port_cluster(port, seq, qual, offs, k, w, 0, **kw)
-        gk = {{"mapped_th": "mapped_threshold", "aligned_th": "aligned_threshold"}.get(a, a): b for a, b in kw.items()}
+        gk = {{"mapped_th": "mapped_threshold", "aligned_th": "aligned_threshold", "min_frac": "min_fraction"}.get(a, a): b
+              for a, b in kw.items()}
         g = _gpu_cluster(ctx, seq, qual, offs, k, w, 0, 48, **gk)
         _same(g, p)
 
