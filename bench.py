@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""bench.py — isonclust2_b200 hot-path benchmark (see DESIGN.md §Measurement).
+"""bench.py — isonclust2_b200 hot-path benchmark (DESIGN.md §Measurement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic ONT-like cDNA reads (BASELINE.json
-configs[1]: ~1.2 kb median, 8 % error, k=11 w=15): quality scores -> host stable sort -> sketches.
-`value` is measured with the reads resident in HBM; `e2e` goes through the public C ABI with pinned HOST
-buffers (H2D of the reads and D2H of scores + sketch summary inside the timed region).
-Multi-GPU: reads are sharded across ranks (one process per GPU, no data-path collective) -> weak scaling.
+One "step" = one pass of the clustering hot path over one batch set of synthetic ONT-like cDNA reads
+(BASELINE.json configs[1]: ~1.3 kb mean, 8 % error, k=11 w=15): quality scores -> stable sort -> HPC minimizer
+sketches -> batches (main.cpp:149-199 rule) -> greedy clustering of every batch in `sahlin` mode (device index
+queries + batched alignment verification).  metric = reads/s clustered.
+  value : reads already resident in HBM when the timed region starts (CUDA events on the library's stream)
+  e2e   : through the public C ABI with pinned HOST buffers; H2D of the reads and D2H of the per-read results are
+          inside the timed region (wall clock bracketed by device synchronisation)
+Multi-GPU: reads are sharded across ranks, one process per GPU, no data-path collective -> weak scaling.
 """
 import argparse
 import json
@@ -22,13 +25,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-K, W_, MIN_QUAL = 11, 15, 7.0
-METRIC = "reads/sec sketched (score+sort+HPC minimizer sketch)"
+K, W_, MIN_QUAL, MODE = 11, 15, 7.0, "sahlin"
+BATCH_KB, BATCH_MAX_SEQ = 50000, 30000  # CmdArgs defaults (args.h:14-15)
+METRIC = "reads/sec clustered (sahlin)"
+KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_full", "index_insert", "align_dp",
+           "align_trace", "classify_errors", "index_rehash", "sketch_reads_long", "gather_minimizers")
 
 
 def clocks_sampler(stop, out, device):
     """nvidia-smi clock/throttle samples during the timed region (B200_PROFILING.md recipe)."""
-    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     while not stop.is_set():
         try:
             r = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
@@ -44,8 +51,9 @@ def clocks_sampler(stop, out, device):
 def summarize_clocks(samples):
     if not samples:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-    sm = sorted(float(s[0]) for s in samples if s[0].replace(".", "").isdigit())
-    mx = [float(s[1]) for s in samples if s[1].replace(".", "").isdigit()]
+    num = lambda s: s.replace(".", "", 1).isdigit()
+    sm = sorted(float(s[0]) for s in samples if num(s[0]))
+    mx = [float(s[1]) for s in samples if num(s[1])]
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
@@ -88,35 +96,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident step: reads already in HBM
+    pipe = dict(k=K, w=W_, mode=MODE, min_qual=MIN_QUAL, batch_kb=BATCH_KB, batch_max_seq=args.batch_max_seq, chunk_size=args.chunk)
+
+    # ---------------- device-resident steps: reads already in HBM
     rs = ctx.upload(seq, qual, offs)
     ctx.sync()
-    score_h, err_h = np.empty(n_reads), np.empty(n_reads)
-
-    def step_resident():
-        rs.score_async(K)
-        rs.scores(score_h, err_h)		       # the host needs them: libm filter + stable sort (host keeps)
-        skip = api.quality_filtered_fast(err_h, MIN_QUAL)
-        order = api.sort_by_qual_scores(score_h)
-        rs.sketch_async(K, W_, skip=skip)
-        return order
-
-    def step_e2e():
-        r2 = ctx.upload(seq, qual, offs)
-        r2.score_async(K)
-        s, e = r2.scores(score_h, err_h)
-        skip = api.quality_filtered_fast(e, MIN_QUAL)
-        order = api.sort_by_qual_scores(s)
-        r2.sketch_async(K, W_, skip=skip)
-        nf, nr = r2.sketch_sizes()
-        r2.close()
-        return order, nf, nr
-
+    res = None
     for _ in range(args.warmup):
-        step_resident()
+        res = api.run_pipeline(ctx, None, None, None, rs=rs, **pipe)
     ctx.sync()
-    nf, nr = rs.sketch_sizes()
-    hpc_total = None
 
     samples, stop = [], threading.Event()
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
@@ -131,32 +119,32 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        step_resident()
+        res = api.run_pipeline(ctx, None, None, None, rs=rs, **pipe)
         e1.record(stream)
         ctx.sync()
         barrier()
         times.append(e0.elapsed_time(e1))
     launches = ctx.launch_count() - launches0
-    kt = {n: ctx.kernel_time(n) for n in ("sketch_reads", "score_reads", "hpc_error_rate", "sketch_reads_long")}
+    kt = {n: ctx.kernel_time(n) for n in KERNELS}
     ctx.timing(False)
+    nf, nr = rs.sketch_sizes()
+    sk = rs.sketch_download(hpc=False)
+    hpc_total = int(sk["hpc_len"].sum())
+    rs.close()
 
     # ---------------- e2e through the C ABI with host buffers
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
+    for _ in range(1):
+        api.run_pipeline(ctx, seq, qual, offs, **pipe)
     e2e_times = []
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
-        step_e2e()
+        api.run_pipeline(ctx, seq, qual, offs, **pipe)
         ctx.sync()
         barrier()
         e2e_times.append((time.perf_counter() - t0) * 1e3)
     stop.set()
     th.join(timeout=2)
-
-    sk = rs.sketch_download(hpc=False)
-    hpc_total = int(sk["hpc_len"].sum())
-    rs.close()
 
     ms = float(np.mean(times))
     ms_e2e = float(np.mean(e2e_times))
@@ -165,27 +153,38 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
-    # roofline of the dominant kernel (sketch_reads): algorithmic bytes per launch / measured launch time
+    # roofline of the dominant data-moving kernel (sketch_reads): algorithmic bytes per launch / measured launch time
+    steps = max(args.steps, 1)
     alg_bytes = 2 * n_bases + 2 * hpc_total + 12 * (nf + nr) + 24 * n_reads
     n_l, tot_ms = kt["sketch_reads"]
     k_ms = tot_ms / max(n_l, 1)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    st = res["stats"]
+    dp_ms = kt["align_dp"][1] / steps
+    gcups = st["cells_aligned"] / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else 0.0
+    clustered = int((res["cluster"] >= 0).sum())
 
     line = {
         "metric": METRIC, "value": world * n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/u32 (+f64 quality chains)", "data": "synthetic",
-        "config": {"workload": f"configs[1]: sort stage over {n_reads} synthetic ONT cDNA reads per GPU (~1.3 kb mean, 8% error), k=11 w=15",
-                   "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "l2": "flushed between timed steps (256 MiB write)",
-                   "parallelism": f"reads sharded x{world}, no collective"},
-        "e2e": {"value": world * n_reads / (ms_e2e * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": 2 * n_bases + 8 * (n_reads + 1) + n_reads,
-                "d2h_bytes_per_step": 16 * n_reads + 8 * n_reads + 64},
+        "dtype": "u8/u32/i32 (+f64 quality chains)", "data": "synthetic",
+        "config": {"workload": f"configs[1] read set: {n_reads} synthetic ONT cDNA reads per GPU (~1.3 kb mean, 8% error), k=11 w=15, "
+                               f"sort + cluster -x sahlin of every batch (B={BATCH_KB} kb, M={args.batch_max_seq})",
+                   "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "batches": len(res["batches"]),
+                   "clusters": int(sum(res["n_clusters"])), "reads_clustered": clustered,
+                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"reads sharded x{world}, no collective"},
+        "e2e": {"value": world * n_reads / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": 2 * n_bases + 8 * (n_reads + 1) + n_reads, "d2h_bytes_per_step": 16 * n_reads + 24 * n_reads},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "icb_k_sketch (sketch_reads)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel_ms": k_ms},
-        "kernels_ms_per_step": {n: (v[1] / max(args.steps, 1)) for n, v in kt.items()},
+        "alignment": {"gcups": gcups, "cells_per_step": st["cells_aligned"], "pairs_per_step": st["pairs_aligned"],
+                      "aln_invoked": st["aln_invoked"], "dp_ms_per_step": dp_ms},
+        "cluster_stats": st,
+        "kernels_ms_per_step": {n: v[1] / steps for n, v in kt.items() if v[0]},
+        "kernel_launches_per_step": {n: v[0] / steps for n, v in kt.items() if v[0]},
         "clocks": summarize_clocks(samples),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -197,37 +196,42 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(seq, qual, offs, budget_s=15.0):
-    """The reference's own CPU implementation of the same step (FillQualScores + SortByQualScores +
-    PrepareSortedBatch, TBB over all host cores) on a bounded sample of the same reads."""
+def cpu_baseline(seq, qual, offs, budget_s=20.0):
+    """The reference's own CPU implementation of the same step on a bounded sample of the same reads:
+    FillQualScores + SortByQualScores + PrepareSortedBatch (TBB, all host cores) then ClusterSortedReads -x sahlin
+    (single-threaded, as in the reference).  Falls back to the C restatement when oracle/_ref is absent."""
     import oracle
+    from isonclust2_b200 import pemp
 
     n = len(offs) - 1
-    sample = min(n, 20000)
     if oracle.have_ref():
         R = oracle.ref()
-        kind = "reference"
-        run = lambda m: R.sort_and_sketch(seq[:offs[m]], qual[:offs[m]], offs[:m + 1], K, W_, MIN_QUAL)
+        kind, cores = "reference", os.cpu_count()
+
+        def run(m):
+            b = R.sort_and_sketch(seq[:offs[m]], qual[:offs[m]], offs[:m + 1], K, W_, MIN_QUAL)
+            b.cluster(0)
     else:
         P = oracle.port()
-        kind = "port"
+        kind, cores = "port", 1
 
         def run(m):
             s, e = P.fill_scores(qual, offs[:m + 1], K)
-            P.sort_order(s)
-            P.sketch_batch(seq, qual, offs[:m + 1], K, W_)
-        sample = min(n, 2000)
+            o = P.sort_order(s)
+            sk = P.sketch_batch(seq, qual, offs[:m + 1], K, W_)
+            P.cluster(seq, offs[:m + 1], sk, s, e, o, K, W_, 0, pemp.load_p_shared(K, W_))
+    sample = min(n, 1000)
     t0 = time.perf_counter()
     run(sample)
     dt = time.perf_counter() - t0
-    # grow the sample towards the time budget (once)
-    if dt < budget_s / 4 and sample < n:
-        sample = int(min(n, sample * min(8.0, budget_s / max(dt, 1e-3) / 2)))
+    if dt < budget_s / 3 and sample < n:  # grow the sample towards the time budget (once)
+        sample = int(min(n, sample * min(10.0, budget_s / max(dt, 1e-3) / 1.5)))
         t0 = time.perf_counter()
         run(sample)
         dt = time.perf_counter() - t0
-    return {"value": sample / dt, "unit": "reads/s", "cores": os.cpu_count() if kind == "reference" else 1, "kind": kind,
-            "sample": f"first {sample} reads of the same workload, {dt:.2f} s"}
+    return {"value": sample / dt, "unit": "reads/s", "cores": cores, "kind": kind,
+            "sample": f"first {sample} reads of the same workload as one batch, {dt:.2f} s "
+                      f"(sort+sketch on {cores} threads, cluster single-threaded like the reference)"}
 
 
 def run_reference(args):
@@ -236,19 +240,19 @@ def run_reference(args):
         return
     from isonclust2_b200 import synth
 
-    n_reads = min(args.reads, 100000)
+    n_reads = min(args.reads, 20000)
     seq, qual, offs = synth.make_reads(n_reads, seed=100, err_set=(0.08,))
-    vals = []
-    for i in range(args.warmup + args.steps):
+    vals, cb = [], None
+    for i in range(min(args.warmup, 1) + args.steps):
         cb = cpu_baseline(seq, qual, offs, budget_s=args.cpu_budget)
-        if i >= args.warmup:
+        if i >= min(args.warmup, 1):
             vals.append(cb["value"])
     v = float(np.mean(vals)) if vals else cb["value"]
     cb["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/u32 (+f64 quality chains)", "data": "synthetic",
-            "config": {"workload": "configs[1] sort stage, bounded sample on the host cores"},
+            "vs_baseline": None, "dtype": "u8/u32/i32 (+f64 quality chains)", "data": "synthetic",
+            "config": {"workload": "configs[1] read set, bounded sample on the host cores: sort + cluster -x sahlin"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -256,12 +260,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU")
+    ap.add_argument("--reads", type=int, default=100_000, help="reads per GPU")
+    ap.add_argument("--batch-max-seq", type=int, default=BATCH_MAX_SEQ)
+    ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

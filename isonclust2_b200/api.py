@@ -257,3 +257,59 @@ class ReadSet:
     def sketch(self, k, w, skip=None, hpc=True):
         self.sketch_async(k, w, skip)
         return self.sketch_download(hpc=hpc)
+
+
+def split_batches(order, lengths, batch_kb=50000, batch_max_seq=30000):
+    """The batch windows of mainSort (main.cpp:149-199): a batch closes with the read that takes it above
+    batch_kb*1000 bases or to batch_max_seq reads.  Returns [(start, end_exclusive)] over the sorted order."""
+    out, start, bases, cnt = [], 0, 0, 0
+    csum = np.cumsum(np.asarray(lengths)[np.asarray(order)])
+    n = len(order)
+    i = 0
+    while i < n:
+        # first index where either limit is hit
+        base0 = csum[start - 1] if start > 0 else 0
+        lim_b = int(np.searchsorted(csum, base0 + batch_kb * 1000, side="right")) if batch_kb > 0 else n
+        lim_n = start + batch_max_seq - 1 if batch_max_seq > 0 else n
+        end = min(lim_b, lim_n, n - 1)
+        if batch_kb <= 0:
+            end = n - 1
+        out.append((start, end + 1))
+        start = end + 1
+        i = start
+    return out
+
+
+def run_pipeline(ctx, seq, qual, offs, k=11, w=15, mode="sahlin", min_qual=7.0, batch_kb=50000, batch_max_seq=30000,
+                 chunk_size=0, rs=None, keep=False, **cluster_kw):
+    """`isONclust2 sort` + one `isONclust2 cluster -x <mode>` per batch, on one device, without the files in between.
+
+    Returns dict(order, batches, cluster (per sorted slot, batch-local ids), strand, n_clusters per batch, stats)."""
+    own = rs is None
+    if own:
+        rs = ctx.upload(seq, qual, offs)
+    try:
+        rs.score_async(k)
+        score, err = rs.scores()
+        skip = quality_filtered(err, min_qual)
+        order = sort_by_qual_scores(score)
+        rs.sketch_async(k, w, skip=skip)
+        lengths = np.diff(rs.offs)
+        batches = split_batches(order, lengths, batch_kb, batch_max_seq)
+        cluster = np.full(len(order), -1, np.int32)
+        strand = np.zeros(len(order), np.int32)
+        ncl, stats = [], []
+        for a, b in batches:
+            cl = Clusterer(rs, k, w, mode=mode, min_qual=min_qual, chunk_size=chunk_size, **cluster_kw)
+            try:
+                c, s = cl.cluster(order[a:b])
+                cluster[a:b], strand[a:b] = c, s
+                ncl.append(cl.n_clusters)
+                stats.append(cl.stats())
+            finally:
+                cl.close()
+        tot = {key: sum(st[key] for st in stats) for key in stats[0]} if stats else {}
+        return dict(order=order, batches=batches, cluster=cluster, strand=strand, n_clusters=ncl, stats=tot, score=score, err=err)
+    finally:
+        if own and not keep:
+            rs.close()

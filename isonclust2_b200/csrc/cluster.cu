@@ -48,14 +48,11 @@ struct icb_clusterer {
     icb_readset* rs = nullptr;
     icb_cluster_params P{};
     int32_t nmax[225];
-    // host copies of per-read scalars
-    std::vector<int32_t> status, hpc_len, nf, nr;
-    std::vector<double> score, raw_err;
+    // host mirror of per-read scalars lives in the read set (shared by all clusterers on it)
     // clusters
     std::vector<int32_t> founder;  // cluster id -> founder read
     // device state
     IcbIndex main_idx, chunk_idx;
-    uint8_t* d_class = nullptr;
     int32_t* d_nmax = nullptr;
     int32_t* d_cls_founder = nullptr;
     int64_t cls_founder_cap = 0;
@@ -69,7 +66,6 @@ struct icb_clusterer {
     uint32_t* d_scratch = nullptr;
     int64_t scratch_words = 0;
     int chunk_cap = 0;
-    int max_m = 0;
     icb_cluster_stats stats{};
 
     int ensure_scratch(int64_t words);
@@ -117,7 +113,7 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
     a.nf = rs->d_nf;
     a.nr = rs->d_nr;
     a.hpc_len = rs->d_hpc_len;
-    a.read_class = d_class;
+    a.read_class = rs->d_class;
     a.chunk_reads = d_chunk_reads;
     a.n_chunk = n_chunk;
     a.list = nullptr;
@@ -153,7 +149,7 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
     if (rc) return rc;
     a.cands = d_cands;
     // shared memory plan: dense counters (Ctot words) + candidate list (2*cap) + bitmaps
-    const int bw = (max_m + 31) / 32;
+    const int bw = (rs->max_m + 31) / 32;
     const int bmWords = std::max(bw, 1024);
     int64_t words_smem = int64_t(Ctot) + 2 * cap + bmWords;
     const int64_t smem_limit_words = (200 * 1024) / 4;
@@ -189,6 +185,8 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 				 int32_t* strand_of)
 {
     cudaStream_t st = ctx->stream;
+    const std::vector<int32_t>&nf = rs->h_nf, &nr = rs->h_nr, &hpc_len = rs->h_hpc_len;
+    const std::vector<double>& raw_err = rs->h_err;
     const int N = int(chunk.size());
     const int C0 = int(founder.size());
     const int k = P.kmer_size;
@@ -522,32 +520,37 @@ int icb_clusterer_create(icb_readset* rs, const icb_cluster_params* p, icb_clust
     else
 	for (int c = 0; c < 225; c++) cl->nmax[c] = 0;
     const int64_t n = rs->n_reads;
-    cl->status.resize(n);
-    cl->hpc_len.resize(n);
-    cl->nf.resize(n);
-    cl->nr.resize(n);
-    cl->score.resize(n);
-    cl->raw_err.resize(n);
     cudaStream_t st = ctx->stream;
-    if (n) {
-	ICB_CUDA(ctx, cudaMemcpyAsync(cl->status.data(), rs->d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	ICB_CUDA(ctx, cudaMemcpyAsync(cl->hpc_len.data(), rs->d_hpc_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	ICB_CUDA(ctx, cudaMemcpyAsync(cl->nf.data(), rs->d_nf, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	ICB_CUDA(ctx, cudaMemcpyAsync(cl->nr.data(), rs->d_nr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	ICB_CUDA(ctx, cudaMemcpyAsync(cl->score.data(), rs->d_score, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-	ICB_CUDA(ctx, cudaMemcpyAsync(cl->raw_err.data(), rs->d_err, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (!rs->host_ready) {
+	rs->h_status.resize(n);
+	rs->h_hpc_len.resize(n);
+	rs->h_nf.resize(n);
+	rs->h_nr.resize(n);
+	rs->h_score.resize(n);
+	rs->h_err.resize(n);
+	if (n) {
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_status.data(), rs->d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_hpc_len.data(), rs->d_hpc_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_nf.data(), rs->d_nf, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_nr.data(), rs->d_nr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_score.data(), rs->d_score, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_err.data(), rs->d_err, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	}
+	if (!rs->d_class) ICB_CUDA(ctx, cudaMalloc((void**)&rs->d_class, n + 16));
+	int rc0 = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, rs->d_class);
+	if (rc0) return rc0;
+	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+	rs->max_m = 0;
+	for (int64_t i = 0; i < n; i++) rs->max_m = std::max(rs->max_m, std::max(rs->h_nf[i], rs->h_nr[i]));
+	rs->host_ready = true;
     }
-    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_class, n + 16));
-    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_nmax, sizeof(int32_t) * 225));
-    ICB_CUDA(ctx, cudaMemcpyAsync(cl->d_nmax, cl->nmax, sizeof(int32_t) * 225, cudaMemcpyHostToDevice, st));
-    int rc = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, cl->d_class);
-    if (rc) return rc;
-    ICB_CUDA(ctx, cudaStreamSynchronize(st));
-    for (int64_t i = 0; i < n; i++) cl->max_m = std::max(cl->max_m, std::max(cl->nf[i], cl->nr[i]));
-    if (cl->max_m >= 32768) {
+    if (rs->max_m >= 32768) {
 	delete cl;
 	return ctx->fail(ICB_ERR_ARG, "a read has 32768 or more minimizers per strand");
     }
+    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_nmax, sizeof(int32_t) * 225));
+    ICB_CUDA(ctx, cudaMemcpyAsync(cl->d_nmax, cl->nmax, sizeof(int32_t) * 225, cudaMemcpyHostToDevice, st));
+    int rc = 0;
     const int cs = cl->P.chunk_size;
     cl->chunk_cap = cs;
     ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_chunk_reads, sizeof(int32_t) * cs));
@@ -570,7 +573,6 @@ void icb_clusterer_destroy(icb_clusterer* cl)
     cudaStreamSynchronize(cl->ctx->stream);
     cl->main_idx.destroy();
     cl->chunk_idx.destroy();
-    cudaFree(cl->d_class);
     cudaFree(cl->d_nmax);
     cudaFree(cl->d_cls_founder);
     cudaFree(cl->d_chunk_reads);
@@ -597,12 +599,12 @@ int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_
 	const int32_t r = order[s];
 	if (r < 0 || r >= cl->rs->n_reads) return ctx->fail(ICB_ERR_ARG, "read index outside the read set");
 	// the skips of ClusterSortedReads (cluster.cpp:116-160)
-	if (cl->status[r] != 1) continue;
-	if (cl->score[r] < 0) continue;
+	if (cl->rs->h_status[r] != 1) continue;
+	if (cl->rs->h_score[r] < 0) continue;
 	const int64_t L = cl->rs->h_offs[r + 1] - cl->rs->h_offs[r];
 	if (uint64_t(L) < uint64_t(unsigned(2 * P.kmer_size))) continue;
-	if (uint64_t(cl->hpc_len[r]) < uint64_t(unsigned(2 * P.kmer_size))) continue;
-	if ((-10 * std::log10(cl->raw_err[r])) <= P.min_qual) continue;
+	if (uint64_t(cl->rs->h_hpc_len[r]) < uint64_t(unsigned(2 * P.kmer_size))) continue;
+	if ((-10 * std::log10(cl->rs->h_err[r])) <= P.min_qual) continue;
 	chunk.push_back(r);
 	slots.push_back(s);
 	if (int(chunk.size()) == cl->chunk_cap) {

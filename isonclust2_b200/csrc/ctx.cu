@@ -226,6 +226,7 @@ void icb_readset_destroy(icb_readset* rs)
     cudaFree(rs->d_counters);
     cudaFree(rs->d_long_list);
     cudaFree(rs->d_long_scratch);
+    cudaFree(rs->d_class);
     delete rs;
 }
 

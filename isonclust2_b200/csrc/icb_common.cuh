@@ -82,6 +82,13 @@ struct icb_readset {
     int32_t* d_long_list = nullptr;
     uint8_t* d_long_scratch = nullptr;
     int64_t total_f = 0, total_r = 0;
+    // host mirror of the per-read scalars the greedy loop reads, and the device error classes (filled once,
+    // by the first clusterer created on this read set)
+    bool host_ready = false;
+    std::vector<int32_t> h_status, h_hpc_len, h_nf, h_nr;
+    std::vector<double> h_score, h_err;
+    int max_m = 0;
+    uint8_t* d_class = nullptr;
 };
 
 // stage launchers (defined in score.cu / sketch.cu)

@@ -325,13 +325,6 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
 
 // ---------------------------------------------------------------- host side of the index
 
-static int fill_u32(icb_ctx* ctx, uint32_t* p, uint32_t v, int64_t n)
-{
-    if (n <= 0) return ICB_OK;
-    ICB_LAUNCH(ctx, "fill_u32", icb_k_fill_u32<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(p, v, n));
-    return ICB_OK;
-}
-
 int IcbIndex::create(icb_ctx* c, uint32_t cap_pow2, int64_t node_cap)
 {
     ctx = c;

@@ -554,6 +554,7 @@ int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const doub
     rs->sk_k = k;
     rs->sk_w = w;
     rs->total_f = rs->total_r = -1;
+    rs->host_ready = false;
     return ICB_OK;
 }
 
