@@ -151,6 +151,8 @@ typedef struct {
     int64_t pairs_aligned; /* DP problems solved (>= what the reference solves: speculative pairs included) */
     int64_t cells_aligned;
     int64_t tie_fallbacks; /* reads whose outcome depended on the reference's candidate order */
+    int64_t decisions;	   /* evaluations of the per-read decision (>= reads: speculative re-evaluations) */
+    double ms_query, ms_full, ms_align, ms_insert, ms_host; /* host wall-clock split of icb_cluster_reads */
 } icb_cluster_stats;
 
 typedef struct icb_clusterer icb_clusterer;

@@ -14,8 +14,9 @@
 //                       (systolic wavefront, 3 shuffles per step).  Strip boundary rows live in an
 //                       L2-resident global line.  4 trace bits per cell are accumulated with funnel
 //                       shifts of sign bits and stored as full 32-byte sectors, one per 8x8 cell tile.
-//   icb_k_align_trace   one thread per pair walks the 8x8 tiles back from the end cell, feeding a k-bit
-//                       shift register whose popcount gives the per-window match count.
+//   traceback_warp      the same warp then walks the 8x8 tiles back from the end cell while they are still in
+//                       L2 (a 4x4-tile window and its 32+32 characters are held across the lanes), feeding a
+//                       k-bit shift register whose popcount gives the per-window match count.
 // Roofline class: integer ALU (GCUPS); trace traffic is 0.5 B/cell.
 #include <algorithm>
 #include <cstring>
@@ -64,10 +65,115 @@ __device__ __forceinline__ uint32_t shf_in(uint32_t acc, int signsrc)
     return __funnelshift_l(uint32_t(signsrc), acc, 1);
 }
 
+struct TraceState {
+    uint32_t reg, mask;
+    int k, limit;
+    long long pushed;
+    int aligned;
+    __device__ __forceinline__ void push(uint32_t bit)
+    {
+	reg = ((reg << 1) | bit) & mask;
+	// windows are counted from the (k+1)-th pushed column on: the reference never tests the last window
+	if (pushed >= k && __popc(reg) >= limit) aligned++;
+	pushed++;
+    }
+    __device__ void push_zeros(long long g)
+    {
+	long long first = g < k ? g : k;
+	for (long long t = 0; t < first; t++) push(0);
+	long long rest = g - first;
+	if (rest > 0) {
+	    // register is all zero now; every further column closes an all-blank window
+	    long long counted = rest;
+	    if (pushed < k) counted -= (k - pushed);
+	    if (counted > 0 && 0 >= limit) aligned += int(counted);
+	    pushed += rest;
+	}
+    }
+};
+
+
+// Traceback of one pair by a whole warp (lane-uniform control flow).  Mirrors parasail_result_get_traceback
+// (traceback_template.c:72-175) and feeds getAlnRatio's window count (cluster.cpp:442-459).
+__device__ icb_align_result traceback_warp(const uint8_t* __restrict__ seq, const PairDesc& d, const uint4* tr, int ncg,
+					   int k, int score, int ei, int ej)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = d.n, m = d.m;
+    TraceState st;
+    st.reg = 0;
+    st.mask = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+    st.k = k;
+    st.limit = d.limit;
+    st.pushed = 0;
+    st.aligned = 0;
+    int i = ei, j = ej;
+    // free tail (traceback_template.c:72-94)
+    if (i + 1 == n) st.push_zeros(m - 1 - j);
+    else st.push_zeros(n - 1 - i);
+    int where = 0;	 // 0 diag, 1 ins (consumes reference), 2 del (consumes query)
+    int ti0 = 1 << 28, tj0 = 1 << 28;  // window anchor (top-left tile), invalid at start
+    uint4 wt = make_uint4(0, 0, 0, 0);
+    uint32_t qc = 0, rc = 0;
+    const int u = lane >> 1, du = u >> 2, dv = u & 3, half = lane & 1;
+    while (i >= 0 || j >= 0) {
+	if (i < 0) {
+	    st.push_zeros(j + 1);
+	    break;
+	}
+	if (j < 0) {
+	    st.push_zeros(i + 1);
+	    break;
+	}
+	const int ti = i >> 3, tj = j >> 3;
+	if (ti < ti0 || ti > ti0 + 3 || tj < tj0 || tj > tj0 + 3) {
+	    // new window with the current tile in its bottom-right corner
+	    ti0 = ti - 3;
+	    tj0 = tj - 3;
+	    const int a = ti0 + du, b = tj0 + dv;
+	    if (a >= 0 && b >= 0) wt = __ldcg(tr + (int64_t(a) * ncg + b) * 2 + half);  // written by this kernel: L2, not the read-only path
+	    const int qi = ti0 * 8 + lane, rj = tj0 * 8 + lane;
+	    qc = (qi >= 0 && qi < n) ? up_char(seq[d.q_off + qi]) : 0u;
+	    rc = (rj >= 0 && rj < m) ? up_char(ref_char(seq, d, rj)) : 1u;
+	}
+	const int uu = (ti - ti0) * 4 + (tj - tj0), r = i & 7;
+	uint32_t comp = (r & 3) == 0 ? wt.x : (r & 3) == 1 ? wt.y : (r & 3) == 2 ? wt.z : wt.w;
+	const uint32_t word = __shfl_sync(0xffffffffu, comp, 2 * uu + (r >> 2));
+	const uint32_t nib = (word >> (4 * (7 - (j & 7)))) & 15u;
+	// nib bits: 8 = H != diagonal, 4 = H != F, 2 = DIAG_E, 1 = DIAG_F
+	if (where == 0) {
+	    if (!(nib & 8u)) {
+		uint32_t a = __shfl_sync(0xffffffffu, qc, i - ti0 * 8), b = __shfl_sync(0xffffffffu, rc, j - tj0 * 8);
+		st.push(a == b ? 1u : 0u);  // traceback.c match_char, case-insensitive
+		i--;
+		j--;
+	    }
+	    else if (nib & 4u) where = 1;  // neither diagonal nor F: INS (traceback_template.c:118-120)
+	    else where = 2;
+	}
+	else if (where == 1) {
+	    st.push(0);
+	    j--;
+	    where = (nib & 2u) ? 0 : 1;
+	}
+	else {
+	    st.push(0);
+	    i--;
+	    where = (nib & 1u) ? 0 : 2;
+	}
+    }
+    icb_align_result r;
+    r.aligned = st.pushed >= k ? st.aligned : 0;
+    r.score = score;
+    r.end_query = ei;
+    r.end_ref = ej;
+    r.comp_len = int(st.pushed);
+    return r;
+}
+
 __global__ void __launch_bounds__(AL_THREADS)
 icb_k_align_dp(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ descs, int n_pairs, uint4* __restrict__ trace,
-	       int* __restrict__ lines, int4* __restrict__ ends /* score, end_query, end_ref, pad */,
-	       unsigned long long* __restrict__ ticket)
+	       int* __restrict__ lines, int k, icb_align_result* __restrict__ out, unsigned long long* __restrict__ ticket)
 {
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -247,119 +353,17 @@ icb_k_align_dp(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ des
 		ci = oi;
 	    }
 	}
-	if (lane == 0) {
-	    int score = best, ei = n - 1, ej = bj;
-	    if (cbest > best || (cbest == best && bj == m - 1)) {
-		score = cbest;
-		ei = ci;
-		ej = m - 1;
-	    }
-	    ends[d.out] = make_int4(score, ei, ej, 0);
+	int score = best, ei = n - 1, ej = bj;
+	if (cbest > best || (cbest == best && bj == m - 1)) {
+	    score = cbest;
+	    ei = ci;
+	    ej = m - 1;
 	}
+	// ---- traceback by the same warp while the trace tiles are still in L2 (all lanes walk in lockstep; the
+	// tiles of a 4x4-tile window and the 32 query / reference characters it spans are held across the lanes)
+	icb_align_result res = traceback_warp(seq, d, tr, ncg, k, score, ei, ej);
+	if (lane == 0) out[d.out] = res;
     }
-}
-
-struct TraceState {
-    uint32_t reg, mask;
-    int k, limit;
-    long long pushed;
-    int aligned;
-    __device__ __forceinline__ void push(uint32_t bit)
-    {
-	reg = ((reg << 1) | bit) & mask;
-	// windows are counted from the (k+1)-th pushed column on: the reference never tests the last window
-	if (pushed >= k && __popc(reg) >= limit) aligned++;
-	pushed++;
-    }
-    __device__ void push_zeros(long long g)
-    {
-	long long first = g < k ? g : k;
-	for (long long t = 0; t < first; t++) push(0);
-	long long rest = g - first;
-	if (rest > 0) {
-	    // register is all zero now; every further column closes an all-blank window
-	    long long counted = rest;
-	    if (pushed < k) counted -= (k - pushed);
-	    if (counted > 0 && 0 >= limit) aligned += int(counted);
-	    pushed += rest;
-	}
-    }
-};
-
-__global__ void __launch_bounds__(64)
-icb_k_align_trace(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ descs, int n_pairs, const uint4* __restrict__ trace,
-		  const int4* __restrict__ ends, int k, icb_align_result* __restrict__ out)
-{
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    const PairDesc d = descs[p];
-    const int n = d.n, m = d.m;
-    const int4 e = ends[d.out];
-    const int ncg = (m + 7) >> 3;
-    const uint4* tr = trace + d.trace_off * 2;
-    TraceState st;
-    st.reg = 0;
-    st.mask = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
-    st.k = k;
-    st.limit = d.limit;
-    st.pushed = 0;
-    st.aligned = 0;
-    int i = e.y, j = e.z;
-    // free tail (traceback_template.c:72-94)
-    if (i + 1 == n) st.push_zeros(m - 1 - j);
-    else st.push_zeros(n - 1 - i);
-    int where = 0;  // 0 diag, 1 ins (consumes reference), 2 del (consumes query)
-    long long tile = -1;
-    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    while (i >= 0 || j >= 0) {
-	if (i < 0) {
-	    st.push_zeros(j + 1);
-	    break;
-	}
-	if (j < 0) {
-	    st.push_zeros(i + 1);
-	    break;
-	}
-	long long t = (long long)(i >> 3) * ncg + (j >> 3);
-	if (t != tile) {
-	    uint4 x = tr[t * 2], y = tr[t * 2 + 1];
-	    w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
-	    w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
-	    tile = t;
-	}
-	uint32_t word = w[0];
-#pragma unroll
-	for (int r = 1; r < 8; r++) word = ((i & 7) == r) ? w[r] : word;
-	uint32_t nib = (word >> (4 * (7 - (j & 7)))) & 15u;
-	// nib bits: 8 = H != diagonal, 4 = H != F, 2 = DIAG_E, 1 = DIAG_F
-	if (where == 0) {
-	    if (!(nib & 8u)) {
-		uint32_t a = up_char(seq[d.q_off + i]), b = up_char(ref_char(seq, d, j));  // traceback.c match_char, case-insensitive
-		st.push(a == b ? 1u : 0u);
-		i--;
-		j--;
-	    }
-	    else if (nib & 4u) where = 1;  // neither diagonal nor F: INS (traceback_template.c:118-120)
-	    else where = 2;
-	}
-	else if (where == 1) {
-	    st.push(0);
-	    j--;
-	    where = (nib & 2u) ? 0 : 1;
-	}
-	else {
-	    st.push(0);
-	    i--;
-	    where = (nib & 1u) ? 0 : 2;
-	}
-    }
-    icb_align_result r;
-    r.aligned = st.pushed >= k ? st.aligned : 0;
-    r.score = e.x;
-    r.end_query = e.y;
-    r.end_ref = e.z;
-    r.comp_len = int(st.pushed);
-    out[d.out] = r;
 }
 
 }  // namespace
@@ -415,13 +419,11 @@ int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int
 	}
 	uint4* d_trace = nullptr;
 	int* d_lines = nullptr;
-	int4* d_ends = nullptr;
 	PairDesc* d_descs = nullptr;
 	icb_align_result* d_out = nullptr;
 	unsigned long long* d_ticket = nullptr;
 	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_trace, size_t(sectors) * 32 + 64, st));
 	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_lines, size_t(ints) * 4 + 64, st));
-	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_ends, sizeof(int4) * n_pairs, st));
 	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_descs, sizeof(PairDesc) * cnt, st));
 	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_out, sizeof(icb_align_result) * n_pairs, st));
 	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_ticket, 8, st));
@@ -432,10 +434,7 @@ int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int
 	if (warps > maxw) warps = maxw;
 	unsigned grid = unsigned((warps + AL_WARPS - 1) / AL_WARPS);
 	ICB_LAUNCH(ctx, "align_dp",
-		   icb_k_align_dp<<<grid, AL_THREADS, 0, st>>>(rs->d_seq, d_descs, int(cnt), d_trace, d_lines, d_ends, d_ticket));
-	ICB_LAUNCH(ctx, "align_trace",
-		   icb_k_align_trace<<<unsigned((cnt + 63) / 64), 64, 0, st>>>(rs->d_seq, d_descs, int(cnt), d_trace, d_ends,
-									      kmer_size, d_out));
+		   icb_k_align_dp<<<grid, AL_THREADS, 0, st>>>(rs->d_seq, d_descs, int(cnt), d_trace, d_lines, kmer_size, d_out, d_ticket));
 	// results are indexed by the caller's pair index (d.out); copy the touched range pair by pair is wasteful,
 	// so stage the whole array once per launch and pick this launch's slots
 	std::vector<icb_align_result> tmp(n_pairs);
@@ -444,7 +443,6 @@ int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int
 	for (auto& d : batch) results[d.out] = tmp[d.out];
 	ICB_CUDA(ctx, cudaFreeAsync(d_trace, st));
 	ICB_CUDA(ctx, cudaFreeAsync(d_lines, st));
-	ICB_CUDA(ctx, cudaFreeAsync(d_ends, st));
 	ICB_CUDA(ctx, cudaFreeAsync(d_descs, st));
 	ICB_CUDA(ctx, cudaFreeAsync(d_out, st));
 	ICB_CUDA(ctx, cudaFreeAsync(d_ticket, st));

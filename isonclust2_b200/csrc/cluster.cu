@@ -11,6 +11,7 @@
 // alignments — is computed on the device per CHUNK of reads, speculatively where the sequential dependency
 // demands it (see index.cu), and consumed here in order.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -39,7 +40,18 @@ struct AlnKey {
     }
 };
 
-enum Outcome { OUT_JOIN, OUT_NEW, OUT_NEED };
+enum Outcome { OUT_JOIN, OUT_NEW, OUT_NEED, OUT_NONE };
+
+struct Stopwatch {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double lap()
+    {
+	auto t1 = std::chrono::steady_clock::now();
+	double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+	t0 = t1;
+	return ms;
+    }
+};
 
 }  // namespace
 
@@ -192,6 +204,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     const int k = P.kmer_size;
     const int CAP = 64;
     stats.chunks++;
+    Stopwatch sw;
     // ---- chunk index: every read of the chunk as a provisional founder (id = C0 + position)
     ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, chunk.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
     {
@@ -210,6 +223,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	if (rc) return rc;
 	chunk_idx.nodes_upper = tot;
     }
+    stats.ms_insert += sw.lap();
     // ---- candidates of every read against snapshot + provisional founders
     std::vector<IcbQueryHeader> hdr;
     std::vector<IcbCand> cands;
@@ -233,7 +247,11 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    cl[over[t]].assign(c2.begin() + int64_t(t) * cap2, c2.begin() + int64_t(t) * cap2 + h2[t].n_cand);
     }
 
+    stats.ms_query += sw.lap();
     std::vector<int> founder_cls(N, -1);  // provisional founder -> real cluster id once committed
+    std::vector<int> eval_version(N, -1);  // founders committed in this chunk when the read was last evaluated
+    std::vector<char> eval_outcome(N, OUT_NONE);
+    int version = 0;
     std::vector<char> committed(N, 0);
     std::map<AlnKey, int> aln;		   // alignment results (aligned window count)
     std::map<int, std::vector<IcbCand>> full;  // full candidate lists for tie reads
@@ -271,8 +289,9 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 
     // decision for the read at `pos` given the founders committed so far.  Returns OUT_NEED when device work is
     // missing (alignment pairs appended to needPairs, tie reads to needFull).
-    auto decide = [&](int pos, int& outCls, int& outStrand, std::vector<AlnKey>& needPairs, std::vector<int32_t>& needFull,
-		      bool countStats) -> Outcome {
+    bool usedAln = false, usedTie = false;
+    auto decide = [&](int pos, int& outCls, int& outStrand, std::vector<AlnKey>& needPairs, std::vector<int32_t>& needFull) -> Outcome {
+	usedAln = usedTie = false;
 	const int r = chunk[pos];
 	std::vector<IcbCand> v;
 	int top = hdr[pos].top_snap;
@@ -313,7 +332,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 			needFull.push_back(pos);
 			return OUT_NEED;
 		    }
-		    if (countStats) stats.tie_fallbacks++;
+		    usedTie = true;
 		    auto order = reference_order(pos, it->second);
 		    for (auto& o : order) {
 			for (auto* p : pass)
@@ -343,7 +362,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    }
 	}
 	if (missing) return OUT_NEED;
-	if (countStats) stats.aln_invoked++;
+	usedAln = true;
 	const unsigned readLen = unsigned(rs->h_offs[r + 1] - rs->h_offs[r]);
 	std::vector<const IcbCand*> pass;
 	for (auto* c : tied) {
@@ -361,7 +380,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    needFull.push_back(pos);
 	    return OUT_NEED;
 	}
-	if (countStats) stats.tie_fallbacks++;
+	usedTie = true;
 	auto order = reference_order(pos, it->second);
 	for (auto& o : order) {
 	    for (auto* p : pass)
@@ -383,7 +402,13 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    int c, s;
 	    std::vector<AlnKey> np;
 	    std::vector<int32_t> nfull;
-	    Outcome o = decide(pos, c, s, np, nfull, !speculative);
+	    // a read already evaluated against the same set of founders, and not waiting for device work, cannot
+	    // contribute anything new while reads before it are still pending
+	    if (speculative && eval_version[pos] == version && eval_outcome[pos] != OUT_NEED) continue;
+	    Outcome o = decide(pos, c, s, np, nfull);
+	    stats.decisions++;
+	    eval_version[pos] = version;
+	    eval_outcome[pos] = char(o);
 	    if (o == OUT_NEED) {
 		speculative = true;  // later reads are only scanned for the device work they will need
 		needPairs.insert(needPairs.end(), np.begin(), np.end());
@@ -392,8 +417,11 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    }
 	    if (speculative) continue;
 	    // commit in order
+	    if (usedAln) stats.aln_invoked++;
+	    if (usedTie) stats.tie_fallbacks++;
 	    if (o == OUT_NEW) {
 		founder_cls[pos] = nextCls;
+		version++;
 		founder.push_back(chunk[pos]);
 		cluster_of[slots[pos]] = nextCls;
 		strand_of[slots[pos]] = 1;
@@ -406,6 +434,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    committed[pos] = 1;
 	    commit_pos = pos + 1;
 	}
+	stats.ms_host += sw.lap();
 	if (commit_pos >= N) break;
 	if (needPairs.empty() && needFull.empty()) return ctx->fail(ICB_ERR_STATE, "greedy loop made no progress");
 	if (!needFull.empty()) {
@@ -418,6 +447,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    if (rc) return rc;
 	    for (size_t t = 0; t < needFull.size(); t++)
 		full[needFull[t]].assign(c2.begin() + foff[t], c2.begin() + foff[t] + h2[t].n_cand);
+	    stats.ms_full += sw.lap();
 	}
 	if (!needPairs.empty()) {
 	    std::sort(needPairs.begin(), needPairs.end());
@@ -447,6 +477,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 		stats.cells_aligned += int64_t(rs->h_offs[pairs[t].read + 1] - rs->h_offs[pairs[t].read]) *
 				       int64_t(rs->h_offs[pairs[t].rep + 1] - rs->h_offs[pairs[t].rep]);
 	    }
+	    stats.ms_align += sw.lap();
 	}
     }
     // ---- AddMinimizers for the clusters founded in this chunk (cluster.cpp:178-180)
@@ -480,6 +511,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	main_idx.nodes_upper += tot;
 	ICB_CUDA(ctx, cudaStreamSynchronize(st));
     }
+    stats.ms_insert += sw.lap();
     return ICB_OK;
 }
 

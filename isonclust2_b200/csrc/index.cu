@@ -70,30 +70,51 @@ __device__ __forceinline__ void for_each_posting(const IcbIndexView& ix, uint32_
 }
 
 // one CTA per founder: one node per DISTINCT forward minimizer value (the reference's `cls > back()` test keeps
-// a cluster once per posting list)
+// a cluster once per posting list).  Node slots are claimed once per 128 minimizers (one atomic per CTA tile,
+// not per node: a single global counter would serialise in L2).
 __global__ void __launch_bounds__(Q_THREADS)
 icb_k_index_insert(IcbIndexView ix, const icb_minimizer* __restrict__ arena, const int64_t* __restrict__ min_off,
 		   const int32_t* __restrict__ nf, const int32_t* __restrict__ reads, const int32_t* __restrict__ ids, int n)
 {
+    __shared__ int s_w[Q_THREADS / 32];
+    __shared__ uint32_t s_base;
     int b = blockIdx.x;
     if (b >= n) return;
     const int r = reads[b];
     const uint32_t id = uint32_t(ids[b]);
     const int M = nf[r];
     const icb_minimizer* m = arena + min_off[r];
-    for (int i = threadIdx.x; i < M; i += Q_THREADS) {
-	const uint32_t v = m[i].Min;
-	bool dup = false;
-	for (int j = 0; j < i; j++)
-	    if (m[j].Min == v) {
-		dup = true;
-		break;
-	    }
-	if (dup) continue;
-	uint32_t s = claim_slot(ix, v);
-	uint32_t nid = atomicAdd(ix.node_count, 1u);
-	uint32_t old = atomicExch(&ix.heads[s], nid);
-	ix.nodes[nid] = make_uint2(id, old);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < M; i0 += Q_THREADS) {
+	const int i = i0 + threadIdx.x;
+	uint32_t v = 0;
+	bool fresh = false;
+	if (i < M) {
+	    v = m[i].Min;
+	    fresh = true;
+	    for (int j = 0; j < i; j++)
+		if (m[j].Min == v) {
+		    fresh = false;
+		    break;
+		}
+	}
+	const uint32_t bal = __ballot_sync(0xffffffffu, fresh);
+	if (lane == 0) s_w[warp] = __popc(bal);
+	__syncthreads();
+	int before = 0, total = 0;
+	for (int w = 0; w < Q_THREADS / 32; w++) {
+	    if (w < warp) before += s_w[w];
+	    total += s_w[w];
+	}
+	if (threadIdx.x == 0) s_base = atomicAdd(ix.node_count, uint32_t(total));
+	__syncthreads();
+	if (fresh) {
+	    const uint32_t nid = s_base + uint32_t(before + __popc(bal & ((1u << lane) - 1u)));
+	    const uint32_t s = claim_slot(ix, v);
+	    const uint32_t old = atomicExch(&ix.heads[s], nid);
+	    ix.nodes[nid] = make_uint2(id, old);
+	}
+	__syncthreads();
     }
 }
 

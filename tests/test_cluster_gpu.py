@@ -109,9 +109,9 @@ def test_cluster_params_variants(port, ctx):
 def test_cluster_no_pemp_row(ctx):
     seq, qual, offs = synth.make_reads(20, seed=55, min_len=300, max_len=400)
     rs = ctx.upload(seq, qual, offs)
-    rs.score(12)
-    rs.sketch_async(12, 47)  # no (k=12, w=47+-2) row in the empirical table
+    rs.score(31)
+    rs.sketch_async(31, 40)  # the empirical table covers k = 10..30 only
     with pytest.raises(api.IcbError) as ei:
-        api.Clusterer(rs, 12, 47, mode="sahlin")
+        api.Clusterer(rs, 31, 40, mode="sahlin", p_shared=pemp.load_p_shared(31, 40))
     assert ei.value.code == -4
     rs.close()
