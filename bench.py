@@ -29,7 +29,7 @@ K, W_, MIN_QUAL, MODE = 11, 15, 7.0, "sahlin"
 BATCH_KB, BATCH_MAX_SEQ = 50000, 30000  # CmdArgs defaults (args.h:14-15)
 METRIC = "reads/sec clustered (sahlin)"
 KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_full", "index_insert", "align_dp",
-           "align_trace", "classify_errors", "index_rehash", "sketch_reads_long", "gather_minimizers")
+           "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "gather_minimizers")
 
 
 def clocks_sampler(stop, out, device):

@@ -22,7 +22,7 @@
 #include <cstring>
 #include <numeric>
 
-#include "icb_common.cuh"
+#include "align.cuh"
 
 namespace {
 
@@ -32,81 +32,27 @@ constexpr int ROWS = 8;		     // rows per lane
 constexpr int STRIP = 32 * ROWS;     // rows per strip
 constexpr int NEG = -(1 << 29);
 
-struct PairDesc {
-    int64_t q_off, r_off;   // byte offsets of read / representative in the sequence buffer
-    int32_t n, m;	    // lengths (query rows, reference columns)
-    int32_t rc;		    // representative is taken reverse-complemented
-    int32_t open;	    // gap open
-    int32_t limit;	    // window counts if matches >= limit
-    int32_t out;	    // slot in the result array
-    int64_t trace_off;	    // in 32-byte sectors
-    int64_t line_off;	    // in ints: boundary line (2*m), last row (m), last column (n rounded to 8)
-};
-
 // A,C,G,T (either case) -> 0..3, anything else -> 4
 __device__ __forceinline__ int base_code(uint32_t c)
 {
     c &= 0xdfu;	 // upper-case
     return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
 }
-// upper-cased character of the reference string as parasail sees it (RevComp applied when rc)
-__device__ __forceinline__ uint32_t ref_char(const uint8_t* __restrict__ seq, const PairDesc& d, int j)
-{
-    if (!d.rc) return seq[d.r_off + j];
-    uint32_t c = seq[d.r_off + (d.m - 1 - j)];
-    return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;  // util.cpp:13-38 (ACGT only reaches here)
-}
-
-__device__ __forceinline__ uint32_t up_char(uint32_t c) { return (c >= 'a' && c <= 'z') ? c - 32u : c; }
-
 __device__ __forceinline__ uint32_t shf_in(uint32_t acc, int signsrc)
 {
     // acc = (acc << 1) | (signsrc < 0)
     return __funnelshift_l(uint32_t(signsrc), acc, 1);
 }
 
-struct TraceState {
-    uint32_t reg, mask;
-    int k, limit;
-    long long pushed;
-    int aligned;
-    __device__ __forceinline__ void push(uint32_t bit)
-    {
-	reg = ((reg << 1) | bit) & mask;
-	// windows are counted from the (k+1)-th pushed column on: the reference never tests the last window
-	if (pushed >= k && __popc(reg) >= limit) aligned++;
-	pushed++;
-    }
-    __device__ void push_zeros(long long g)
-    {
-	long long first = g < k ? g : k;
-	for (long long t = 0; t < first; t++) push(0);
-	long long rest = g - first;
-	if (rest > 0) {
-	    // register is all zero now; every further column closes an all-blank window
-	    long long counted = rest;
-	    if (pushed < k) counted -= (k - pushed);
-	    if (counted > 0 && 0 >= limit) aligned += int(counted);
-	    pushed += rest;
-	}
-    }
-};
-
-
 // Traceback of one pair by a whole warp (lane-uniform control flow).  Mirrors parasail_result_get_traceback
 // (traceback_template.c:72-175) and feeds getAlnRatio's window count (cluster.cpp:442-459).
-__device__ icb_align_result traceback_warp(const uint8_t* __restrict__ seq, const PairDesc& d, const uint4* tr, int ncg,
+__device__ icb_align_result traceback_warp(const uint8_t* __restrict__ seq, const IcbPairDesc& d, const uint4* tr, int ncg,
 					   int k, int score, int ei, int ej)
 {
     const int lane = threadIdx.x & 31;
     const int n = d.n, m = d.m;
-    TraceState st;
-    st.reg = 0;
-    st.mask = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
-    st.k = k;
-    st.limit = d.limit;
-    st.pushed = 0;
-    st.aligned = 0;
+    IcbWindowCounter st;
+    st.init(k, d.limit);
     int i = ei, j = ej;
     // free tail (traceback_template.c:72-94)
     if (i + 1 == n) st.push_zeros(m - 1 - j);
@@ -133,8 +79,8 @@ __device__ icb_align_result traceback_warp(const uint8_t* __restrict__ seq, cons
 	    const int a = ti0 + du, b = tj0 + dv;
 	    if (a >= 0 && b >= 0) wt = __ldcg(tr + (int64_t(a) * ncg + b) * 2 + half);  // written by this kernel: L2, not the read-only path
 	    const int qi = ti0 * 8 + lane, rj = tj0 * 8 + lane;
-	    qc = (qi >= 0 && qi < n) ? up_char(seq[d.q_off + qi]) : 0u;
-	    rc = (rj >= 0 && rj < m) ? up_char(ref_char(seq, d, rj)) : 1u;
+	    qc = (qi >= 0 && qi < n) ? icb_up_char(seq[d.q_off + qi]) : 0u;
+	    rc = (rj >= 0 && rj < m) ? icb_up_char(icb_ref_char(seq, d, rj)) : 1u;
 	}
 	const int uu = (ti - ti0) * 4 + (tj - tj0), r = i & 7;
 	uint32_t comp = (r & 3) == 0 ? wt.x : (r & 3) == 1 ? wt.y : (r & 3) == 2 ? wt.z : wt.w;
@@ -172,7 +118,7 @@ __device__ icb_align_result traceback_warp(const uint8_t* __restrict__ seq, cons
 }
 
 __global__ void __launch_bounds__(AL_THREADS)
-icb_k_align_dp(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ descs, int n_pairs, uint4* __restrict__ trace,
+icb_k_align32_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, int n_pairs, uint4* __restrict__ trace,
 	       int* __restrict__ lines, int k, icb_align_result* __restrict__ out, unsigned long long* __restrict__ ticket)
 {
     const int lane = threadIdx.x & 31;
@@ -181,7 +127,7 @@ icb_k_align_dp(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ des
 	if (lane == 0) p = int(atomicAdd(ticket, 1ull));
 	p = __shfl_sync(0xffffffffu, p, 0);
 	if (p >= n_pairs) break;
-	const PairDesc d = descs[p];
+	const IcbPairDesc d = descs[p];
 	const int n = d.n, m = d.m, o = d.open;
 	int* bound = lines + d.line_off;	   // (H,F) of the strip's bottom row per column
 	int* lastrow = bound + 2 * m;		   // H[n-1][j]
@@ -220,7 +166,7 @@ icb_k_align_dp(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ des
 		if ((s & 31) == 0) {
 		    int jj = s + lane;
 		    if (jj < m) {
-			pre_b = base_code(ref_char(seq, d, jj));
+			pre_b = base_code(icb_ref_char(seq, d, jj));
 			if (strip > 0) {
 			    pre_h = bound[2 * jj];
 			    pre_f = bound[2 * jj + 1];
@@ -368,26 +314,134 @@ icb_k_align_dp(const uint8_t* __restrict__ seq, const PairDesc* __restrict__ des
 
 }  // namespace
 
-extern "C" {
+// ------------------------------------------------------------------------------------------------ host side
 
-int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size, icb_align_result* results)
+int IcbAlignWorkspace::ensure(icb_ctx* ctx, size_t trace_need, size_t lines_need, int64_t pairs_need)
 {
-    if (!rs || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results))) return ICB_ERR_ARG;
-    icb_ctx* ctx = rs->ctx;
-    if (kmer_size < 1 || kmer_size > 32) return ctx->fail(ICB_ERR_ARG, "kmer_size must be in [1,32]");
-    if (n_pairs == 0) return ICB_OK;
-    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // growth happens a handful of times per context; steady state allocates nothing
+    if (trace_need > trace_bytes) {
+	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_trace);
+	d_trace = nullptr;
+	trace_bytes = 0;
+	size_t want = std::max(trace_need + trace_need / 4, size_t(64) << 20);
+	ICB_CUDA(ctx, cudaMalloc((void**)&d_trace, want));
+	trace_bytes = want;
+    }
+    if (lines_need > lines_bytes) {
+	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_lines);
+	d_lines = nullptr;
+	lines_bytes = 0;
+	size_t want = std::max(lines_need * 2, size_t(4) << 20);
+	ICB_CUDA(ctx, cudaMalloc((void**)&d_lines, want));
+	lines_bytes = want;
+    }
+    if (pairs_need > pair_cap) {
+	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_descs);
+	cudaFree(d_ends);
+	cudaFree(d_out);
+	cudaFreeHost(h_descs);
+	cudaFreeHost(h_out);
+	cudaFreeHost(h_ends);
+	d_descs = nullptr;
+	d_ends = nullptr;
+	d_out = nullptr;
+	h_descs = nullptr;
+	h_out = nullptr;
+	h_ends = nullptr;
+	pair_cap = 0;
+	int64_t want = std::max<int64_t>(pairs_need * 2, 4096);
+	ICB_CUDA(ctx, cudaMalloc((void**)&d_descs, sizeof(IcbPairDesc) * want));
+	ICB_CUDA(ctx, cudaMalloc((void**)&d_ends, sizeof(IcbAlignEnd) * want));
+	ICB_CUDA(ctx, cudaMalloc((void**)&d_out, sizeof(icb_align_result) * want));
+	ICB_CUDA(ctx, cudaMallocHost((void**)&h_descs, sizeof(IcbPairDesc) * want));
+	ICB_CUDA(ctx, cudaMallocHost((void**)&h_out, sizeof(icb_align_result) * want));
+	ICB_CUDA(ctx, cudaMallocHost((void**)&h_ends, sizeof(IcbAlignEnd) * want));
+	pair_cap = want;
+    }
+    if (!d_ticket) ICB_CUDA(ctx, cudaMalloc((void**)&d_ticket, 64));
+    return ICB_OK;
+}
+
+void IcbAlignWorkspace::release()
+{
+    cudaFree(d_trace);
+    cudaFree(d_lines);
+    cudaFree(d_descs);
+    cudaFree(d_ends);
+    cudaFree(d_out);
+    cudaFree(d_ticket);
+    cudaFreeHost(h_descs);
+    cudaFreeHost(h_out);
+    cudaFreeHost(h_ends);
+    *this = IcbAlignWorkspace();
+}
+
+int icb_align32_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, const IcbPairDesc* descs, int64_t cnt,
+		    int64_t tiles, int64_t line_words, int k)
+{
+    if (cnt <= 0) return ICB_OK;
     cudaStream_t st = ctx->stream;
-    // descriptors, largest matrices first (longest-processing-time order over the persistent warps)
-    std::vector<PairDesc> descs(n_pairs);
-    const int64_t budget_sectors = (int64_t(6) << 30) / 32;  // trace arena per launch: 6 GiB
-    std::vector<int64_t> order(n_pairs);
-    std::iota(order.begin(), order.end(), 0);
-    for (int64_t p = 0; p < n_pairs; p++) {
+    int rc = ws.ensure(ctx, size_t(tiles) * 32 + 64, size_t(line_words) * 4 + 64, cnt);
+    if (rc) return rc;
+    ICB_CUDA(ctx, cudaMemsetAsync(ws.d_ticket, 0, 8, st));
+    ICB_CUDA(ctx, cudaMemcpyAsync(ws.d_descs, descs, sizeof(IcbPairDesc) * cnt, cudaMemcpyHostToDevice, st));
+    int64_t warps = std::min<int64_t>(cnt, int64_t(ctx->sm_count) * 16);
+    unsigned grid = unsigned((warps + AL_WARPS - 1) / AL_WARPS);
+    ICB_LAUNCH(ctx, "align_dp32",
+	       icb_k_align32_dp<<<grid, AL_THREADS, 0, st>>>(d_seq, ws.d_descs, int(cnt), reinterpret_cast<uint4*>(ws.d_trace), ws.d_lines,
+							       k, ws.d_out, ws.d_ticket));
+    return ICB_OK;
+}
+
+namespace {
+
+constexpr int64_t LIMIT16 = 8000;			  // align16: H + 2j + 64 must stay below 2^15
+constexpr int64_t TRACE_BUDGET_TILES = (int64_t(4) << 30) / 32;  // trace arena per launch: 4 GiB
+
+struct Launch {
+    std::vector<IcbPairDesc> descs;
+    std::vector<int64_t> slot;	// caller's result index of each desc
+    int64_t tiles = 0, words = 0;
+    int max_m = 0;
+};
+
+// run one launch on the chosen back end and scatter its results; pairs the packed kernel refused are appended to `redo`
+int run_launch(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, Launch& L, bool fast, int k, icb_align_result* results,
+	       std::vector<int64_t>* redo)
+{
+    const int64_t cnt = int64_t(L.descs.size());
+    if (cnt == 0) return ICB_OK;
+    cudaStream_t st = ctx->stream;
+    int rc = ws.ensure(ctx, size_t(L.tiles) * 32 + 64, size_t(L.words) * 4 + 64, cnt);
+    if (rc) return rc;
+    memcpy(ws.h_descs, L.descs.data(), sizeof(IcbPairDesc) * cnt);
+    rc = fast ? icb_align16_run(ctx, ws, d_seq, ws.h_descs, cnt, L.tiles, L.words, L.max_m, k)
+	      : icb_align32_run(ctx, ws, d_seq, ws.h_descs, cnt, L.tiles, L.words, k);
+    if (rc) return rc;
+    ICB_CUDA(ctx, cudaMemcpyAsync(ws.h_out, ws.d_out, sizeof(icb_align_result) * cnt, cudaMemcpyDeviceToHost, st));
+    ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < cnt; i++) {
+	if (fast && ws.h_out[i].comp_len < 0) redo->push_back(L.slot[i]);
+	else results[L.slot[i]] = ws.h_out[i];
+    }
+    return ICB_OK;
+}
+
+}  // namespace
+
+int icb_align_pairs_on(icb_ctx* ctx, icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size,
+		       icb_align_result* results)
+{
+    if (n_pairs == 0) return ICB_OK;
+    if (!ctx->align_ws) ctx->align_ws = new IcbAlignWorkspace;
+    IcbAlignWorkspace& ws = *ctx->align_ws;
+    auto make_desc = [&](int64_t p, IcbPairDesc& d) -> int {
 	const icb_pair& q = pairs[p];
 	if (q.read < 0 || q.read >= rs->n_reads || q.rep < 0 || q.rep >= rs->n_reads)
 	    return ctx->fail(ICB_ERR_ARG, "pair index outside the read set");
-	PairDesc& d = descs[p];
 	d.q_off = rs->h_offs[q.read];
 	d.r_off = rs->h_offs[q.rep];
 	d.n = int32_t(rs->h_offs[q.read + 1] - rs->h_offs[q.read]);
@@ -396,59 +450,80 @@ int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int
 	d.rc = q.strand == -1;
 	d.open = q.gap_open;
 	d.limit = q.limit;
-	d.out = int32_t(p);
+	d.pad = 0;
+	return ICB_OK;
+    };
+    // largest matrices first (longest-processing-time order over the SMs)
+    std::vector<int64_t> fast, slow;
+    std::vector<IcbPairDesc> all(n_pairs);
+    for (int64_t p = 0; p < n_pairs; p++) {
+	int rc = make_desc(p, all[p]);
+	if (rc) return rc;
+	const bool ok16 = std::max(all[p].n, all[p].m) <= LIMIT16 && all[p].open >= 1 && all[p].open <= 16;
+	(ok16 ? fast : slow).push_back(p);
     }
-    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
-	return int64_t(descs[x].n) * descs[x].m > int64_t(descs[y].n) * descs[y].m;
-    });
-    int64_t done = 0;
-    while (done < n_pairs) {
-	// take as many pairs as fit the trace budget
-	int64_t sectors = 0, ints = 0, cnt = 0;
-	std::vector<PairDesc> batch;
-	while (done + cnt < n_pairs) {
-	    PairDesc d = descs[order[done + cnt]];
-	    int64_t s = int64_t((d.n + 7) / 8) * ((d.m + 7) / 8);
-	    if (cnt > 0 && sectors + s > budget_sectors) break;
-	    d.trace_off = sectors;
-	    d.line_off = ints;
-	    sectors += s;
-	    ints += 3 * int64_t(d.m) + ((d.n + 7) & ~7) + 8;
-	    batch.push_back(d);
-	    cnt++;
+    auto by_cells = [&](int64_t x, int64_t y) { return int64_t(all[x].n) * all[x].m > int64_t(all[y].n) * all[y].m; };
+    std::sort(fast.begin(), fast.end(), by_cells);
+    // ---- packed 16-bit path
+    {
+	size_t done = 0;
+	while (done < fast.size()) {
+	    Launch L;
+	    while (done < fast.size()) {
+		IcbPairDesc d = all[fast[done]];
+		d.ncg = (d.m + 71) >> 3;
+		const int64_t t = int64_t((d.n + 7) >> 3) * d.ncg;
+		if (!L.descs.empty() && L.tiles + t > TRACE_BUDGET_TILES) break;
+		d.trace_off = L.tiles;
+		d.line_off = L.words;
+		d.out = int32_t(L.descs.size());
+		L.tiles += t;
+		L.words += d.m + 8;
+		L.max_m = std::max(L.max_m, d.m);
+		L.descs.push_back(d);
+		L.slot.push_back(fast[done]);
+		done++;
+	    }
+	    int rc = run_launch(ctx, ws, rs->d_seq, L, true, kmer_size, results, &slow);
+	    if (rc) return rc;
 	}
-	uint4* d_trace = nullptr;
-	int* d_lines = nullptr;
-	PairDesc* d_descs = nullptr;
-	icb_align_result* d_out = nullptr;
-	unsigned long long* d_ticket = nullptr;
-	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_trace, size_t(sectors) * 32 + 64, st));
-	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_lines, size_t(ints) * 4 + 64, st));
-	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_descs, sizeof(PairDesc) * cnt, st));
-	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_out, sizeof(icb_align_result) * n_pairs, st));
-	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_ticket, 8, st));
-	ICB_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, 8, st));
-	ICB_CUDA(ctx, cudaMemcpyAsync(d_descs, batch.data(), sizeof(PairDesc) * cnt, cudaMemcpyHostToDevice, st));
-	int64_t warps = cnt;
-	int64_t maxw = int64_t(ctx->sm_count) * 16;
-	if (warps > maxw) warps = maxw;
-	unsigned grid = unsigned((warps + AL_WARPS - 1) / AL_WARPS);
-	ICB_LAUNCH(ctx, "align_dp",
-		   icb_k_align_dp<<<grid, AL_THREADS, 0, st>>>(rs->d_seq, d_descs, int(cnt), d_trace, d_lines, kmer_size, d_out, d_ticket));
-	// results are indexed by the caller's pair index (d.out); copy the touched range pair by pair is wasteful,
-	// so stage the whole array once per launch and pick this launch's slots
-	std::vector<icb_align_result> tmp(n_pairs);
-	ICB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_out, sizeof(icb_align_result) * n_pairs, cudaMemcpyDeviceToHost, st));
-	ICB_CUDA(ctx, cudaStreamSynchronize(st));
-	for (auto& d : batch) results[d.out] = tmp[d.out];
-	ICB_CUDA(ctx, cudaFreeAsync(d_trace, st));
-	ICB_CUDA(ctx, cudaFreeAsync(d_lines, st));
-	ICB_CUDA(ctx, cudaFreeAsync(d_descs, st));
-	ICB_CUDA(ctx, cudaFreeAsync(d_out, st));
-	ICB_CUDA(ctx, cudaFreeAsync(d_ticket, st));
-	done += cnt;
+    }
+    // ---- 32-bit path: very long sequences, characters outside ACGT
+    std::sort(slow.begin(), slow.end(), by_cells);
+    {
+	size_t done = 0;
+	while (done < slow.size()) {
+	    Launch L;
+	    while (done < slow.size()) {
+		IcbPairDesc d = all[slow[done]];
+		d.ncg = (d.m + 7) >> 3;
+		const int64_t t = int64_t((d.n + 7) >> 3) * d.ncg;
+		if (!L.descs.empty() && L.tiles + t > TRACE_BUDGET_TILES) break;
+		d.trace_off = L.tiles;
+		d.line_off = L.words;
+		d.out = int32_t(L.descs.size());
+		L.tiles += t;
+		L.words += 3 * int64_t(d.m) + ((d.n + 7) & ~7) + 8;
+		L.descs.push_back(d);
+		L.slot.push_back(slow[done]);
+		done++;
+	    }
+	    int rc = run_launch(ctx, ws, rs->d_seq, L, false, kmer_size, results, nullptr);
+	    if (rc) return rc;
+	}
     }
     return ICB_OK;
+}
+
+extern "C" {
+
+int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size, icb_align_result* results)
+{
+    if (!rs || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results))) return ICB_ERR_ARG;
+    icb_ctx* ctx = rs->ctx;
+    if (kmer_size < 1 || kmer_size > 32) return ctx->fail(ICB_ERR_ARG, "kmer_size must be in [1,32]");
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return icb_align_pairs_on(ctx, rs, pairs, n_pairs, kmer_size, results);
 }
 
 }  // extern "C"

@@ -2,7 +2,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "icb_common.cuh"
+#include "align.cuh"
 
 int icb_ctx::fail_cuda(cudaError_t e, const char* what, const char* file, int line)
 {
@@ -93,6 +93,10 @@ void icb_ctx_destroy(icb_ctx* ctx)
     cudaSetDevice(ctx->device);
     ctx->timers_collect();
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->align_ws) {
+	ctx->align_ws->release();
+	delete ctx->align_ws;
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

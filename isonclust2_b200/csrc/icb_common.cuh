@@ -17,8 +17,11 @@ struct icb_kernel_timer {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
+struct IcbAlignWorkspace;
+
 struct icb_ctx {
     int device = 0;
+    IcbAlignWorkspace* align_ws = nullptr;  // stage 3 buffers (align.cuh), created on first use
     int sm_count = ICB_SM_COUNT_FALLBACK;
     cudaStream_t stream = nullptr;
     std::string last_error;

@@ -120,3 +120,29 @@ def test_align_empty_and_bad_args(ctx):
     with pytest.raises(api.IcbError):
         rs.align_pairs(_mk_pairs([(0, 5, 1, 2, 5)]), 11)  # index outside the read set
     rs.close()
+
+
+def test_align_multi_pass_and_32bit_path(port, ctx):
+    """Reads above 2048 rows (several passes of the packed kernel) and above 8000 bases (32-bit kernel)."""
+    rng = np.random.default_rng(10)
+    rnd = lambda n: ACGT[rng.integers(0, 4, n)]
+
+    def mutate(s, e):
+        out = []
+        for c in s:
+            r = rng.random()
+            if r < e / 3:
+                continue
+            if r < 2 * e / 3:
+                out.append(ACGT[rng.integers(0, 4)])
+            if r < e and r >= 2 * e / 3:
+                c = ACGT[rng.integers(0, 4)]
+            out.append(c)
+        return bytes(np.array(out, np.uint8))
+
+    g1, g2, g3 = rnd(2300), rnd(4500), rnd(8300)
+    reads = [mutate(g1, 0.05), mutate(g1, 0.1), mutate(g2, 0.08), mutate(g2, 0.03), bytes(g2[500:4100]), mutate(g3, 0.06),
+             mutate(g3, 0.06), bytes(rnd(2049)), bytes(rnd(2048)), bytes(rnd(4097))]
+    rows = [(0, 1, 1, 3, 8), (1, 0, 1, 2, 7), (2, 3, 1, 3, 8), (3, 2, -1, 4, 9), (4, 2, 1, 3, 8), (2, 4, 1, 5, 8), (5, 6, 1, 3, 8),
+            (6, 5, -1, 2, 8), (0, 2, 1, 3, 6), (7, 8, 1, 3, 5), (8, 7, 1, 3, 5), (9, 7, -1, 2, 5), (3, 9, 1, 4, 5), (5, 2, 1, 3, 8)]
+    _check(port, ctx, reads, _mk_pairs(rows), 11)
