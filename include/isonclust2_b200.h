@@ -164,9 +164,23 @@ void icb_clusterer_destroy(icb_clusterer* cl);
  * (MatchStrand after cluster.cpp:235-246), 0 if skipped.  May be called repeatedly; later calls continue on the
  * clusters founded so far. */
 int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_t* cluster_of, int32_t* strand_of);
+/* Registers clusters that exist already — the left batch of a merge (`cluster -l A.cer -r B.cer`, cluster.cpp:67-106
+ * works on leftBatch->MinDB as loaded): rep_reads[c] is the read whose forward sketch represents the next cluster id
+ * (AddMinimizers, minimizer.cpp:31-42).  A merge is then icb_cluster_reads over the right batch's representatives in
+ * the right batch's cluster order. */
+int icb_clusterer_seed(icb_clusterer* cl, const int32_t* rep_reads, int64_t n);
 int64_t icb_clusterer_n_clusters(const icb_clusterer* cl);
 int icb_clusterer_founders(const icb_clusterer* cl, int32_t* founder_read);
 int icb_clusterer_stats(const icb_clusterer* cl, icb_cluster_stats* stats);
+
+/* Initial clustering of n_batches independent sorted batches of one read set — what the reference's pipeline runs as
+ * one `isONclust2 cluster` process per batch file (README.md:105-117).  Batch b is order[bounds[b] .. bounds[b+1]);
+ * cluster ids are batch-local.  n_workers host threads (0 = one per host core, at most 16) each drive one CUDA stream, so
+ * the device always has several batches' kernels in flight; results do not depend on n_workers.
+ * n_clusters[n_batches] and stats (summed over the batches) may be NULL. */
+int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,
+			int32_t n_batches, int32_t n_workers, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
+			icb_cluster_stats* stats);
 
 #ifdef __cplusplus
 }

@@ -86,20 +86,46 @@ class ClusterStats(C.Structure):
 MODES = {"sahlin": 0, "fast": 1, "furious": 2}
 
 
+def make_params(k, w, mode="sahlin", min_shared=5, mapped_threshold=0.65, aligned_threshold=0.2, min_fraction=0.8,
+                min_prob_no_hits=0.1, min_qual=7.0, chunk_size=0, p_shared=None):
+    """CmdArgs defaults of args.h:13-28 + the InitMinSharedMap(k, w) grid."""
+    from . import pemp
+    P = ClusterParams(kmer_size=k, window_size=w, mode=MODES.get(mode, mode), min_shared=min_shared,
+                      mapped_threshold=mapped_threshold, aligned_threshold=aligned_threshold, min_fraction=min_fraction,
+                      min_prob_no_hits=min_prob_no_hits, min_qual=min_qual, chunk_size=chunk_size)
+    ps = np.ascontiguousarray(pemp.load_p_shared(k, w) if p_shared is None else p_shared, dtype=np.float64).reshape(225)
+    for i in range(225):
+        P.p_shared[i] = ps[i]
+    return P
+
+
+def cluster_batches(rs, order, bounds, k, w, n_workers=0, **params):
+    """One `isONclust2 cluster -x <mode>` per batch order[bounds[b]:bounds[b+1]], several batches in flight on the device.
+
+    Returns (cluster per slot (batch-local ids), strand per slot, clusters per batch, stats summed)."""
+    c = rs.ctx
+    P = make_params(k, w, **params)
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    bounds = np.ascontiguousarray(bounds, dtype=np.int64)
+    nb = len(bounds) - 1
+    cl, st = np.full(len(order), -1, np.int32), np.zeros(len(order), np.int32)
+    ncl = np.zeros(max(nb, 1), np.int64)
+    stats = ClusterStats()
+    c.check(c.L.icb_cluster_batches(rs.h, C.byref(P), order.ctypes.data, bounds.ctypes.data, nb, n_workers, cl.ctypes.data,
+                                    st.ctypes.data, ncl.ctypes.data, C.byref(stats)))
+    return cl, st, ncl[:nb], {n: getattr(stats, n) for n, _ in ClusterStats._fields_}
+
+
 class Clusterer:
     """ClusterSortedReads (cluster.cpp:67-322) for an initial clustering; CmdArgs defaults of args.h:13-28."""
 
     def __init__(self, rs, k, w, mode="sahlin", min_shared=5, mapped_threshold=0.65, aligned_threshold=0.2, min_fraction=0.8,
                  min_prob_no_hits=0.1, min_qual=7.0, chunk_size=0, p_shared=None):
-        from . import pemp
         self.rs = rs
         c = rs.ctx
-        P = ClusterParams(kmer_size=k, window_size=w, mode=MODES.get(mode, mode), min_shared=min_shared,
-                          mapped_threshold=mapped_threshold, aligned_threshold=aligned_threshold, min_fraction=min_fraction,
-                          min_prob_no_hits=min_prob_no_hits, min_qual=min_qual, chunk_size=chunk_size)
-        ps = np.ascontiguousarray(pemp.load_p_shared(k, w) if p_shared is None else p_shared, dtype=np.float64).reshape(225)
-        for i in range(225):
-            P.p_shared[i] = ps[i]
+        P = make_params(k, w, mode=mode, min_shared=min_shared, mapped_threshold=mapped_threshold,
+                        aligned_threshold=aligned_threshold, min_fraction=min_fraction, min_prob_no_hits=min_prob_no_hits,
+                        min_qual=min_qual, chunk_size=chunk_size, p_shared=p_shared)
         h = C.c_void_p()
         c.check(c.L.icb_clusterer_create(rs.h, C.byref(P), C.byref(h)))
         self.h = h
@@ -108,6 +134,12 @@ class Clusterer:
         if self.h:
             self.rs.ctx.L.icb_clusterer_destroy(self.h)
             self.h = None
+
+    def seed(self, rep_reads):
+        """Existing clusters (the left batch of a merge): rep_reads[c] represents the next cluster id."""
+        c = self.rs.ctx
+        rep = np.ascontiguousarray(rep_reads, dtype=np.int32)
+        c.check(c.L.icb_clusterer_seed(self.h, rep.ctypes.data, len(rep)))
 
     def cluster(self, order):
         c = self.rs.ctx
@@ -282,7 +314,7 @@ def split_batches(order, lengths, batch_kb=50000, batch_max_seq=30000):
 
 
 def run_pipeline(ctx, seq, qual, offs, k=11, w=15, mode="sahlin", min_qual=7.0, batch_kb=50000, batch_max_seq=30000,
-                 chunk_size=0, rs=None, keep=False, **cluster_kw):
+                 chunk_size=0, rs=None, keep=False, n_workers=0, **cluster_kw):
     """`isONclust2 sort` + one `isONclust2 cluster -x <mode>` per batch, on one device, without the files in between.
 
     Returns dict(order, batches, cluster (per sorted slot, batch-local ids), strand, n_clusters per batch, stats)."""
@@ -297,19 +329,10 @@ def run_pipeline(ctx, seq, qual, offs, k=11, w=15, mode="sahlin", min_qual=7.0, 
         rs.sketch_async(k, w, skip=skip)
         lengths = np.diff(rs.offs)
         batches = split_batches(order, lengths, batch_kb, batch_max_seq)
-        cluster = np.full(len(order), -1, np.int32)
-        strand = np.zeros(len(order), np.int32)
-        ncl, stats = [], []
-        for a, b in batches:
-            cl = Clusterer(rs, k, w, mode=mode, min_qual=min_qual, chunk_size=chunk_size, **cluster_kw)
-            try:
-                c, s = cl.cluster(order[a:b])
-                cluster[a:b], strand[a:b] = c, s
-                ncl.append(cl.n_clusters)
-                stats.append(cl.stats())
-            finally:
-                cl.close()
-        tot = {key: sum(st[key] for st in stats) for key in stats[0]} if stats else {}
+        bounds = np.array([a for a, _ in batches] + [batches[-1][1] if batches else 0], dtype=np.int64)
+        cluster, strand, ncl, tot = cluster_batches(rs, order, bounds, k, w, n_workers=n_workers, mode=mode, min_qual=min_qual,
+                                                    chunk_size=chunk_size, **cluster_kw)
+        ncl = [int(x) for x in ncl]
         return dict(order=order, batches=batches, cluster=cluster, strand=strand, n_clusters=ncl, stats=tot, score=score, err=err)
     finally:
         if own and not keep:

@@ -15,8 +15,14 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <string>
 #include <unordered_map>
 
+#include <atomic>
+#include <thread>
+
+#include "align.cuh"
 #include "index.cuh"
 
 namespace {
@@ -56,7 +62,7 @@ struct Stopwatch {
 }  // namespace
 
 struct icb_clusterer {
-    icb_ctx* ctx = nullptr;
+    icb_ctx* ctx = nullptr;  // the context (stream) this clusterer launches on: the read set's, or a worker's child context
     icb_readset* rs = nullptr;
     icb_cluster_params P{};
     int32_t nmax[225];
@@ -79,40 +85,116 @@ struct icb_clusterer {
     int64_t scratch_words = 0;
     int chunk_cap = 0;
     icb_cluster_stats stats{};
+    // pinned host staging (asynchronous copies, no hidden stream synchronisation on pageable memory)
+    int32_t* h_i32 = nullptr;	 // 3 * chunk_cap: chunk reads / ids / list
+    IcbQueryHeader* h_hdr = nullptr;
+    IcbCand* h_cands = nullptr;
+    int64_t h_cands_cap = 0;
+    int64_t* h_off = nullptr;	 // chunk_cap + 1
+
+    int init_buffers();
+    void free_buffers();
+    int reset();
+    int seed(const int32_t* rep_reads, int64_t n);
 
     int ensure_scratch(int64_t words);
     int ensure_cands(int64_t n);
     int query(const std::vector<int32_t>& chunk, int C0, const std::vector<int32_t>* list, int mode, int cap,
-	      std::vector<IcbQueryHeader>& hdr, std::vector<IcbCand>& cands, std::vector<int64_t>* full_off);
+	      const std::vector<int32_t>* live);
+    int upload_founders(int64_t from);
     int process_chunk(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of, int32_t* strand_of);
 };
 
 int icb_clusterer::ensure_scratch(int64_t words)
 {
     if (words <= scratch_words) return ICB_OK;
+    ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_scratch);
     d_scratch = nullptr;
     scratch_words = 0;
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_scratch, size_t(words) * 4));
-    scratch_words = words;
+    const int64_t want = words + words / 2;  // geometric: the index grows with every chunk
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_scratch, size_t(want) * 4));
+    scratch_words = want;
     return ICB_OK;
 }
 
 int icb_clusterer::ensure_cands(int64_t n)
 {
-    if (n <= cands_cap) return ICB_OK;
-    cudaFree(d_cands);
-    d_cands = nullptr;
-    cands_cap = 0;
-    int64_t want = std::max<int64_t>(n, 1 << 16);
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_cands, size_t(want) * sizeof(IcbCand)));
-    cands_cap = want;
+    if (n > cands_cap) {
+	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_cands);
+	d_cands = nullptr;
+	cands_cap = 0;
+	const int64_t want = std::max<int64_t>(n + n / 2, 1 << 16);
+	ICB_CUDA(ctx, cudaMalloc((void**)&d_cands, size_t(want) * sizeof(IcbCand)));
+	cands_cap = want;
+    }
+    if (n > h_cands_cap) {
+	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFreeHost(h_cands);
+	h_cands = nullptr;
+	h_cands_cap = 0;
+	const int64_t want = std::max<int64_t>(n + n / 2, 1 << 16);
+	ICB_CUDA(ctx, cudaMallocHost((void**)&h_cands, size_t(want) * sizeof(IcbCand)));
+	h_cands_cap = want;
+    }
     return ICB_OK;
 }
 
-// one query launch over (a subset of) the chunk; results copied to the host
+int icb_clusterer::init_buffers()
+{
+    const int cs = chunk_cap;
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_nmax, sizeof(int32_t) * 225));
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_chunk_reads, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_list, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_ids, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_hdr, sizeof(IcbQueryHeader) * cs));
+    ICB_CUDA(ctx, cudaMalloc((void**)&d_full_off, sizeof(int64_t) * (cs + 1)));
+    ICB_CUDA(ctx, cudaMallocHost((void**)&h_i32, sizeof(int32_t) * (3 * cs + 256)));
+    ICB_CUDA(ctx, cudaMallocHost((void**)&h_hdr, sizeof(IcbQueryHeader) * cs));
+    ICB_CUDA(ctx, cudaMallocHost((void**)&h_off, sizeof(int64_t) * (cs + 1)));
+    memcpy(h_i32 + 3 * cs, nmax, sizeof(int32_t) * 225);
+    ICB_CUDA(ctx, cudaMemcpyAsync(d_nmax, h_i32 + 3 * cs, sizeof(int32_t) * 225, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = main_idx.create(ctx, 1u << 16, 1 << 16);
+    if (rc) return rc;
+    rc = chunk_idx.create(ctx, 1u << 18, 1 << 17);
+    if (rc) return rc;
+    ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ICB_OK;
+}
+
+void icb_clusterer::free_buffers()
+{
+    main_idx.destroy();
+    chunk_idx.destroy();
+    cudaFree(d_nmax);
+    cudaFree(d_cls_founder);
+    cudaFree(d_chunk_reads);
+    cudaFree(d_list);
+    cudaFree(d_ids);
+    cudaFree(d_hdr);
+    cudaFree(d_cands);
+    cudaFree(d_full_off);
+    cudaFree(d_scratch);
+    cudaFreeHost(h_i32);
+    cudaFreeHost(h_hdr);
+    cudaFreeHost(h_cands);
+    cudaFreeHost(h_off);
+}
+
+// forget every cluster (the buffers and their capacities stay): the next batch starts from an empty index
+int icb_clusterer::reset()
+{
+    founder.clear();
+    stats = icb_cluster_stats{};
+    return main_idx.clear();
+}
+
+// one query launch over (a subset of) the chunk; results land in the pinned mirrors h_hdr / h_cands.
+// mode 0: `cap` records per item at item*cap.  mode 1: item t at h_off[t], sized by `live` (the n_total a mode-0
+// query reported for that read).
 int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::vector<int32_t>* list, int mode, int cap,
-			 std::vector<IcbQueryHeader>& hdr, std::vector<IcbCand>& cands, std::vector<int64_t>* full_off)
+			 const std::vector<int32_t>* live)
 {
     cudaStream_t st = ctx->stream;
     const int n_chunk = int(chunk.size());
@@ -131,7 +213,9 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
     a.list = nullptr;
     a.n_list = 0;
     if (list) {
-	ICB_CUDA(ctx, cudaMemcpyAsync(d_list, list->data(), sizeof(int32_t) * n_items, cudaMemcpyHostToDevice, st));
+	int32_t* h_list = h_i32 + 2 * chunk_cap;
+	memcpy(h_list, list->data(), sizeof(int32_t) * n_items);
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_list, h_list, sizeof(int32_t) * n_items, cudaMemcpyHostToDevice, st));
 	a.list = d_list;
 	a.n_list = n_items;
     }
@@ -147,17 +231,16 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
     a.hdr = d_hdr;
     a.full_off = nullptr;
     int64_t n_records;
-    std::vector<int64_t> foff;
     if (mode == 1) {
-	foff.resize(n_items + 1);
-	for (int i = 0; i <= n_items; i++) foff[i] = int64_t(i) * 2 * Ctot;
-	n_records = foff[n_items];
-	ICB_CUDA(ctx, cudaMemcpyAsync(d_full_off, foff.data(), sizeof(int64_t) * n_items, cudaMemcpyHostToDevice, st));
+	h_off[0] = 0;
+	for (int i = 0; i < n_items; i++) h_off[i + 1] = h_off[i] + (*live)[i];
+	n_records = h_off[n_items];
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_full_off, h_off, sizeof(int64_t) * n_items, cudaMemcpyHostToDevice, st));
 	a.full_off = d_full_off;
     }
     else
 	n_records = int64_t(n_items) * cap;
-    int rc = ensure_cands(n_records);
+    int rc = ensure_cands(std::max<int64_t>(n_records, 1));
     if (rc) return rc;
     a.cands = d_cands;
     // shared memory plan: dense counters (Ctot words) + candidate list (2*cap) + bitmaps
@@ -184,12 +267,72 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
     }
     rc = icb_query_launch(ctx, a, n_blocks, size_t(words_smem) * 4);
     if (rc) return rc;
-    hdr.resize(n_items);
-    ICB_CUDA(ctx, cudaMemcpyAsync(hdr.data(), d_hdr, sizeof(IcbQueryHeader) * n_items, cudaMemcpyDeviceToHost, st));
-    cands.resize(n_records);
-    ICB_CUDA(ctx, cudaMemcpyAsync(cands.data(), d_cands, sizeof(IcbCand) * n_records, cudaMemcpyDeviceToHost, st));
+    ICB_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, sizeof(IcbQueryHeader) * n_items, cudaMemcpyDeviceToHost, st));
+    if (n_records > 0)
+	ICB_CUDA(ctx, cudaMemcpyAsync(h_cands, d_cands, sizeof(IcbCand) * n_records, cudaMemcpyDeviceToHost, st));
     ICB_CUDA(ctx, cudaStreamSynchronize(st));
-    if (full_off) *full_off = foff;
+    return ICB_OK;
+}
+
+// AddMinimizers (minimizer.cpp:31-42) for clusters that exist already: the left batch of a merge
+// (cluster.cpp:67-106 works on leftBatch->MinDB as loaded).  rep_reads[c] = the read whose forward sketch
+// represents cluster `n_clusters + c`.
+int icb_clusterer::seed(const int32_t* rep_reads, int64_t n)
+{
+    if (n <= 0) return ICB_OK;
+    cudaStream_t st = ctx->stream;
+    const int64_t C0 = int64_t(founder.size());
+    int64_t tot = 0;
+    for (int64_t i = 0; i < n; i++) {
+	const int32_t r = rep_reads[i];
+	if (r < 0 || r >= rs->n_reads || rs->h_status[r] != 1) return ctx->fail(ICB_ERR_ARG, "seed: representative is not a sketched read");
+	tot += rs->h_nf[r];
+    }
+    int rc = main_idx.reserve(tot);
+    if (rc) return rc;
+    founder.insert(founder.end(), rep_reads, rep_reads + n);
+    rc = upload_founders(C0);
+    if (rc) return rc;
+    // ids and reads of the new clusters, staged through the pinned block in pieces of chunk_cap
+    for (int64_t done = 0; done < n; done += chunk_cap) {
+	const int cnt = int(std::min<int64_t>(chunk_cap, n - done));
+	for (int i = 0; i < cnt; i++) {
+	    h_i32[i] = rep_reads[done + i];
+	    h_i32[chunk_cap + i] = int32_t(C0 + done + i);
+	}
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, h_i32, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, h_i32 + chunk_cap, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, st));
+	rc = icb_index_insert(ctx, main_idx, rs, d_chunk_reads, d_ids, cnt);
+	if (rc) return rc;
+	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    main_idx.nodes_upper += tot;
+    return ICB_OK;
+}
+
+// device copy of founder[from..]
+int icb_clusterer::upload_founders(int64_t from)
+{
+    cudaStream_t st = ctx->stream;
+    const int64_t n = int64_t(founder.size());
+    if (n > cls_founder_cap) {
+	const int64_t ncap = std::max<int64_t>(cls_founder_cap * 2, n + 4096);
+	int32_t* nd = nullptr;
+	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+	ICB_CUDA(ctx, cudaMalloc((void**)&nd, sizeof(int32_t) * ncap));
+	if (from > 0) ICB_CUDA(ctx, cudaMemcpyAsync(nd, d_cls_founder, sizeof(int32_t) * from, cudaMemcpyDeviceToDevice, st));
+	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+	cudaFree(d_cls_founder);
+	d_cls_founder = nd;
+	cls_founder_cap = ncap;
+    }
+    int32_t* stage = h_i32 + 2 * chunk_cap;
+    for (int64_t done = from; done < n; done += chunk_cap) {
+	const int64_t cnt = std::min<int64_t>(chunk_cap, n - done);
+	memcpy(stage, founder.data() + done, sizeof(int32_t) * cnt);
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_cls_founder + done, stage, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, st));
+	if (done + cnt < n) ICB_CUDA(ctx, cudaStreamSynchronize(st));  // the staging block is reused by the next piece
+    }
     return ICB_OK;
 }
 
@@ -206,45 +349,42 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     stats.chunks++;
     Stopwatch sw;
     // ---- chunk index: every read of the chunk as a provisional founder (id = C0 + position)
-    ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, chunk.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
     {
-	std::vector<int32_t> ids(N);
 	int64_t tot = 0;
 	for (int i = 0; i < N; i++) {
-	    ids[i] = C0 + i;
+	    h_i32[i] = chunk[i];
+	    h_i32[chunk_cap + i] = C0 + i;
 	    tot += nf[chunk[i]];
 	}
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, h_i32, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, h_i32 + chunk_cap, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
 	int rc = chunk_idx.clear();
 	if (rc) return rc;
 	rc = chunk_idx.reserve(tot);
 	if (rc) return rc;
-	ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, ids.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
 	rc = icb_index_insert(ctx, chunk_idx, rs, d_chunk_reads, d_ids, N);
 	if (rc) return rc;
 	chunk_idx.nodes_upper = tot;
     }
     stats.ms_insert += sw.lap();
     // ---- candidates of every read against snapshot + provisional founders
-    std::vector<IcbQueryHeader> hdr;
-    std::vector<IcbCand> cands;
-    int rc = query(chunk, C0, nullptr, 0, CAP, hdr, cands, nullptr);
+    int rc = query(chunk, C0, nullptr, 0, CAP, nullptr);
     if (rc) return rc;
     stats.reads_queried += N;
+    std::vector<IcbQueryHeader> hdr(h_hdr, h_hdr + N);
     // per-read candidate lists (reads whose list overflowed are re-queried with room for every key)
     std::vector<std::vector<IcbCand>> cl(N);
     std::vector<int32_t> over;
     for (int i = 0; i < N; i++) {
 	if (hdr[i].overflow) over.push_back(i);
-	else cl[i].assign(cands.begin() + int64_t(i) * CAP, cands.begin() + int64_t(i) * CAP + hdr[i].n_cand);
+	else cl[i].assign(h_cands + int64_t(i) * CAP, h_cands + int64_t(i) * CAP + hdr[i].n_cand);
     }
     if (!over.empty()) {
-	std::vector<IcbQueryHeader> h2;
-	std::vector<IcbCand> c2;
 	const int cap2 = 2 * (C0 + N);
-	rc = query(chunk, C0, &over, 0, cap2, h2, c2, nullptr);
+	rc = query(chunk, C0, &over, 0, cap2, nullptr);
 	if (rc) return rc;
 	for (size_t t = 0; t < over.size(); t++)
-	    cl[over[t]].assign(c2.begin() + int64_t(t) * cap2, c2.begin() + int64_t(t) * cap2 + h2[t].n_cand);
+	    cl[over[t]].assign(h_cands + int64_t(t) * cap2, h_cands + int64_t(t) * cap2 + h_hdr[t].n_cand);
     }
 
     stats.ms_query += sw.lap();
@@ -440,13 +580,12 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	if (!needFull.empty()) {
 	    std::sort(needFull.begin(), needFull.end());
 	    needFull.erase(std::unique(needFull.begin(), needFull.end()), needFull.end());
-	    std::vector<IcbQueryHeader> h2;
-	    std::vector<IcbCand> c2;
-	    std::vector<int64_t> foff;
-	    rc = query(chunk, C0, &needFull, 1, 0, h2, c2, &foff);
+	    std::vector<int32_t> live(needFull.size());
+	    for (size_t t = 0; t < needFull.size(); t++) live[t] = hdr[needFull[t]].n_total;
+	    rc = query(chunk, C0, &needFull, 1, 0, &live);
 	    if (rc) return rc;
 	    for (size_t t = 0; t < needFull.size(); t++)
-		full[needFull[t]].assign(c2.begin() + foff[t], c2.begin() + foff[t] + h2[t].n_cand);
+		full[needFull[t]].assign(h_cands + h_off[t], h_cands + h_off[t] + h_hdr[t].n_cand);
 	    stats.ms_full += sw.lap();
 	}
 	if (!needPairs.empty()) {
@@ -469,7 +608,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 		p.limit = lim < -1.0 ? -1 : (lim > double(k + 1) ? k + 1 : int(lim));
 	    }
 	    std::vector<icb_align_result> res(pairs.size());
-	    rc = icb_align_pairs(rs, pairs.data(), int64_t(pairs.size()), k, res.data());
+	    rc = icb_align_pairs_on(ctx, rs, pairs.data(), int64_t(pairs.size()), k, res.data());
 	    if (rc) return rc;
 	    stats.pairs_aligned += int64_t(pairs.size());
 	    for (size_t t = 0; t < needPairs.size(); t++) {
@@ -492,54 +631,75 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     if (!fr.empty()) {
 	rc = main_idx.reserve(tot);
 	if (rc) return rc;
-	if (int64_t(founder.size()) > cls_founder_cap) {
-	    int64_t ncap = std::max<int64_t>(cls_founder_cap * 2, int64_t(founder.size()) + 1024);
-	    int32_t* nd = nullptr;
-	    ICB_CUDA(ctx, cudaMalloc((void**)&nd, sizeof(int32_t) * ncap));
-	    if (C0 > 0) ICB_CUDA(ctx, cudaMemcpyAsync(nd, d_cls_founder, sizeof(int32_t) * C0, cudaMemcpyDeviceToDevice, st));
-	    ICB_CUDA(ctx, cudaStreamSynchronize(st));
-	    cudaFree(d_cls_founder);
-	    d_cls_founder = nd;
-	    cls_founder_cap = ncap;
-	}
-	ICB_CUDA(ctx, cudaMemcpyAsync(d_cls_founder + C0, founder.data() + C0, sizeof(int32_t) * (founder.size() - C0),
-				      cudaMemcpyHostToDevice, st));
-	ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, fr.data(), sizeof(int32_t) * fr.size(), cudaMemcpyHostToDevice, st));
-	ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, fi.data(), sizeof(int32_t) * fi.size(), cudaMemcpyHostToDevice, st));
+	rc = upload_founders(C0);
+	if (rc) return rc;
+	memcpy(h_i32, fr.data(), sizeof(int32_t) * fr.size());
+	memcpy(h_i32 + chunk_cap, fi.data(), sizeof(int32_t) * fi.size());
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, h_i32, sizeof(int32_t) * fr.size(), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, h_i32 + chunk_cap, sizeof(int32_t) * fi.size(), cudaMemcpyHostToDevice, st));
 	rc = icb_index_insert(ctx, main_idx, rs, d_chunk_reads, d_ids, int(fr.size()));
 	if (rc) return rc;
 	main_idx.nodes_upper += tot;
-	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+	ICB_CUDA(ctx, cudaStreamSynchronize(st));  // the pinned staging block is rewritten by the next chunk
     }
     stats.ms_insert += sw.lap();
     return ICB_OK;
 }
 
-extern "C" {
-
-int icb_clusterer_create(icb_readset* rs, const icb_cluster_params* p, icb_clusterer** out)
+// per-read scalars the greedy loop reads on the host + the device error classes: once per read set
+int icb_readset_prepare_host(icb_readset* rs)
 {
-    if (!rs || !p || !out) return ICB_ERR_ARG;
-    *out = nullptr;
     icb_ctx* ctx = rs->ctx;
+    if (rs->host_ready) return ICB_OK;
+    const int64_t n = rs->n_reads;
+    cudaStream_t st = ctx->stream;
+    rs->h_status.resize(n);
+    rs->h_hpc_len.resize(n);
+    rs->h_nf.resize(n);
+    rs->h_nr.resize(n);
+    rs->h_score.resize(n);
+    rs->h_err.resize(n);
+    if (n) {
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_status.data(), rs->d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_hpc_len.data(), rs->d_hpc_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_nf.data(), rs->d_nf, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_nr.data(), rs->d_nr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_score.data(), rs->d_score, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_err.data(), rs->d_err, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    }
+    if (!rs->d_class) ICB_CUDA(ctx, cudaMalloc((void**)&rs->d_class, n + 16));
+    int rc0 = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, rs->d_class);
+    if (rc0) return rc0;
+    ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    rs->max_m = 0;
+    for (int64_t i = 0; i < n; i++) rs->max_m = std::max(rs->max_m, std::max(rs->h_nf[i], rs->h_nr[i]));
+    rs->host_ready = true;
+    return ICB_OK;
+}
+
+// a clusterer on an explicit context (the read set's own, or a worker's child context with its own stream);
+// errors are reported on `ctx`
+static int clusterer_create_on(icb_ctx* ctx, icb_readset* rs, const icb_cluster_params* p, icb_clusterer** out)
+{
+    *out = nullptr;
     if (!rs->scored || !rs->sketched) return ctx->fail(ICB_ERR_STATE, "icb_clusterer_create needs scored and sketched reads");
     if (p->kmer_size != rs->sk_k || p->window_size != rs->sk_w)
 	return ctx->fail(ICB_ERR_ARG, "k / w differ from the ones the reads were sketched with");
     if (p->mode < 0 || p->mode > 2) return ctx->fail(ICB_ERR_ARG, "mode must be 0 (sahlin), 1 (fast) or 2 (furious)");
+    if (!rs->host_ready) return ctx->fail(ICB_ERR_STATE, "read set host mirror missing");
+    if (rs->max_m >= 32768) return ctx->fail(ICB_ERR_ARG, "a read has 32768 or more minimizers per strand");
     ICB_CUDA(ctx, cudaSetDevice(ctx->device));
-    auto cl = new icb_clusterer;
+    std::unique_ptr<icb_clusterer> cl(new icb_clusterer);
     cl->ctx = ctx;
     cl->rs = rs;
     cl->P = *p;
     if (cl->P.chunk_size <= 0) cl->P.chunk_size = 256;
+    cl->chunk_cap = cl->P.chunk_size;
     // n_max table (cluster.cpp:335-349: pow(pError, n) >= minProbNoHits with the HOST libm; monotone in n)
     if (p->mode != 2) {
 	for (int c = 0; c < 225; c++) {
 	    double ps = p->p_shared[c];
-	    if (!(ps == ps)) {
-		delete cl;
-		return ctx->fail(ICB_ERR_NO_PEMP, "Empirical probability lookup failure!");
-	    }
+	    if (!(ps == ps)) return ctx->fail(ICB_ERR_NO_PEMP, "Empirical probability lookup failure!");
 	    double pe = 1.0 - ps;
 	    int32_t n = -1;
 	    for (int32_t t = 0; t < (1 << 20); t++) {
@@ -551,51 +711,27 @@ int icb_clusterer_create(icb_readset* rs, const icb_cluster_params* p, icb_clust
     }
     else
 	for (int c = 0; c < 225; c++) cl->nmax[c] = 0;
-    const int64_t n = rs->n_reads;
-    cudaStream_t st = ctx->stream;
-    if (!rs->host_ready) {
-	rs->h_status.resize(n);
-	rs->h_hpc_len.resize(n);
-	rs->h_nf.resize(n);
-	rs->h_nr.resize(n);
-	rs->h_score.resize(n);
-	rs->h_err.resize(n);
-	if (n) {
-	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_status.data(), rs->d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_hpc_len.data(), rs->d_hpc_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_nf.data(), rs->d_nf, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_nr.data(), rs->d_nr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_score.data(), rs->d_score, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_err.data(), rs->d_err, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-	}
-	if (!rs->d_class) ICB_CUDA(ctx, cudaMalloc((void**)&rs->d_class, n + 16));
-	int rc0 = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, rs->d_class);
-	if (rc0) return rc0;
-	ICB_CUDA(ctx, cudaStreamSynchronize(st));
-	rs->max_m = 0;
-	for (int64_t i = 0; i < n; i++) rs->max_m = std::max(rs->max_m, std::max(rs->h_nf[i], rs->h_nr[i]));
-	rs->host_ready = true;
+    int rc = cl->init_buffers();
+    if (rc) {
+	cl->free_buffers();
+	return rc;
     }
-    if (rs->max_m >= 32768) {
-	delete cl;
-	return ctx->fail(ICB_ERR_ARG, "a read has 32768 or more minimizers per strand");
-    }
-    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_nmax, sizeof(int32_t) * 225));
-    ICB_CUDA(ctx, cudaMemcpyAsync(cl->d_nmax, cl->nmax, sizeof(int32_t) * 225, cudaMemcpyHostToDevice, st));
-    int rc = 0;
-    const int cs = cl->P.chunk_size;
-    cl->chunk_cap = cs;
-    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_chunk_reads, sizeof(int32_t) * cs));
-    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_list, sizeof(int32_t) * cs));
-    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_ids, sizeof(int32_t) * cs));
-    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_hdr, sizeof(IcbQueryHeader) * cs));
-    ICB_CUDA(ctx, cudaMalloc((void**)&cl->d_full_off, sizeof(int64_t) * (cs + 1)));
-    rc = cl->main_idx.create(ctx, 1u << 16, 1 << 16);
-    if (rc) return rc;
-    rc = cl->chunk_idx.create(ctx, 1u << 16, 1 << 16);
-    if (rc) return rc;
-    *out = cl;
+    *out = cl.release();
     return ICB_OK;
+}
+
+extern "C" {
+
+int icb_clusterer_create(icb_readset* rs, const icb_cluster_params* p, icb_clusterer** out)
+{
+    if (!rs || !p || !out) return ICB_ERR_ARG;
+    *out = nullptr;
+    icb_ctx* ctx = rs->ctx;
+    if (!rs->scored || !rs->sketched) return ctx->fail(ICB_ERR_STATE, "icb_clusterer_create needs scored and sketched reads");
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = icb_readset_prepare_host(rs);
+    if (rc) return rc;
+    return clusterer_create_on(ctx, rs, p, out);
 }
 
 void icb_clusterer_destroy(icb_clusterer* cl)
@@ -603,18 +739,94 @@ void icb_clusterer_destroy(icb_clusterer* cl)
     if (!cl) return;
     cudaSetDevice(cl->ctx->device);
     cudaStreamSynchronize(cl->ctx->stream);
-    cl->main_idx.destroy();
-    cl->chunk_idx.destroy();
-    cudaFree(cl->d_nmax);
-    cudaFree(cl->d_cls_founder);
-    cudaFree(cl->d_chunk_reads);
-    cudaFree(cl->d_list);
-    cudaFree(cl->d_ids);
-    cudaFree(cl->d_hdr);
-    cudaFree(cl->d_cands);
-    cudaFree(cl->d_full_off);
-    cudaFree(cl->d_scratch);
+    cl->free_buffers();
     delete cl;
+}
+
+int icb_clusterer_seed(icb_clusterer* cl, const int32_t* rep_reads, int64_t n)
+{
+    if (!cl || n < 0 || (n > 0 && !rep_reads)) return ICB_ERR_ARG;
+    ICB_CUDA(cl->ctx, cudaSetDevice(cl->ctx->device));
+    return cl->seed(rep_reads, n);
+}
+
+int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,
+			int32_t n_batches, int32_t n_workers, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
+			icb_cluster_stats* stats)
+{
+    if (!rs || !params || n_batches < 0 || (n_batches > 0 && (!order || !bounds || !cluster_of || !strand_of))) return ICB_ERR_ARG;
+    icb_ctx* ctx = rs->ctx;
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (stats) *stats = icb_cluster_stats{};
+    if (n_batches == 0) return ICB_OK;
+    if (!rs->scored || !rs->sketched) return ctx->fail(ICB_ERR_STATE, "icb_cluster_batches needs scored and sketched reads");
+    for (int b = 0; b < n_batches; b++)
+	if (bounds[b] < 0 || bounds[b + 1] < bounds[b]) return ctx->fail(ICB_ERR_ARG, "batch bounds must be non-decreasing");
+    int rc = icb_readset_prepare_host(rs);
+    if (rc) return rc;
+    ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // scores / sketches are complete before other streams read them
+    int nw = n_workers > 0 ? n_workers : int(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u));
+    nw = std::min(nw, int(n_batches));
+    std::atomic<int> next(0), first_err(0);
+    std::vector<icb_ctx*> kids(nw, nullptr);
+    std::vector<icb_cluster_stats> wstats(nw);
+    std::vector<std::string> werr(nw);
+    for (int w = 0; w < nw; w++) {
+	kids[w] = icb_ctx_create_child(ctx);
+	if (!kids[w]) {
+	    for (auto k : kids) icb_ctx_destroy_child(ctx, k);
+	    return ctx->fail(ICB_ERR_CUDA, "cannot create a worker stream");
+	}
+    }
+    auto work = [&](int w) {
+	icb_ctx* c = kids[w];
+	cudaSetDevice(c->device);
+	icb_clusterer* cl = nullptr;
+	int rc = clusterer_create_on(c, rs, params, &cl);
+	while (!rc) {
+	    const int b = next.fetch_add(1);
+	    if (b >= n_batches || first_err.load()) break;
+	    rc = cl->reset();
+	    if (rc) break;
+	    rc = icb_cluster_reads(cl, order + bounds[b], bounds[b + 1] - bounds[b], cluster_of + bounds[b], strand_of + bounds[b]);
+	    if (rc) break;
+	    if (n_clusters) n_clusters[b] = int64_t(cl->founder.size());
+	    const icb_cluster_stats& s = cl->stats;
+	    icb_cluster_stats& t = wstats[w];
+	    t.chunks += s.chunks; t.rounds += s.rounds; t.reads_queried += s.reads_queried; t.aln_invoked += s.aln_invoked;
+	    t.pairs_aligned += s.pairs_aligned; t.cells_aligned += s.cells_aligned; t.tie_fallbacks += s.tie_fallbacks;
+	    t.decisions += s.decisions; t.ms_query += s.ms_query; t.ms_full += s.ms_full; t.ms_align += s.ms_align;
+	    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host;
+	}
+	if (rc) {
+	    int z = 0;
+	    first_err.compare_exchange_strong(z, rc);
+	    werr[w] = c->last_error;
+	}
+	if (cl) icb_clusterer_destroy(cl);
+    };
+    if (nw == 1) work(0);
+    else {
+	std::vector<std::thread> th;
+	for (int w = 0; w < nw; w++) th.emplace_back(work, w);
+	for (auto& t : th) t.join();
+    }
+    for (int w = 0; w < nw; w++) {
+	if (stats) {
+	    const icb_cluster_stats& s = wstats[w];
+	    stats->chunks += s.chunks; stats->rounds += s.rounds; stats->reads_queried += s.reads_queried;
+	    stats->aln_invoked += s.aln_invoked; stats->pairs_aligned += s.pairs_aligned; stats->cells_aligned += s.cells_aligned;
+	    stats->tie_fallbacks += s.tie_fallbacks; stats->decisions += s.decisions; stats->ms_query += s.ms_query;
+	    stats->ms_full += s.ms_full; stats->ms_align += s.ms_align; stats->ms_insert += s.ms_insert; stats->ms_host += s.ms_host;
+	}
+	icb_ctx_destroy_child(ctx, kids[w]);  // folds the worker's kernel timers and launch count into the parent
+    }
+    if (first_err.load()) {
+	for (auto& e : werr)
+	    if (!e.empty()) return ctx->fail(first_err.load(), e);
+	return ctx->fail(first_err.load(), "worker failed");
+    }
+    return ICB_OK;
 }
 
 int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_t* cluster_of, int32_t* strand_of)

@@ -60,6 +60,39 @@ void icb_ctx::timers_collect()
     }
 }
 
+icb_ctx* icb_ctx_create_child(icb_ctx* parent)
+{
+    auto ctx = new icb_ctx;
+    ctx->device = parent->device;
+    ctx->sm_count = parent->sm_count;
+    ctx->timing = parent->timing;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+	delete ctx;
+	return nullptr;
+    }
+    return ctx;
+}
+
+void icb_ctx_destroy_child(icb_ctx* parent, icb_ctx* child)
+{
+    if (!child) return;
+    cudaSetDevice(child->device);
+    child->timers_collect();
+    for (auto& kv : child->timers) {
+	auto& t = parent->timers[kv.first];
+	t.launches += kv.second.launches;
+	t.total_ms += kv.second.total_ms;
+    }
+    parent->launch_count += child->launch_count;
+    for (auto e : child->event_pool) cudaEventDestroy(e);
+    if (child->align_ws) {
+	child->align_ws->release();
+	delete child->align_ws;
+    }
+    cudaStreamDestroy(child->stream);
+    delete child;
+}
+
 extern "C" {
 
 int icb_device_count(void)

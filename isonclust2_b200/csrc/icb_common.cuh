@@ -94,6 +94,11 @@ struct icb_readset {
     uint8_t* d_class = nullptr;
 };
 
+// a worker's context: same device, own stream and timers; destroy folds timers / launch count into the parent
+icb_ctx* icb_ctx_create_child(icb_ctx* parent);
+void icb_ctx_destroy_child(icb_ctx* parent, icb_ctx* child);
+int icb_readset_prepare_host(icb_readset* rs);
+
 // stage launchers (defined in score.cu / sketch.cu)
 int icb_launch_score(icb_readset* rs, int k, const double* tab, const double* tab_nomin);
 int icb_launch_error_rate(icb_readset* rs, const uint8_t* d_qual, const int64_t* d_offs, const int32_t* d_len,

@@ -69,6 +69,8 @@ def load():
     L.icb_clusterer_n_clusters.restype = _i64
     L.icb_clusterer_founders.argtypes = [_p, _p]
     L.icb_clusterer_stats.argtypes = [_p, _p]
+    L.icb_clusterer_seed.argtypes = [_p, _p, _i64]
+    L.icb_cluster_batches.argtypes = [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]
     L.icb_init_qual_tab.argtypes = [_p, _i32]
     L.icb_init_qual_tab.restype = None
     L.icb_quality_filter.argtypes = [_p, _i64, _dbl, _p]

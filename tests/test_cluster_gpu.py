@@ -115,3 +115,69 @@ def test_cluster_no_pemp_row(ctx):
         api.Clusterer(rs, 31, 40, mode="sahlin", p_shared=pemp.load_p_shared(31, 40))
     assert ei.value.code == -4
     rs.close()
+
+
+def _members(rc):
+    """read -> (cluster, strand) from the reference's cluster lists (element 0 of a cluster is the representative copy)."""
+    ra, pos = {}, 0
+    for c, sz in enumerate(rc["sizes"]):
+        for j in range(1, sz):
+            ra[int(rc["ids"][pos + j])] = (c, int(rc["strands"][pos + j]))
+        pos += sz
+    return ra
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cluster_batches_and_merge_vs_reference(ref, ctx, mode):
+    """Two sorted batches clustered concurrently (icb_cluster_batches), then merged left <- right (icb_clusterer_seed +
+    icb_cluster_reads over the right batch's representatives) against the UNMODIFIED reference doing the same
+    (`cluster -l A`, `cluster -l B`, `cluster -l A -r B`, cluster.cpp:67-322)."""
+    k, w = 11, 15
+    n, h = 1400, 800
+    seq, qual, offs = synth.make_reads(n, seed=61 + mode)
+    rb = ref.sort_and_sketch(seq, qual, offs, k, w)
+    _, _, order = rb.scores()
+    A, B = rb.slice(0, h - 1, 0), rb.slice(h, n - 1, 1)
+    ra, rbb = A.cluster(mode), B.cluster(mode)
+    mem_a, mem_b = _members(ra), _members(rbb)
+    rm = A.cluster(mode, right=B)
+    mem_m = _members(rm)
+
+    rs = ctx.upload(seq, qual, offs)
+    try:
+        score, err = rs.score(k)
+        assert (api.sort_by_qual_scores(score) == order).all()
+        rs.sketch_async(k, w, skip=api.quality_filtered(err, 7.0))
+        bounds = np.array([0, h, n], np.int64)
+        res = {}
+        for nw in (1, 2):
+            cl, st, ncl, stats = api.cluster_batches(rs, order, bounds, k, w, n_workers=nw, mode=mode, chunk_size=128)
+            res[nw] = (cl.copy(), st.copy(), ncl.copy())
+        assert (res[1][0] == res[2][0]).all() and (res[1][1] == res[2][1]).all() and (res[1][2] == res[2][2]).all()
+        cl, st, ncl = res[2]
+        assert int(ncl[0]) == ra["n_clusters"] and int(ncl[1]) == rbb["n_clusters"]
+        ga = {int(order[s]): (int(cl[s]), int(st[s])) for s in range(0, h) if cl[s] >= 0}
+        gb = {int(order[s]): (int(cl[s]), int(st[s])) for s in range(h, n) if cl[s] >= 0}
+        assert ga == mem_a and gb == mem_b
+        # founders in cluster-id order = first read assigned to each cluster
+        def founders(lo, hi, nc):
+            f = np.full(nc, -1, np.int32)
+            for s in range(lo, hi):
+                if cl[s] >= 0 and f[cl[s]] < 0:
+                    f[cl[s]] = order[s]
+            return f
+        fa, fb = founders(0, h, int(ncl[0])), founders(h, n, int(ncl[1]))
+        m = api.Clusterer(rs, k, w, mode=mode, chunk_size=64)
+        try:
+            m.seed(fa)
+            tc, ts = m.cluster(fb)
+            assert m.n_clusters == rm["n_clusters"]
+        finally:
+            m.close()
+        gm = dict(ga)
+        for r, (c, s) in gb.items():
+            assert tc[c] >= 0
+            gm[r] = (int(tc[c]), s * (-1 if ts[c] == -1 else 1))
+        assert gm == mem_m
+    finally:
+        rs.close()
