@@ -11,7 +11,7 @@
 //   rows need the low rows' result of the same column, so they trail by one step).  A step is therefore four
 //   dependent packed cell updates = 8 cells, each update VIADDMNMX.S16x2 x2 (E, F), PRMT (score look-up),
 //   VIMNMX3.S16x2 (H) plus the four trace bits.  Thread g trails thread g-1 by two columns; inside a warp the
-//   hand-over is one shuffle per value, between warps a shared-memory ring read 9 steps later (warps are staggered
+//   hand-over is one shuffle per value, between warps a shared-memory ring read 8 steps after it is written (warps are staggered
 //   by 72 steps and meet at a barrier every 8 steps).
 //   Scores are stored biased, H~ = H + 2j + 64: the diagonal increment becomes {0,+4} (one byte-permute from a
 //   one-hot word per reference base), every packed value stays positive (plain 32-bit adds never carry between the
@@ -34,6 +34,7 @@ constexpr int A16_WARPS = A16_THREADS / 32;
 constexpr int A16_LAG = 72;			   // warp-to-warp stagger in steps (>= 63 + 8, multiple of 8)
 constexpr int A16_PASS_ROWS = A16_THREADS * 8;	   // 2048 query rows per pass
 constexpr int A16_BIAS = 64;
+constexpr int A16_RING = 64;			   // ring slots per warp (steps)
 constexpr uint32_t ONE2 = 0x00010001u;
 constexpr uint32_t FULL = 0xffffffffu;
 
@@ -52,7 +53,7 @@ __device__ __forceinline__ int code5(uint32_t c)
 }
 
 struct Lane16 {
-    uint32_t H[4], E[4], Ta[4], Tb[4], SEL[4];
+    uint32_t H[4], E[4], T[4], SEL[4];
     uint32_t hb, fb, hup_prev, Wprev;
     int rbest, rbj;  // best of the last row (owner lane only): first maximum
     int cbest, ci;   // best of the last column over this lane's rows: smallest row among equals
@@ -60,41 +61,51 @@ struct Lane16 {
 
 struct Pass16 {
     const uint32_t* W;	 // shared: one-hot score word per reference column, W[m] = 0
-    uint2* ring;	 // shared: [warp][32] hand-over of (H, F) between warps
+    uint2* ring;	 // shared: [warp][A16_RING] hand-over of (H, F) between warps
     uint32_t* line;	 // global: bottom row of the previous pass / of this pass
     int m, n;
     int lane, warp, pass;
     int row0;		 // first query row of this lane in this pass
     uint32_t NEGO, C2O;	 // packed -open, packed 2-open
-    bool read_line, write_line;
-    bool owner_warp;	 // this warp holds the last query row
-    int owner_lane, owner_rr;
+    int top;		 // where thread 0 of the warp takes the row above from: 0 the ring, 1 the matrix edge, 2 the line
+    bool write_line;	 // this thread is the last of a pass that is followed by another
+    bool owner;		 // this thread holds the last query row
+    int owner_rr;
 };
 
+// EDGE: some thread of the warp is outside its column range or at a boundary column in this block.
+// SPECIAL: the warp is the first of the CTA (its thread 0 takes the row above from the matrix edge / the previous pass)
+// or the last of a pass that is followed by another (its thread 31 writes the line).
 template <int Q, bool EDGE>
-__device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl)
+__device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl, const uint32_t* __restrict__ Wp, const uint2* __restrict__ rd,
+				       uint2* __restrict__ wr)
 {
+    // Wp = W + sl0 - 2*lane, rd / wr = this block's 8 ring slots to read / write (all offsets below are compile-time)
     const int lane = P.lane;
     const int jl = sl - 2 * lane;
-    const int sg = sl + A16_LAG * P.warp;
+    // thread 31 publishes the values it holds after the PREVIOUS step; the next warp reads them 8 steps later
+    if (lane == 31) wr[Q] = make_uint2(S.hb, S.fb);
     uint32_t x = __shfl_up_sync(FULL, S.hb, 1);
     uint32_t y = __shfl_up_sync(FULL, S.fb, 1);
-    if (lane == 0) {
-	if (P.warp == 0) {
-	    if (!P.read_line || jl < 0 || jl >= P.m) {
-		x = uint32_t(2 * jl + A16_BIAS) << 16;	// H[-1][j] = 0
-		y = 0x00010000u;			// F[-1][j] = -inf
-	    }
-	    else {
-		const uint32_t v = __ldcg(P.line + jl);
-		x = v << 16;
-		y = v & 0xffff0000u;
-	    }
+    {
+	uint32_t x0, y0;
+	if (P.top == 0) {  // from the warp above
+	    const uint2 v = rd[Q];
+	    x0 = v.x;
+	    y0 = v.y;
 	}
-	else {
-	    const uint2 v = P.ring[(P.warp - 1) * 32 + ((sg - 9) & 31)];
-	    x = v.x;
-	    y = v.y;
+	else if (P.top == 1 || jl < 0 || jl >= P.m) {  // first row of the matrix: H[-1][j] = 0, F[-1][j] = -inf
+	    x0 = uint32_t(2 * jl + A16_BIAS) << 16;
+	    y0 = 0x00010000u;
+	}
+	else {	// bottom row of the previous pass
+	    const uint32_t v = __ldcg(P.line + jl);
+	    x0 = v << 16;
+	    y0 = v & 0xffff0000u;
+	}
+	if (lane == 0) {
+	    x = x0;
+	    y = y0;
 	}
     }
     uint32_t hup = prmt(x, S.hb, 0x5432);  // low half <- the rows above (previous thread's high half), high half <- own low half
@@ -103,10 +114,9 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl)
     S.hup_prev = hup;
     const bool active = EDGE ? (jl >= 0 && jl <= P.m) : true;
     if (active) {
-	const uint32_t Wlo = P.W[jl];
+	const uint32_t Wlo = Wp[Q];
 	const uint32_t Whi = S.Wprev;
 	S.Wprev = Wlo;
-	constexpr int sh = 4 * (3 - (Q & 3));
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
 	    const uint32_t sc = prmt(Wlo, Whi, S.SEL[r]);
@@ -121,13 +131,8 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl)
 	    const uint32_t bv = __vmins2(Hn - F, ONE2);
 	    const uint32_t bx = __vmins2(En - ex, ONE2);
 	    const uint32_t by = __vmins2(F - fx, ONE2);
-	    uint32_t t = (Q < 4) ? S.Ta[r] : S.Tb[r];
-	    t = bu * (8u << sh) + t;
-	    t = bv * (4u << sh) + t;
-	    t = bx * (2u << sh) + t;
-	    t = by * (1u << sh) + t;
-	    if (Q < 4) S.Ta[r] = t;
-	    else S.Tb[r] = t;
+	    const uint32_t nib = ((bu * 2u + bv) * 2u + bx) * 2u + by;
+	    S.T[r] = (Q == 0 && !EDGE) ? nib : S.T[r] * 16u + nib;  // 4 steps x 4 bits per half, first step in the top nibble
 	    hd = S.H[r];
 	    S.H[r] = Hn;
 	    S.E[r] = En;
@@ -169,7 +174,7 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl)
 		}
 	    }
 	}
-	if (P.owner_warp && lane == P.owner_lane) {
+	if (P.owner) {
 	    const int r = P.owner_rr & 3;
 	    const uint32_t hv = r == 0 ? S.H[0] : r == 1 ? S.H[1] : r == 2 ? S.H[2] : S.H[3];
 	    const bool hi = P.owner_rr >= 4;
@@ -180,27 +185,35 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl)
 		S.rbj = col;
 	    }
 	}
-    }
-    if (lane == 31) {
-	P.ring[P.warp * 32 + (sg & 31)] = make_uint2(S.hb, S.fb);
-	if (P.write_line && P.warp == A16_WARPS - 1) {
+	if (P.write_line) {  // last thread of a pass that is not the last: its bottom row feeds the next pass
 	    const int jh = jl - 1;
 	    if (jh >= 0 && jh < P.m) __stcg(P.line + jh, (S.hb >> 16) | (S.fb & 0xffff0000u));
 	}
     }
+    else if (EDGE) {
+	// keep the nibble positions of the half tile aligned with the step index
+#pragma unroll
+	for (int r = 0; r < 4; r++) S.T[r] *= 16u;
+    }
 }
 
+// four steps (sl0 is a multiple of 4) and the 16-byte half tile they fill
 template <bool EDGE>
-__device__ __forceinline__ void block16(Lane16& S, const Pass16& P, int sl0)
+__device__ __forceinline__ void quad16(Lane16& S, const Pass16& P, int sl0, uint4* __restrict__ half_tile, bool store)
 {
-    step16<0, EDGE>(S, P, sl0 + 0);
-    step16<1, EDGE>(S, P, sl0 + 1);
-    step16<2, EDGE>(S, P, sl0 + 2);
-    step16<3, EDGE>(S, P, sl0 + 3);
-    step16<4, EDGE>(S, P, sl0 + 4);
-    step16<5, EDGE>(S, P, sl0 + 5);
-    step16<6, EDGE>(S, P, sl0 + 6);
-    step16<7, EDGE>(S, P, sl0 + 7);
+    const int sg0 = sl0 + A16_LAG * P.warp;  // global step of the quad start
+    const uint32_t* Wp = P.W + (sl0 - 2 * P.lane);
+    const uint2* rd = P.ring + (P.warp > 0 ? (P.warp - 1) * A16_RING : 0) + (sg0 & (A16_RING - 1));
+    uint2* wr = P.ring + P.warp * A16_RING + ((sg0 + 8) & (A16_RING - 1));
+    if (EDGE) {
+#pragma unroll
+	for (int r = 0; r < 4; r++) S.T[r] = 0;
+    }
+    step16<0, EDGE>(S, P, sl0 + 0, Wp, rd, wr);
+    step16<1, EDGE>(S, P, sl0 + 1, Wp, rd, wr);
+    step16<2, EDGE>(S, P, sl0 + 2, Wp, rd, wr);
+    step16<3, EDGE>(S, P, sl0 + 3, Wp, rd, wr);
+    if (store) *half_tile = make_uint4(S.T[0], S.T[1], S.T[2], S.T[3]);
 }
 
 __global__ void __launch_bounds__(A16_THREADS, 2)
@@ -208,7 +221,7 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 		 uint32_t* __restrict__ lines, IcbAlignEnd* __restrict__ ends)
 {
     extern __shared__ uint32_t smW[];  // m + 1 words
-    __shared__ uint2 s_ring[A16_WARPS * 32];
+    __shared__ uint2 s_ring[A16_WARPS * A16_RING];
     __shared__ int s_red[A16_WARPS * 2];
     __shared__ int s_row[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -251,7 +264,7 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
     P.NEGO = pack2(-d.open, -d.open);
     P.C2O = pack2(2 - d.open, 2 - d.open);
     const int npass = (n + A16_PASS_ROWS - 1) / A16_PASS_ROWS;
-    const int nloc = (m + 63 + 7) & ~7;	 // local steps: thread 31 of a warp finishes column m at step m + 62
+    const int nloc = (m + 64 + 7) & ~7;	 // local steps: thread 31 finishes column m at step m + 62 and publishes it at m + 63
     const int last = n - 1;
     uint4* tr = trace + d.trace_off * 2;
 
@@ -260,10 +273,9 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	const int nw = min(A16_WARPS, (rows_left + 255) >> 8);
 	P.pass = pass;
 	P.row0 = pass * A16_PASS_ROWS + tid * 8;
-	P.read_line = pass > 0;
-	P.write_line = pass + 1 < npass;
-	P.owner_warp = (last / A16_PASS_ROWS == pass) && (((last % A16_PASS_ROWS) >> 8) == warp);
-	P.owner_lane = ((last % A16_PASS_ROWS) >> 3) & 31;
+	P.top = warp > 0 ? 0 : (pass == 0 ? 1 : 2);
+	P.write_line = pass + 1 < npass && tid == A16_THREADS - 1;
+	P.owner = (last / A16_PASS_ROWS == pass) && (((last % A16_PASS_ROWS) >> 3) == tid);
 	P.owner_rr = last & 7;
 	// per-thread constants: the score selectors of its 8 rows
 #pragma unroll
@@ -274,8 +286,7 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	    S.SEL[r] = uint32_t(alo) | 0x80u | (uint32_t(4 + ahi) << 8) | 0x8000u;
 	    S.H[r] = pack2(A16_BIAS - 2, A16_BIAS - 2);	 // H[i][-1] = 0 at column -1
 	    S.E[r] = ONE2;				 // E[i][-1] = -inf
-	    S.Ta[r] = 0;
-	    S.Tb[r] = 0;
+	    S.T[r] = 0;
 	}
 	S.hb = pack2(A16_BIAS - 2, A16_BIAS - 2);
 	S.fb = ONE2;
@@ -288,18 +299,16 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	    const int sl0 = blk * 8 - A16_LAG * warp;
 	    if (warp < nw && sl0 >= 0 && sl0 < nloc) {
 		const bool edge = sl0 < 63 || sl0 + 7 > m - 2;
-		if (edge) block16<true>(S, P, sl0);
-		else block16<false>(S, P, sl0);
-		// flush the 8x8-step tile
-		if (rows_valid && sl0 + 7 >= 2 * lane && sl0 <= 2 * lane + m) {
-		    uint4* dst = tr + (int64_t(rowblock) * d.ncg + (sl0 >> 3)) * 2;
-		    dst[0] = make_uint4(S.Ta[0], S.Ta[1], S.Ta[2], S.Ta[3]);
-		    dst[1] = make_uint4(S.Tb[0], S.Tb[1], S.Tb[2], S.Tb[3]);
+		// the 8x8-step tile, filled half by half
+		const bool store = rows_valid && sl0 + 7 >= 2 * lane && sl0 <= 2 * lane + m;
+		uint4* dst = tr + (int64_t(rowblock) * d.ncg + (sl0 >> 3)) * 2;
+		if (edge) {
+#pragma unroll 1
+		    for (int hq = 0; hq < 2; hq++) quad16<true>(S, P, sl0 + 4 * hq, dst + hq, store);
 		}
-#pragma unroll
-		for (int r = 0; r < 4; r++) {
-		    S.Ta[r] = 0;
-		    S.Tb[r] = 0;
+		else {
+#pragma unroll 1
+		    for (int hq = 0; hq < 2; hq++) quad16<false>(S, P, sl0 + 4 * hq, dst + hq, store);
 		}
 	    }
 	    __syncthreads();

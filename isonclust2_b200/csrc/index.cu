@@ -15,6 +15,8 @@
 // hits in minimizer order: a bitmap over the read's minimizer ranks per relevant candidate, filled in a second
 // walk, then scanned by one thread per candidate.  Roofline class: L2/HBM latency-bound gathers (posting
 // chains), reported as hits/s; bytes per read = 12(M_f+M_r) + 8(M_f+M_r) + 8H + 16C.
+#include <mutex>
+
 #include "index.cuh"
 
 namespace {
@@ -423,13 +425,21 @@ int icb_index_insert(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, const i
 int icb_query_launch(icb_ctx* ctx, const IcbQueryArgs& a, int n_blocks, size_t smem_bytes)
 {
     if (n_blocks <= 0) return ICB_OK;
+    // the opt-in shared-memory ceiling is per function and process-wide: raise it once to the largest plan the host
+    // side ever makes (cluster.cu caps the plan at 200 KiB) so concurrent worker threads never lower it under each other
+    static std::once_flag once;
+    static cudaError_t once_err = cudaSuccess;
+    std::call_once(once, [] {
+	once_err = cudaFuncSetAttribute(icb_k_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	if (once_err == cudaSuccess)
+	    once_err = cudaFuncSetAttribute(icb_k_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    ICB_CUDA(ctx, once_err);
     if (a.smem_cnt) {
-	ICB_CUDA(ctx, cudaFuncSetAttribute(icb_k_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
 	ICB_LAUNCH(ctx, a.mode ? "index_query_full" : "index_query",
 		   icb_k_query<true><<<n_blocks, Q_THREADS, smem_bytes, ctx->stream>>>(a));
     }
     else {
-	ICB_CUDA(ctx, cudaFuncSetAttribute(icb_k_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
 	ICB_LAUNCH(ctx, a.mode ? "index_query_full" : "index_query",
 		   icb_k_query<false><<<n_blocks, Q_THREADS, smem_bytes, ctx->stream>>>(a));
     }
