@@ -216,7 +216,7 @@ __device__ __forceinline__ void quad16(Lane16& S, const Pass16& P, int sl0, uint
     if (store) *half_tile = make_uint4(S.T[0], S.T[1], S.T[2], S.T[3]);
 }
 
-__global__ void __launch_bounds__(A16_THREADS, 2)
+__global__ void __launch_bounds__(A16_THREADS, 4)
 icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, uint4* __restrict__ trace,
 		 uint32_t* __restrict__ lines, IcbAlignEnd* __restrict__ ends)
 {
