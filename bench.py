@@ -96,7 +96,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    pipe = dict(k=K, w=W_, mode=MODE, min_qual=MIN_QUAL, batch_kb=BATCH_KB, batch_max_seq=args.batch_max_seq, chunk_size=args.chunk)
+    pipe = dict(k=K, w=W_, mode=MODE, min_qual=MIN_QUAL, batch_kb=BATCH_KB, batch_max_seq=args.batch_max_seq, chunk_size=args.chunk,
+                n_workers=args.workers)
 
     # ---------------- device-resident steps: reads already in HBM
     rs = ctx.upload(seq, qual, offs)
@@ -169,8 +170,7 @@ def run_ours(args):
         "metric": METRIC, "value": world * n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/u32/i32 (+f64 quality chains)", "data": "synthetic",
-        "config": {"workload": f"configs[1] read set: {n_reads} synthetic ONT cDNA reads per GPU (~1.3 kb mean, 8% error), k=11 w=15, "
-                               f"sort + cluster -x sahlin of every batch (B={BATCH_KB} kb, M={args.batch_max_seq})",
+        "config": {**workload_config(n_reads, args.batch_max_seq),
                    "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "batches": len(res["batches"]),
                    "clusters": int(sum(res["n_clusters"])), "reads_clustered": clustered,
                    "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"reads sharded x{world}, no collective"},
@@ -188,7 +188,7 @@ def run_ours(args):
         "clocks": summarize_clocks(samples),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(seq, qual, offs, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = cpu_baseline_subprocess(args)
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -196,65 +196,108 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(seq, qual, offs, budget_s=20.0):
-    """The reference's own CPU implementation of the same step on a bounded sample of the same reads:
-    FillQualScores + SortByQualScores + PrepareSortedBatch (TBB, all host cores) then ClusterSortedReads -x sahlin
-    (single-threaded, as in the reference).  Falls back to the C restatement when oracle/_ref is absent."""
+def _ref_cluster_worker(args):
+    """One `isONclust2 cluster -x sahlin` job: runs in a forked child on the parent's sorted batch (copy-on-write)."""
+    lo, hi, nr = args
+    t0 = time.perf_counter()
+    rc = _REF_STATE["batch"].slice(lo, hi, nr).cluster(0)
+    return rc["n_clusters"], time.perf_counter() - t0
+
+
+_REF_STATE = {}
+
+
+def reference_step(seq, qual, offs, batch_reads, cores):
+    """The reference's own CPU implementation of one step over the given reads: `sort` (FillQualScores + SortByQualScores +
+    PrepareSortedBatch, TBB on all host cores) then one single-threaded `cluster -x sahlin` job per batch, `cores` jobs at a
+    time — how the reference's pipeline runs it (README.md:105-117).  Returns (seconds, clusters, kind)."""
+    import multiprocessing as mp
+
     import oracle
     from isonclust2_b200 import pemp
 
     n = len(offs) - 1
+    bounds = list(range(0, n, batch_reads)) + [n]
+    t0 = time.perf_counter()
     if oracle.have_ref():
         R = oracle.ref()
-        kind, cores = "reference", os.cpu_count()
-
-        def run(m):
-            b = R.sort_and_sketch(seq[:offs[m]], qual[:offs[m]], offs[:m + 1], K, W_, MIN_QUAL)
-            b.cluster(0)
-    else:
-        P = oracle.port()
-        kind, cores = "port", 1
-
-        def run(m):
-            s, e = P.fill_scores(qual, offs[:m + 1], K)
-            o = P.sort_order(s)
-            sk = P.sketch_batch(seq, qual, offs[:m + 1], K, W_)
-            P.cluster(seq, offs[:m + 1], sk, s, e, o, K, W_, 0, pemp.load_p_shared(K, W_))
-    sample = min(n, 1000)
-    t0 = time.perf_counter()
-    run(sample)
-    dt = time.perf_counter() - t0
-    if dt < budget_s / 3 and sample < n:  # grow the sample towards the time budget (once)
-        sample = int(min(n, sample * min(10.0, budget_s / max(dt, 1e-3) / 1.5)))
-        t0 = time.perf_counter()
-        run(sample)
-        dt = time.perf_counter() - t0
-    return {"value": sample / dt, "unit": "reads/s", "cores": cores, "kind": kind,
-            "sample": f"first {sample} reads of the same workload as one batch, {dt:.2f} s "
-                      f"(sort+sketch on {cores} threads, cluster single-threaded like the reference)"}
+        batch = R.sort_and_sketch(seq, qual, offs, K, W_, MIN_QUAL)
+        _REF_STATE["batch"] = batch
+        jobs = [(bounds[i], bounds[i + 1] - 1, i) for i in range(len(bounds) - 1)]
+        if len(jobs) == 1:
+            out = [_ref_cluster_worker(jobs[0])]
+        else:
+            with mp.get_context("fork").Pool(min(cores, len(jobs))) as pool:
+                out = pool.map(_ref_cluster_worker, jobs, chunksize=1)
+        _REF_STATE.clear()
+        return time.perf_counter() - t0, int(sum(o[0] for o in out)), "reference"
+    # no compiled reference on this box: the C restatement, one thread
+    P = oracle.port()
+    s, e = P.fill_scores(qual, offs, K)
+    o = P.sort_order(s)
+    sk = P.sketch_batch(seq, qual, offs, K, W_)
+    ncl = 0
+    for i in range(len(bounds) - 1):
+        ncl += P.cluster(seq, offs, sk, s, e, o[bounds[i]:bounds[i + 1]], K, W_, 0, pemp.load_p_shared(K, W_))["n_clusters"]
+    return time.perf_counter() - t0, int(ncl), "port"
 
 
-def run_reference(args):
+def run_reference(args, quiet=False):
+    """--impl reference: the reference's CPU path on the host cores, on a bounded sample of the same workload
+    (same generator and seed, same k / w / mode / batch size; `cores` batches so every core has one cluster job)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
+    import oracle
     from isonclust2_b200 import synth
 
-    n_reads = min(args.reads, 20000)
-    seq, qual, offs = synth.make_reads(n_reads, seed=100, err_set=(0.08,))
-    vals, cb = [], None
-    for i in range(min(args.warmup, 1) + args.steps):
-        cb = cpu_baseline(seq, qual, offs, budget_s=args.cpu_budget)
-        if i >= min(args.warmup, 1):
-            vals.append(cb["value"])
-    v = float(np.mean(vals)) if vals else cb["value"]
-    cb["value"] = v
+    cores = os.cpu_count() or 1
+    batch_reads = min(args.batch_max_seq, args.ref_batch_reads)
+    n_batches = max(1, min(cores, args.reads // batch_reads)) if oracle.have_ref() else 1
+    n_reads = n_batches * batch_reads
+    seq, qual, offs = synth.make_reads(args.reads, seed=100, err_set=(0.08,))
+    seq, qual, offs = seq[:offs[n_reads]], qual[:offs[n_reads]], offs[:n_reads + 1]
+    for _ in range(args.warmup):  # a CPU run has nothing to warm but the page cache: one small batch per warm-up step
+        m = min(n_reads, 500)
+        reference_step(seq[:offs[m]], qual[:offs[m]], offs[:m + 1], m, 1)
+    secs, kind, ncl = [], "port", 0
+    for _ in range(max(args.steps, 1)):
+        dt, ncl, kind = reference_step(seq, qual, offs, batch_reads, cores)
+        secs.append(dt)
+    dt = float(np.mean(secs))
+    v = n_reads / dt
+    used = min(cores, n_batches) if kind == "reference" else 1
+    cb = {"value": v, "unit": "reads/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+          "sample": f"{n_reads} reads of the same workload = {n_batches} batches of {batch_reads}: sort + sketch on {cores} TBB threads, "
+                    f"then {used} single-threaded `cluster -x sahlin` jobs in parallel; {dt:.1f} s per step, {ncl} clusters"}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u32/i32 (+f64 quality chains)", "data": "synthetic",
-            "config": {"workload": "configs[1] read set, bounded sample on the host cores: sort + cluster -x sahlin"},
+            "config": workload_config(args.reads, args.batch_max_seq),
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    if not quiet:
+        print(json.dumps(line), flush=True)
+    return line
+
+
+def cpu_baseline_subprocess(args):
+    """cpu_baseline of the main line: the reference arm on a smaller bounded sample, in a fresh process (no CUDA state
+    is forked)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--reads", str(args.reads),
+           "--batch-max-seq", str(args.batch_max_seq), "--ref-batch-reads", str(args.cpu_baseline_batch_reads)]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"value": None, "unit": "reads/s", "cores": 0, "kind": "failed", "sample": (r.stderr or "no output")[-300:]}
+    except Exception as ex:  # noqa: BLE001
+        return {"value": None, "unit": "reads/s", "cores": 0, "kind": "failed", "sample": repr(ex)[:300]}
+
+
+def workload_config(reads, batch_max_seq):
+    return {"workload": f"configs[1] read set: {reads} synthetic ONT cDNA reads per GPU (~1.3 kb mean, 8% error), k={K} w={W_}, "
+                        f"sort + cluster -x {MODE} of every batch (B={BATCH_KB} kb, M={batch_max_seq})"}
 
 
 def main():
@@ -262,12 +305,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads", type=int, default=100_000, help="reads per GPU")
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU (configs[1]: 1M)")
+    ap.add_argument("--workers", type=int, default=0, help="batches in flight per GPU (0 = library default)")
+    ap.add_argument("--ref-batch-reads", type=int, default=BATCH_MAX_SEQ, help="--impl reference: reads per batch of its sample")
+    ap.add_argument("--cpu-baseline-batch-reads", type=int, default=5000, help="cpu_baseline leg: reads per batch of its sample")
     ap.add_argument("--batch-max-seq", type=int, default=BATCH_MAX_SEQ)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
