@@ -50,8 +50,11 @@ struct SketchArgs {
     int64_t* min_off;
     int32_t* nf;
     int32_t* nr;
-    unsigned long long* counters;  // [0] arena cursor [1] error flags [2] long list cursor [3] work ticket
-    int32_t* long_list;
+    unsigned long long* counters;  // [0] arena cursor [1] error flags [2] list-1 length [3] ticket (stage 1) [4] list-2 length
+				   // [5] ticket (stage 2) [6] ticket (stage 3)
+    int32_t* long_list;		   // list 1: reads the warp kernel handed on (too long for it, or too many minimizers)
+    int32_t* long_list2;	   // list 2: reads longer than the shared-memory CTA kernel takes
+    int use_list;		   // CTA kernel: 0 = all reads by ticket, 1 = the reads of list 1
     uint8_t* long_scratch;	   // GLOBAL variant: per-CTA scratch
     int64_t long_scratch_stride;
     int64_t lmax;		   // capacity (bases) of the per-read buffers
@@ -152,11 +155,15 @@ __global__ void __launch_bounds__(SK_THREADS) icb_k_sketch(SketchArgs a)
 	__syncthreads();
 	if (tid == 0) {
 	    if (GLOBAL) {
-		unsigned long long t = atomicAdd(&a.counters[3], 1ull);
+		unsigned long long t = atomicAdd(&a.counters[6], 1ull);
+		s_next = t < a.counters[4] ? a.long_list2[t] : -1;
+	    }
+	    else if (a.use_list) {
+		unsigned long long t = atomicAdd(&a.counters[5], 1ull);
 		s_next = t < a.counters[2] ? a.long_list[t] : -1;
 	    }
 	    else {
-		unsigned long long t = atomicAdd(&a.counters[3], 1ull);
+		unsigned long long t = atomicAdd(&a.counters[5], 1ull);
 		s_next = t < (unsigned long long)a.n_reads ? int(t) : -1;
 	    }
 	}
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(SK_THREADS) icb_k_sketch(SketchArgs a)
 		continue;
 	    }
 	    if (L > lmax) {
-		if (tid == 0) a.long_list[atomicAdd(&a.counters[2], 1ull)] = r;
+		if (tid == 0) a.long_list2[atomicAdd(&a.counters[4], 1ull)] = r;
 		continue;
 	    }
 	}
@@ -409,6 +416,369 @@ __global__ void __launch_bounds__(SK_THREADS) icb_k_sketch(SketchArgs a)
     }
 }
 
+// ================================================================================================
+// Warp-per-read kernel (the fast path: 2k + 5 <= 32 bits of key, W in {5, 8}, raw length <= SW_LMAX)
+//
+// One warp owns one read; nothing is block-synchronised.  Every lane keeps 16 consecutive bases (phase A) or 16
+// consecutive windows (phase B) in registers, so the per-base work is SWAR / packed arithmetic instead of one thread
+// per base:
+//   A. run ends of a 16-base chunk from three SWAR operations per word, ranks by popc + one warp scan, the run
+//      maximum of the qualities by a 16-step register loop (carried across lanes by a segmented warp scan);
+//   B. the compressed read is packed twice at 2 bits per base — big-endian (forward k-mers are the top bits of a funnel
+//      shift) and little-endian complemented (reverse-complement k-mers are the low bits) — and validated (ACGT only);
+//      a window minimum is VIMNMX3 over packed keys (value << 5 | position in the lane's frame), which yields the
+//      leftmost (forward) / rightmost (reverse strand) argmin directly; "argmin changed" is one compare of two keys;
+//   C. flagged argmin positions go to a per-warp list in shared memory, the read's slice of the arena is claimed with
+//      one atomicAdd and lane j writes minimizer j: fully coalesced 12-byte records.
+constexpr int SW_WARPS = 8;
+constexpr int SW_THREADS = SW_WARPS * 32;
+constexpr int SW_LMAX = 3072;		    // longest raw read on this path
+constexpr int SW_HBUF = SW_LMAX + 32;	    // bytes per compressed buffer: 16-byte phase of the global slot + slack
+constexpr int SW_NWORD = SW_LMAX / 16 + 4;  // packed words per stream
+constexpr int SW_LIST = SW_HBUF / 2;	    // argmin positions (uint16) per strand that fit the reused buffers
+constexpr int SW_PER_WARP = 2 * SW_HBUF + 2 * SW_NWORD * 4;
+constexpr int SW_TICKET = 4;		    // reads taken per ticket
+
+__device__ __forceinline__ uint32_t sw_prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+// bit i of the result = byte i of x is non-zero
+__device__ __forceinline__ uint32_t sw_nonzero_bytes(uint32_t x)
+{
+    uint32_t t = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+    return (t * 0x00204081u) >> 28;
+}
+
+template <int W>
+__global__ void __launch_bounds__(SW_THREADS, 3) icb_k_sketch_warp(SketchArgs a)
+{
+    extern __shared__ __align__(16) uint8_t sw_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* hs = sw_smem + warp * SW_PER_WARP;
+    uint8_t* hq = hs + SW_HBUF;
+    uint32_t* Fs = reinterpret_cast<uint32_t*>(hq + SW_HBUF);
+    uint32_t* Rs = Fs + SW_NWORD;
+    const int k = a.k;
+    const uint32_t kmask = (1u << (2 * k)) - 1u;
+
+    for (;;) {
+	long long t0 = 0;
+	if (lane == 0) t0 = (long long)atomicAdd(&a.counters[3], (unsigned long long)SW_TICKET);
+	t0 = __shfl_sync(0xffffffffu, t0, 0);
+	if (t0 >= a.n_reads) break;
+	for (int tr = 0; tr < SW_TICKET; tr++) {
+	    const long long r = t0 + tr;
+	    if (r >= a.n_reads) break;
+	    __syncwarp();
+	    const int64_t start = a.offs[r];
+	    const int L = int(a.offs[r + 1] - start);
+	    if (a.skip && a.skip[r]) {
+		if (lane == 0) { a.status[r] = 0; a.hpc_len[r] = 0; a.nf[r] = 0; a.nr[r] = 0; a.min_off[r] = 0; }
+		continue;
+	    }
+	    // qualscore.cpp:62-63: compress only if raw length > 2k or >= w
+	    if (!(unsigned(L) > unsigned(2 * k) || unsigned(L) >= unsigned(a.w))) {
+		if (lane == 0) { a.status[r] = 2; a.hpc_len[r] = 0; a.nf[r] = 0; a.nr[r] = 0; a.min_off[r] = 0; }
+		continue;
+	    }
+	    if (L > SW_LMAX) {
+		if (lane == 0) a.long_list[atomicAdd(&a.counters[2], 1ull)] = int(r);
+		continue;
+	    }
+	    const int shiftA = int(start & 15);  // hs / hq keep the 16-byte phase of the global slot
+	    const uint8_t* gseq = a.seq + (start - shiftA);
+	    const uint8_t* gqual = a.qual + (start - shiftA);
+
+	    // ============================================================ phase A: homopolymer compression
+	    int runBase = 0;
+	    int tileCarry = -128;  // running quality maximum of a run left open by the previous tile
+	    const int nchunks = (shiftA + L + 15) >> 4;
+	    for (int c0 = 0; c0 < nchunks; c0 += 32) {
+		const int c = c0 + lane;
+		const int pfirst = 16 * c - shiftA;  // raw position of byte 0 of this lane's chunk
+		uint4 s4 = make_uint4(0, 0, 0, 0), q4 = make_uint4(0, 0, 0, 0);
+		if (c < nchunks) {
+		    s4 = *reinterpret_cast<const uint4*>(gseq + 16 * c);
+		    q4 = *reinterpret_cast<const uint4*>(gqual + 16 * c);
+		}
+		// valid bytes of the chunk: raw positions 0 .. L-1
+		const int lo = max(0, -pfirst), hi = min(16, L - pfirst);
+		uint32_t vmask = hi > lo ? ((0xffffu >> (16 - hi)) & (0xffffu << lo)) : 0u;
+		// the byte after the chunk: first byte of the next lane's chunk; lane 31 reads it (it exists: slack after the buffers)
+		uint32_t nb = __shfl_down_sync(0xffffffffu, s4.x, 1);
+		if (lane == 31) nb = (c < nchunks) ? uint32_t(gseq[16 * c + 16]) : 0u;
+		// run ends: byte i differs from byte i+1
+		uint32_t e = sw_nonzero_bytes(s4.x ^ __funnelshift_r(s4.x, s4.y, 8)) |
+			     (sw_nonzero_bytes(s4.y ^ __funnelshift_r(s4.y, s4.z, 8)) << 4) |
+			     (sw_nonzero_bytes(s4.z ^ __funnelshift_r(s4.z, s4.w, 8)) << 8) |
+			     (sw_nonzero_bytes(s4.w ^ __funnelshift_r(s4.w, nb, 8)) << 12);
+		const int ilast = L - 1 - pfirst;  // the last base of the read always ends a run
+		if (ilast >= 0 && ilast < 16) e |= 1u << ilast;
+		e &= vmask;
+		if (vmask != 0xffffu) {
+		    // bytes outside the read must not contribute to a run maximum: quality -128
+		    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+#pragma unroll
+		    for (int i = 0; i < 4; i++) {
+			m0 |= ((vmask >> i) & 1u) * (0xffu << (8 * i));
+			m1 |= ((vmask >> (4 + i)) & 1u) * (0xffu << (8 * i));
+			m2 |= ((vmask >> (8 + i)) & 1u) * (0xffu << (8 * i));
+			m3 |= ((vmask >> (12 + i)) & 1u) * (0xffu << (8 * i));
+		    }
+		    q4.x = (q4.x & m0) | (0x80808080u & ~m0);
+		    q4.y = (q4.y & m1) | (0x80808080u & ~m1);
+		    q4.z = (q4.z & m2) | (0x80808080u & ~m2);
+		    q4.w = (q4.w & m3) | (0x80808080u & ~m3);
+		}
+		// ranks of the run ends
+		const int cnt = __popc(e);
+		int inc = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+		    int v = __shfl_up_sync(0xffffffffu, inc, d);
+		    if (lane >= d) inc += v;
+		}
+		int pos = shiftA + runBase + inc - cnt;
+		const int pos0 = pos;
+		runBase += __shfl_sync(0xffffffffu, inc, 31);
+		// 16-step register loop: running maximum of the open run, one (base, max) pair stored per run end
+		int qmax = -128;
+		const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+		const uint32_t qw[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+		for (int i = 0; i < 16; i++) {
+		    const uint32_t ch = (sw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+		    const int qv = int(qw[i >> 2] << (24 - 8 * (i & 3))) >> 24;  // hpc.cpp:24 compares chars (signed)
+		    qmax = max(qmax, qv);
+		    if (e & (1u << i)) {
+			hs[pos] = uint8_t(ch);
+			hq[pos] = uint8_t(qmax);
+			pos++;
+			qmax = -128;
+		    }
+		}
+		// carry of a run that is still open at the end of a chunk into the next chunk(s)
+		const bool open = vmask != 0 && !(e & 0x8000u) && hi == 16;
+		int cv = open ? qmax : -128;
+		bool pass = open && e == 0;  // the whole chunk belongs to one open run
+		if (lane == 0 && pass) cv = max(cv, tileCarry);
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+		    const int v2 = __shfl_up_sync(0xffffffffu, cv, d);
+		    const int p2 = __shfl_up_sync(0xffffffffu, int(pass), d);
+		    if (lane >= d && pass) {
+			cv = max(cv, v2);
+			pass = p2 != 0;
+		    }
+		}
+		int carryIn = __shfl_up_sync(0xffffffffu, cv, 1);
+		if (lane == 0) carryIn = tileCarry;
+		tileCarry = __shfl_sync(0xffffffffu, cv, 31);
+		if (carryIn > -128 && e != 0) {
+		    const int qv = int((signed char)hq[pos0]);
+		    if (carryIn > qv) hq[pos0] = uint8_t(carryIn);
+		}
+	    }
+	    __syncwarp();
+	    const int Lh = runBase;
+	    if (unsigned(Lh) < unsigned(2 * k) || unsigned(Lh) < unsigned(a.w)) {  // qualscore.cpp:65-66
+		if (lane == 0) { a.status[r] = 3; a.hpc_len[r] = Lh; a.nf[r] = 0; a.nr[r] = 0; a.min_off[r] = 0; }
+		continue;
+	    }
+	    // ---- pack 2 bits per base (both streams), check ACGT; word j of a stream = compressed bases 16j .. 16j+15
+	    {
+		const uint32_t* hsw = reinterpret_cast<const uint32_t*>(hs);
+		const int wsh = shiftA >> 2, bsh = 8 * (shiftA & 3);
+		const int nwords = (Lh + 15) >> 4;
+		uint32_t badacc = 0;
+		for (int j = lane; j < SW_NWORD; j += 32) {
+		    uint32_t F = 0, R = 0;
+		    if (j < nwords) {
+			uint32_t x[5];
+#pragma unroll
+			for (int i = 0; i < 5; i++) x[i] = hsw[wsh + 4 * j + i];
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+			    const uint32_t wv = __funnelshift_r(x[i], x[i + 1], bsh);	// bases 16j+4i .. +3, first base in the low byte
+			    const uint32_t cd = ((wv >> 1) & 0x03030303u) ^ ((wv >> 2) & 0x01010101u);	// A,C,G,T -> 0..3 per byte
+			    uint32_t sel = (cd | (cd >> 4)) & 0x00ff00ffu;
+			    sel = (sel | (sel >> 8)) & 0xffffu;
+			    uint32_t diff = sw_prmt(0x54474341u, 0u, sel) ^ wv;	// "ACGT"[code] must give the base back
+			    const int nvalid = Lh - (16 * j + 4 * i);
+			    if (nvalid < 4) diff &= nvalid <= 0 ? 0u : (0xffffffffu >> (32 - 8 * nvalid));
+			    badacc |= diff;
+			    F |= ((cd * 0x40100401u) >> 24) << (24 - 8 * i);		   // b0<<6 | b1<<4 | b2<<2 | b3
+			    R |= (((cd ^ 0x03030303u) * 0x01041040u) >> 24) << (8 * i);   // complement: b0 | b1<<2 | b2<<4 | b3<<6
+			}
+		    }
+		    Fs[j] = F;
+		    Rs[j] = R;
+		}
+		if (__any_sync(0xffffffffu, badacc != 0)) {
+		    // the reference's RevComp throws here (util.cpp:31-33)
+		    if (lane == 0) { atomicOr(&a.counters[1], 1ull); a.status[r] = -1; a.hpc_len[r] = Lh; a.nf[r] = 0; a.nr[r] = 0; a.min_off[r] = 0; }
+		    continue;
+		}
+	    }
+	    // ---- compressed read -> global (16-byte chunks share the phase of the global slot)
+	    {
+		uint8_t* gs = a.hpc_seq + (start - shiftA);
+		uint8_t* gq = a.hpc_qual + (start - shiftA);
+		const int lo = shiftA, hi = shiftA + Lh;
+		const int nch = (hi + 15) >> 4;
+		for (int c = lane; c < nch; c += 32) {
+		    const int b0 = c << 4;
+		    if (b0 >= lo && b0 + 16 <= hi) {
+			reinterpret_cast<uint4*>(gs)[c] = reinterpret_cast<const uint4*>(hs)[c];
+			reinterpret_cast<uint4*>(gq)[c] = reinterpret_cast<const uint4*>(hq)[c];
+		    }
+		    else {
+			for (int b = b0; b < b0 + 16; b++)
+			    if (b >= lo && b < hi) {
+				gs[b] = hs[b];
+				gq[b] = hq[b];
+			    }
+		    }
+		}
+	    }
+	    __syncwarp();
+	    // ============================================================ phase B: window minima, flags, argmin lists
+	    uint16_t* posF = reinterpret_cast<uint16_t*>(hs);  // the compressed bytes are in global memory now
+	    uint16_t* posR = reinterpret_cast<uint16_t*>(hq);
+	    const int nk = Lh - k;	   // k-mers per strand (kmer_index.cpp:12 drops the last one)
+	    const int nwin = nk - W + 1;   // forward windows q = 0 .. nwin-1, reverse windows (forward coordinates) q = 1 .. nwin
+	    int Mf = 0, Mr = 0;
+	    bool overflow = false;
+	    if (nwin > 0) {
+		uint32_t prevF = 0, prevR = 0;	// last window keys of the previous tile's lane 31 (in that lane's frame)
+		for (int q00 = 0; q00 <= nwin + 1; q00 += 512) {
+		    const int q0 = q00 + 16 * lane;
+		    const int jw = min(q0 >> 4, SW_NWORD - 3);	// lanes past the end of the read only produce unused keys
+		    const uint32_t fB = Fs[jw], fC = Fs[jw + 1], fD = Fs[jw + 2], rB = Rs[jw], rC = Rs[jw + 1], rD = Rs[jw + 2];
+		    // keys of the k-mers at positions q0 + o, o = 0 .. 15 + W - 1; frame index i = o + 1 (i = 0 is position q0 - 1)
+		    uint32_t kf[16 + W - 1], kr[16 + W - 1];
+#pragma unroll
+		    for (int o = 0; o < 16 + W - 1; o++) {
+			const uint32_t y = o == 0 ? fB : (o < 16 ? __funnelshift_l(fC, fB, 2 * o) : (o == 16 ? fC : __funnelshift_l(fD, fC, 2 * (o - 16))));
+			const uint32_t vf = y >> (32 - 2 * k);
+			const uint32_t z = o == 0 ? rB : (o < 16 ? __funnelshift_r(rB, rC, 2 * o) : (o == 16 ? rC : __funnelshift_r(rC, rD, 2 * (o - 16))));
+			const uint32_t vr = z & kmask;
+			kf[o] = vf * 32u + uint32_t(o + 1);	   // smallest key = smallest value, leftmost position
+			kr[o] = vr * 32u + uint32_t(31 - (o + 1)); // reverse strand: leftmost there = rightmost here
+		    }
+		    uint32_t mf[16], mr[16];
+#pragma unroll
+		    for (int t = 0; t < 16; t++) {
+			uint32_t x = kf[t], y = kr[t];
+#pragma unroll
+			for (int u = 1; u + 1 < W; u += 2) {
+			    x = __vimin3_u32(x, kf[t + u], kf[t + u + 1]);
+			    y = __vimin3_u32(y, kr[t + u], kr[t + u + 1]);
+			}
+			if ((W & 1) == 0) {
+			    x = min(x, kf[t + W - 1]);
+			    y = min(y, kr[t + W - 1]);
+			}
+			mf[t] = x;
+			mr[t] = y;
+		    }
+		    // key of the window before this lane's first one, moved into this lane's frame (16 positions further)
+		    uint32_t pf = __shfl_up_sync(0xffffffffu, mf[15], 1), pr = __shfl_up_sync(0xffffffffu, mr[15], 1);
+		    if (lane == 0) {
+			pf = prevF;
+			pr = prevR;
+		    }
+		    pf -= 16u;	// forward key holds +index
+		    pr += 16u;	// reverse key holds 31 - index
+		    prevF = __shfl_sync(0xffffffffu, mf[15], 31);
+		    prevR = __shfl_sync(0xffffffffu, mr[15], 31);
+		    // forward flag of window q: its argmin differs from window q-1 (always for q = 0)
+		    // reverse flag, kept by the owner of window q, belongs to window q-1: its argmin differs from window q
+		    // (always for q-1 = nwin)
+		    uint32_t ff = 0, fr = 0;
+#pragma unroll
+		    for (int t = 0; t < 16; t++) {
+			const int q = q0 + t;
+			const uint32_t bf = t == 0 ? pf : mf[t - 1];
+			const uint32_t br = t == 0 ? pr : mr[t - 1];
+			const bool f1 = q < nwin && (q == 0 || mf[t] != bf);
+			const bool f2 = q - 1 >= 1 && q - 1 <= nwin && (q - 1 == nwin || mr[t] != br);
+			ff |= uint32_t(f1) << t;
+			fr |= uint32_t(f2) << t;
+		    }
+		    // ranks
+		    const int cf = __popc(ff), cr = __popc(fr);
+		    int inc = cf | (cr << 16);
+#pragma unroll
+		    for (int d = 1; d < 32; d <<= 1) {
+			int v = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += v;
+		    }
+		    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+		    int rf = Mf + (inc & 0xffff) - cf, rr = Mr + (inc >> 16) - cr;
+		    Mf += tot & 0xffff;
+		    Mr += tot >> 16;
+		    if (Mf > SW_LIST || Mr > SW_LIST) {
+			overflow = true;
+			break;
+		    }
+		    // argmin positions (k-mer start, forward coordinates) of the flagged windows
+#pragma unroll
+		    for (int t = 0; t < 16; t++) {
+			if (ff & (1u << t)) posF[rf++] = uint16_t(q0 - 1 + int(mf[t] & 31u));
+			if (fr & (1u << t)) {
+			    const uint32_t key = t == 0 ? pr : mr[t - 1];
+			    posR[rr++] = uint16_t(q0 - 1 + (31 - int(key & 31u)));
+			}
+		    }
+		}
+	    }
+	    if (overflow) {  // more minimizers than the shared-memory lists hold: the CTA kernel takes the read
+		if (lane == 0) a.long_list[atomicAdd(&a.counters[2], 1ull)] = int(r);
+		continue;
+	    }
+	    __syncwarp();
+	    // ============================================================ phase C: claim the slice, write triples
+	    long long base = 0;
+	    if (lane == 0) {
+		base = (long long)atomicAdd(&a.counters[0], (unsigned long long)(Mf + Mr));
+		a.status[r] = 1;
+		a.hpc_len[r] = Lh;
+		a.nf[r] = Mf;
+		a.nr[r] = Mr;
+		a.min_off[r] = base;
+	    }
+	    base = __shfl_sync(0xffffffffu, base, 0);
+	    if (base + Mf + Mr <= a.mins_capacity) {
+		icb_minimizer* of = a.mins + base;
+		icb_minimizer* orv = of + Mf;
+		for (int j = lane; j < Mf; j += 32) {
+		    const int p = posF[j];
+		    const uint32_t y = __funnelshift_l(Fs[(p >> 4) + 1], Fs[p >> 4], 2 * (p & 15));
+		    icb_minimizer m;
+		    m.Min = y >> (32 - 2 * k);
+		    m.Pos = uint32_t(p);
+		    m.Index = uint32_t(j);
+		    of[j] = m;
+		}
+		for (int j = lane; j < Mr; j += 32) {
+		    const int p = posR[j];
+		    const uint32_t z = __funnelshift_r(Rs[p >> 4], Rs[(p >> 4) + 1], 2 * (p & 15));
+		    const int idx = Mr - 1 - j;
+		    icb_minimizer m;
+		    m.Min = z & kmask;
+		    m.Pos = uint32_t(nk - p);  // position in reverse-complement coordinates
+		    m.Index = uint32_t(idx);
+		    orv[idx] = m;
+		}
+	    }
+	}
+    }
+}
+
 template <typename PT>
 size_t per_read_bytes(int64_t lmax)
 {
@@ -457,22 +827,49 @@ int icb_launch_sketch(icb_readset* rs, int k, int w, const uint8_t* d_skip)
     a.nr = rs->d_nr;
     a.counters = rs->d_counters;
     a.long_list = rs->d_long_list;
+    a.long_list2 = rs->d_long_list + rs->n_reads + 1;
+    a.use_list = 0;
     a.long_scratch = nullptr;
     a.long_scratch_stride = 0;
     a.lmax = LMAX_FAST;
     if (rs->n_reads == 0) return ICB_OK;
+    cudaStream_t st = ctx->stream;
+    const int W = w - k + 1;
 
-    size_t smem = STAGE_BYTES + per_read_bytes<uint16_t>(LMAX_FAST);
-    ICB_CUDA(ctx, cudaFuncSetAttribute(icb_k_sketch<false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    int per_sm = 0;
-    ICB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icb_k_sketch<false, uint16_t>, SK_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
-    int64_t grid = int64_t(ctx->sm_count) * per_sm;
-    if (grid > rs->n_reads) grid = rs->n_reads;
-    ICB_LAUNCH(ctx, "sketch_reads", icb_k_sketch<false, uint16_t><<<unsigned(grid), SK_THREADS, smem, ctx->stream>>>(a));
-
+    // ---- stage 1: warp-per-read kernel (keys of 2k + 5 bits, compiled window widths)
+    const bool warp_path = 2 * k + 5 <= 32 && k >= 2 && (W == 5 || W == 8);
+    if (warp_path) {
+	const size_t smem = size_t(SW_WARPS) * SW_PER_WARP;
+	auto kern = W == 5 ? icb_k_sketch_warp<5> : icb_k_sketch_warp<8>;
+	ICB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	int per_sm = 0;
+	ICB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SW_THREADS, smem));
+	if (per_sm < 1) per_sm = 1;
+	int64_t grid = int64_t(ctx->sm_count) * per_sm;
+	const int64_t need = (rs->n_reads + int64_t(SW_WARPS) * SW_TICKET - 1) / (int64_t(SW_WARPS) * SW_TICKET);
+	if (grid > need) grid = need;
+	ICB_LAUNCH(ctx, "sketch_reads", kern<<<unsigned(grid), SW_THREADS, smem, st>>>(a));
+	// reads it handed on (longer than SW_LMAX, or too many minimizers for its lists)
+	unsigned long long c[8];
+	ICB_CUDA(ctx, cudaMemcpyAsync(c, rs->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+	if (c[2] == 0) return ICB_OK;
+	a.use_list = 1;
+    }
+    // ---- stage 2: CTA-per-read kernel, buffers in shared memory (every k / w; reads up to LMAX_FAST)
+    {
+	size_t smem = STAGE_BYTES + per_read_bytes<uint16_t>(LMAX_FAST);
+	ICB_CUDA(ctx, cudaFuncSetAttribute(icb_k_sketch<false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	int per_sm = 0;
+	ICB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icb_k_sketch<false, uint16_t>, SK_THREADS, smem));
+	if (per_sm < 1) per_sm = 1;
+	int64_t grid = int64_t(ctx->sm_count) * per_sm;
+	if (grid > rs->n_reads) grid = rs->n_reads;
+	ICB_LAUNCH(ctx, warp_path ? "sketch_reads_cta" : "sketch_reads",
+		   icb_k_sketch<false, uint16_t><<<unsigned(grid), SK_THREADS, smem, st>>>(a));
+    }
+    // ---- stage 3: the same code with its buffers in a global scratch arena, for reads above LMAX_FAST
     if (rs->max_len > LMAX_FAST) {
-	// slow path for the reads the fast kernel listed: same code, buffers in global scratch
 	const int nblk = 64;
 	int64_t lmaxL = (rs->max_len + 63) & ~int64_t(31);
 	int64_t stride = (int64_t(per_read_bytes<uint32_t>(lmaxL)) + 255) & ~int64_t(255);
@@ -483,9 +880,8 @@ int icb_launch_sketch(icb_readset* rs, int k, int w, const uint8_t* d_skip)
 	a.long_scratch = rs->d_long_scratch;
 	a.long_scratch_stride = stride;
 	a.lmax = lmaxL;
-	ICB_CUDA(ctx, cudaMemsetAsync(rs->d_counters + 3, 0, sizeof(unsigned long long), ctx->stream));
 	ICB_LAUNCH(ctx, "sketch_reads_long",
-		   icb_k_sketch<true, uint32_t><<<nblk, SK_THREADS, STAGE_BYTES, ctx->stream>>>(a));
+		   icb_k_sketch<true, uint32_t><<<nblk, SK_THREADS, STAGE_BYTES, st>>>(a));
     }
     return ICB_OK;
 }
@@ -514,7 +910,7 @@ int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const doub
     SK_ALLOC(rs->d_min_off, sizeof(int64_t) * (n + 1));
     SK_ALLOC(rs->d_nf, sizeof(int32_t) * (n + 1));
     SK_ALLOC(rs->d_nr, sizeof(int32_t) * (n + 1));
-    SK_ALLOC(rs->d_long_list, sizeof(int32_t) * (n + 1));
+    SK_ALLOC(rs->d_long_list, sizeof(int32_t) * 2 * (n + 1));  // list 1 and list 2
     uint8_t* d_skip = nullptr;
     if (skip && n > 0) {
 	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_skip, n, ctx->stream));

@@ -130,6 +130,9 @@ def test_sketch_edge_cases(port, ctx):
         rnd(1000) + b"G" * 3000 + rnd(90),		    # long run crossing tiles, still on the fast path
         rnd(4097), rnd(9000), rnd(20000),		    # global-scratch path
         b"T" * 5000 + rnd(100),
+        rnd(3071), rnd(3072), rnd(3073),		    # limit of the warp-per-read path
+        rnd(7) + b"C" * 9 + rnd(16) + b"G" * 33 + rnd(5) + b"T" * 16 + rnd(11) + b"A" * 600 + rnd(700),  # runs across 16-base chunks
+        b"AC" * 1536, b"ACG" * 1000,			    # as many minimizers as a read can have
     ]
     quals = [bytes(rng.integers(35, 75, len(r)).astype(np.uint8)) for r in reads]
     seq, qual, offs = _flat(reads, quals)
@@ -137,6 +140,11 @@ def test_sketch_edge_cases(port, ctx):
     skip = np.zeros(len(reads), np.uint8)
     skip[[3, 9, 18]] = 1
     _check_sketch(port, ctx, seq, qual, offs, k, w, skip=skip)
+    _check_sketch(port, ctx, seq, qual, offs, 13, 20)
+    # unaligned slot starts: the same reads behind a 1..15-byte first read
+    for pad in (1, 5, 15):
+        s2, q2, o2 = _flat([rnd(pad)] + reads[6:], [bytes([60] * pad)] + quals[6:])
+        _check_sketch(port, ctx, s2, q2, o2, k, w)
 
 
 def test_sketch_empty_and_invalid(ctx):
