@@ -29,7 +29,7 @@ K, W_, MIN_QUAL, MODE = 11, 15, 7.0, "sahlin"
 BATCH_KB, BATCH_MAX_SEQ = 50000, 30000  # CmdArgs defaults (args.h:14-15)
 METRIC = "reads/sec clustered (sahlin)"
 KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_full", "index_insert", "align_dp",
-           "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "gather_minimizers")
+           "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "sketch_reads_cta", "gather_minimizers")
 
 
 def clocks_sampler(stop, out, device):
@@ -111,8 +111,6 @@ def run_ours(args):
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
     th.start()
 
-    ctx.timing(True)
-    ctx.timing_reset()
     launches0 = ctx.launch_count()
     times = []
     for _ in range(args.steps):
@@ -126,6 +124,14 @@ def run_ours(args):
         barrier()
         times.append(e0.elapsed_time(e1))
     launches = ctx.launch_count() - launches0
+    # one more pass with an event pair around every kernel launch (the library's per-kernel timers): kernel-level
+    # durations for the roofline; not part of the timed steps above
+    ctx.timing(True)
+    ctx.timing_reset()
+    l2_flush.add_(1)
+    barrier()
+    res = api.run_pipeline(ctx, None, None, None, rs=rs, **pipe)
+    ctx.sync()
     kt = {n: ctx.kernel_time(n) for n in KERNELS}
     ctx.timing(False)
     nf, nr = rs.sketch_sizes()
@@ -155,7 +161,7 @@ def run_ours(args):
     ms, ms_e2e = float(t[0]), float(t[1])
 
     # roofline of the dominant data-moving kernel (sketch_reads): algorithmic bytes per launch / measured launch time
-    steps = max(args.steps, 1)
+    steps = 1  # the kernel timers cover the single profiling pass
     alg_bytes = 2 * n_bases + 2 * hpc_total + 12 * (nf + nr) + 24 * n_reads
     n_l, tot_ms = kt["sketch_reads"]
     k_ms = tot_ms / max(n_l, 1)

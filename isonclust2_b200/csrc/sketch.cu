@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(SW_THREADS, 3) icb_k_sketch_warp(SketchArgs a)
 		    int v = __shfl_up_sync(0xffffffffu, inc, d);
 		    if (lane >= d) inc += v;
 		}
-		int pos = shiftA + runBase + inc - cnt;
-		const int pos0 = pos;
+		uint8_t* ph = hs + (shiftA + runBase + inc - cnt);  // hq = hs + SW_HBUF
+		uint8_t* const ph0 = ph;
 		runBase += __shfl_sync(0xffffffffu, inc, 31);
 		// 16-step register loop: running maximum of the open run, one (base, max) pair stored per run end
 		int qmax = -128;
@@ -550,13 +550,14 @@ __global__ void __launch_bounds__(SW_THREADS, 3) icb_k_sketch_warp(SketchArgs a)
 		const uint32_t qw[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
 		for (int i = 0; i < 16; i++) {
-		    const uint32_t ch = (sw[i >> 2] >> (8 * (i & 3))) & 0xffu;
-		    const int qv = int(qw[i >> 2] << (24 - 8 * (i & 3))) >> 24;  // hpc.cpp:24 compares chars (signed)
+		    // byte i of the quality word, sign-extended (hpc.cpp:24 compares chars): prmt with sign replication
+		    const int qv = int(sw_prmt(qw[i >> 2], 0u, 0x8880u | uint32_t(i & 3) | (uint32_t(i & 3) << 4) | (uint32_t(i & 3) << 8) |
+									    (uint32_t(i & 3) << 12)));
 		    qmax = max(qmax, qv);
 		    if (e & (1u << i)) {
-			hs[pos] = uint8_t(ch);
-			hq[pos] = uint8_t(qmax);
-			pos++;
+			ph[0] = uint8_t(sw[i >> 2] >> (8 * (i & 3)));
+			ph[SW_HBUF] = uint8_t(qmax);
+			ph++;
 			qmax = -128;
 		    }
 		}
@@ -565,21 +566,23 @@ __global__ void __launch_bounds__(SW_THREADS, 3) icb_k_sketch_warp(SketchArgs a)
 		int cv = open ? qmax : -128;
 		bool pass = open && e == 0;  // the whole chunk belongs to one open run
 		if (lane == 0 && pass) cv = max(cv, tileCarry);
+		if (__any_sync(0xffffffffu, pass)) {  // rare: a run longer than a chunk passes its maximum through whole chunks
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-		    const int v2 = __shfl_up_sync(0xffffffffu, cv, d);
-		    const int p2 = __shfl_up_sync(0xffffffffu, int(pass), d);
-		    if (lane >= d && pass) {
-			cv = max(cv, v2);
-			pass = p2 != 0;
+		    for (int d = 1; d < 32; d <<= 1) {
+			const int v2 = __shfl_up_sync(0xffffffffu, cv, d);
+			const int p2 = __shfl_up_sync(0xffffffffu, int(pass), d);
+			if (lane >= d && pass) {
+			    cv = max(cv, v2);
+			    pass = p2 != 0;
+			}
 		    }
 		}
 		int carryIn = __shfl_up_sync(0xffffffffu, cv, 1);
 		if (lane == 0) carryIn = tileCarry;
 		tileCarry = __shfl_sync(0xffffffffu, cv, 31);
 		if (carryIn > -128 && e != 0) {
-		    const int qv = int((signed char)hq[pos0]);
-		    if (carryIn > qv) hq[pos0] = uint8_t(carryIn);
+		    const int qv = int((signed char)ph0[SW_HBUF]);
+		    if (carryIn > qv) ph0[SW_HBUF] = uint8_t(carryIn);
 		}
 	    }
 	    __syncwarp();
@@ -594,25 +597,33 @@ __global__ void __launch_bounds__(SW_THREADS, 3) icb_k_sketch_warp(SketchArgs a)
 		const int wsh = shiftA >> 2, bsh = 8 * (shiftA & 3);
 		const int nwords = (Lh + 15) >> 4;
 		uint32_t badacc = 0;
-		for (int j = lane; j < SW_NWORD; j += 32) {
+		for (int j = lane; j < nwords + 3; j += 32) {  // three zero words behind the read: lanes past its end read them
 		    uint32_t F = 0, R = 0;
 		    if (j < nwords) {
 			uint32_t x[5];
 #pragma unroll
 			for (int i = 0; i < 5; i++) x[i] = hsw[wsh + 4 * j + i];
+			uint32_t dacc = 0, dlast[4];
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
 			    const uint32_t wv = __funnelshift_r(x[i], x[i + 1], bsh);	// bases 16j+4i .. +3, first base in the low byte
 			    const uint32_t cd = ((wv >> 1) & 0x03030303u) ^ ((wv >> 2) & 0x01010101u);	// A,C,G,T -> 0..3 per byte
 			    uint32_t sel = (cd | (cd >> 4)) & 0x00ff00ffu;
 			    sel = (sel | (sel >> 8)) & 0xffffu;
-			    uint32_t diff = sw_prmt(0x54474341u, 0u, sel) ^ wv;	// "ACGT"[code] must give the base back
-			    const int nvalid = Lh - (16 * j + 4 * i);
-			    if (nvalid < 4) diff &= nvalid <= 0 ? 0u : (0xffffffffu >> (32 - 8 * nvalid));
-			    badacc |= diff;
+			    dlast[i] = sw_prmt(0x54474341u, 0u, sel) ^ wv;	// "ACGT"[code] must give the base back
+			    dacc |= dlast[i];
 			    F |= ((cd * 0x40100401u) >> 24) << (24 - 8 * i);		   // b0<<6 | b1<<4 | b2<<2 | b3
 			    R |= (((cd ^ 0x03030303u) * 0x01041040u) >> 24) << (8 * i);   // complement: b0 | b1<<2 | b2<<4 | b3<<6
 			}
+			if (j == nwords - 1) {	// the last word may hold stale bytes behind the read: only its first Lh - 16j bases count
+			    dacc = 0;
+#pragma unroll
+			    for (int i = 0; i < 4; i++) {
+				const int nvalid = Lh - (16 * j + 4 * i);
+				dacc |= nvalid >= 4 ? dlast[i] : (nvalid <= 0 ? 0u : (dlast[i] & (0xffffffffu >> (32 - 8 * nvalid))));
+			    }
+			}
+			badacc |= dacc;
 		    }
 		    Fs[j] = F;
 		    Rs[j] = R;
@@ -628,20 +639,21 @@ __global__ void __launch_bounds__(SW_THREADS, 3) icb_k_sketch_warp(SketchArgs a)
 		uint8_t* gs = a.hpc_seq + (start - shiftA);
 		uint8_t* gq = a.hpc_qual + (start - shiftA);
 		const int lo = shiftA, hi = shiftA + Lh;
-		const int nch = (hi + 15) >> 4;
-		for (int c = lane; c < nch; c += 32) {
-		    const int b0 = c << 4;
-		    if (b0 >= lo && b0 + 16 <= hi) {
-			reinterpret_cast<uint4*>(gs)[c] = reinterpret_cast<const uint4*>(hs)[c];
-			reinterpret_cast<uint4*>(gq)[c] = reinterpret_cast<const uint4*>(hq)[c];
-		    }
-		    else {
-			for (int b = b0; b < b0 + 16; b++)
-			    if (b >= lo && b < hi) {
-				gs[b] = hs[b];
-				gq[b] = hq[b];
-			    }
-		    }
+		const int cfull0 = (lo + 15) >> 4, cfull1 = hi >> 4;  // chunks [cfull0, cfull1) lie entirely inside [lo, hi)
+		for (int c = cfull0 + lane; c < cfull1; c += 32) {
+		    reinterpret_cast<uint4*>(gs)[c] = reinterpret_cast<const uint4*>(hs)[c];
+		    reinterpret_cast<uint4*>(gq)[c] = reinterpret_cast<const uint4*>(hq)[c];
+		}
+		// head [lo, 16*cfull0) and tail [16*cfull1, hi): at most 15 bytes each, one byte per lane
+		const int headEnd = min(hi, cfull0 << 4);
+		if (lo + lane < headEnd && lane < 16) {
+		    gs[lo + lane] = hs[lo + lane];
+		    gq[lo + lane] = hq[lo + lane];
+		}
+		const int tail0 = max(cfull1 << 4, headEnd) + (lane - 16);
+		if (lane >= 16 && tail0 < hi) {
+		    gs[tail0] = hs[tail0];
+		    gq[tail0] = hq[tail0];
 		}
 	    }
 	    __syncwarp();
@@ -701,13 +713,23 @@ __global__ void __launch_bounds__(SW_THREADS, 3) icb_k_sketch_warp(SketchArgs a)
 		    uint32_t ff = 0, fr = 0;
 #pragma unroll
 		    for (int t = 0; t < 16; t++) {
-			const int q = q0 + t;
 			const uint32_t bf = t == 0 ? pf : mf[t - 1];
 			const uint32_t br = t == 0 ? pr : mr[t - 1];
-			const bool f1 = q < nwin && (q == 0 || mf[t] != bf);
-			const bool f2 = q - 1 >= 1 && q - 1 <= nwin && (q - 1 == nwin || mr[t] != br);
-			ff |= uint32_t(f1) << t;
-			fr |= uint32_t(f2) << t;
+			ff += min(mf[t] ^ bf, 1u) << t;	 // keys differ <=> argmin positions differ
+			fr += min(mr[t] ^ br, 1u) << t;
+		    }
+		    {
+			// forward: windows q0+t in [0, nwin), window 0 always; reverse (bit t <-> window q0+t-1): windows in [1, nwin],
+			// window nwin always
+			const int fhi = min(16, nwin - q0);
+			const uint32_t fvalid = fhi > 0 ? (0xffffu >> (16 - fhi)) : 0u;
+			if (q0 == 0) ff |= 1u;
+			ff &= fvalid;
+			const int rlo = max(0, 2 - q0), rhi = min(16, nwin + 2 - q0);
+			const uint32_t rvalid = rhi > rlo ? ((0xffffu >> (16 - rhi)) & (0xffffu << rlo)) : 0u;
+			const int tl = nwin + 1 - q0;
+			if (tl >= 0 && tl < 16) fr |= 1u << tl;
+			fr &= rvalid;
 		    }
 		    // ranks
 		    const int cf = __popc(ff), cr = __popc(fr);
