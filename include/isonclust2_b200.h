@@ -153,6 +153,7 @@ typedef struct {
     int64_t tie_fallbacks; /* reads whose outcome depended on the reference's candidate order */
     int64_t decisions;	   /* evaluations of the per-read decision (>= reads: speculative re-evaluations) */
     double ms_query, ms_full, ms_align, ms_insert, ms_host; /* host wall-clock split of icb_cluster_reads */
+    double ms_cpu; /* CPU time (CLOCK_THREAD_CPUTIME_ID) the calling threads spent inside icb_cluster_reads */
 } icb_cluster_stats;
 
 typedef struct icb_clusterer icb_clusterer;
@@ -175,7 +176,7 @@ int icb_clusterer_stats(const icb_clusterer* cl, icb_cluster_stats* stats);
 
 /* Initial clustering of n_batches independent sorted batches of one read set — what the reference's pipeline runs as
  * one `isONclust2 cluster` process per batch file (README.md:105-117).  Batch b is order[bounds[b] .. bounds[b+1]);
- * cluster ids are batch-local.  n_workers host threads (0 = one per host core, at most 16) each drive one CUDA stream, so
+ * cluster ids are batch-local.  n_workers host threads (0 = three per host core, at most 48; a worker sleeps while its stream is busy) each drive one CUDA stream, so
  * the device always has several batches' kernels in flight; results do not depend on n_workers.
  * n_clusters[n_batches] and stats (summed over the batches) may be NULL. */
 int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,

@@ -320,28 +320,28 @@ int IcbAlignWorkspace::ensure(icb_ctx* ctx, size_t trace_need, size_t lines_need
 {
     // growth happens a handful of times per context; steady state allocates nothing
     if (trace_need > trace_bytes) {
-	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	cudaFree(d_trace);
+	ICB_CUDA(ctx, ctx->wait());
+	icb_dfree(ctx, d_trace);
 	d_trace = nullptr;
 	trace_bytes = 0;
 	size_t want = std::max(trace_need + trace_need / 4, size_t(64) << 20);
-	ICB_CUDA(ctx, cudaMalloc((void**)&d_trace, want));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_trace, want));
 	trace_bytes = want;
     }
     if (lines_need > lines_bytes) {
-	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	cudaFree(d_lines);
+	ICB_CUDA(ctx, ctx->wait());
+	icb_dfree(ctx, d_lines);
 	d_lines = nullptr;
 	lines_bytes = 0;
 	size_t want = std::max(lines_need * 2, size_t(4) << 20);
-	ICB_CUDA(ctx, cudaMalloc((void**)&d_lines, want));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_lines, want));
 	lines_bytes = want;
     }
     if (pairs_need > pair_cap) {
-	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	cudaFree(d_descs);
-	cudaFree(d_ends);
-	cudaFree(d_out);
+	ICB_CUDA(ctx, ctx->wait());
+	icb_dfree(ctx, d_descs);
+	icb_dfree(ctx, d_ends);
+	icb_dfree(ctx, d_out);
 	cudaFreeHost(h_descs);
 	cudaFreeHost(h_out);
 	cudaFreeHost(h_ends);
@@ -353,26 +353,26 @@ int IcbAlignWorkspace::ensure(icb_ctx* ctx, size_t trace_need, size_t lines_need
 	h_ends = nullptr;
 	pair_cap = 0;
 	int64_t want = std::max<int64_t>(pairs_need * 2, 4096);
-	ICB_CUDA(ctx, cudaMalloc((void**)&d_descs, sizeof(IcbPairDesc) * want));
-	ICB_CUDA(ctx, cudaMalloc((void**)&d_ends, sizeof(IcbAlignEnd) * want));
-	ICB_CUDA(ctx, cudaMalloc((void**)&d_out, sizeof(icb_align_result) * want));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_descs, sizeof(IcbPairDesc) * want));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_ends, sizeof(IcbAlignEnd) * want));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_out, sizeof(icb_align_result) * want));
 	ICB_CUDA(ctx, cudaMallocHost((void**)&h_descs, sizeof(IcbPairDesc) * want));
 	ICB_CUDA(ctx, cudaMallocHost((void**)&h_out, sizeof(icb_align_result) * want));
 	ICB_CUDA(ctx, cudaMallocHost((void**)&h_ends, sizeof(IcbAlignEnd) * want));
 	pair_cap = want;
     }
-    if (!d_ticket) ICB_CUDA(ctx, cudaMalloc((void**)&d_ticket, 64));
+    if (!d_ticket) ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_ticket, 64));
     return ICB_OK;
 }
 
-void IcbAlignWorkspace::release()
+void IcbAlignWorkspace::release(icb_ctx* ctx)
 {
-    cudaFree(d_trace);
-    cudaFree(d_lines);
-    cudaFree(d_descs);
-    cudaFree(d_ends);
-    cudaFree(d_out);
-    cudaFree(d_ticket);
+    icb_dfree(ctx, d_trace);
+    icb_dfree(ctx, d_lines);
+    icb_dfree(ctx, d_descs);
+    icb_dfree(ctx, d_ends);
+    icb_dfree(ctx, d_out);
+    icb_dfree(ctx, d_ticket);
     cudaFreeHost(h_descs);
     cudaFreeHost(h_out);
     cudaFreeHost(h_ends);
@@ -399,7 +399,7 @@ int icb_align32_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, c
 namespace {
 
 constexpr int64_t LIMIT16 = 8000;			  // align16: H + 2j + 64 must stay below 2^15
-constexpr int64_t TRACE_BUDGET_TILES = (int64_t(4) << 30) / 32;  // trace arena per launch: 4 GiB
+constexpr int64_t TRACE_BUDGET_TILES = (int64_t(1) << 30) / 32;  // trace arena per launch (and per worker): 1 GiB
 
 struct Launch {
     std::vector<IcbPairDesc> descs;
@@ -422,7 +422,7 @@ int run_launch(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, Launch
 	      : icb_align32_run(ctx, ws, d_seq, ws.h_descs, cnt, L.tiles, L.words, k);
     if (rc) return rc;
     ICB_CUDA(ctx, cudaMemcpyAsync(ws.h_out, ws.d_out, sizeof(icb_align_result) * cnt, cudaMemcpyDeviceToHost, st));
-    ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    ICB_CUDA(ctx, ctx->wait());
     for (int64_t i = 0; i < cnt; i++) {
 	if (fast && ws.h_out[i].comp_len < 0) redo->push_back(L.slot[i]);
 	else results[L.slot[i]] = ws.h_out[i];

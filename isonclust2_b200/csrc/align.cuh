@@ -38,7 +38,7 @@ struct IcbAlignWorkspace {
     IcbAlignEnd* h_ends = nullptr;
     int64_t pair_cap = 0;
     int ensure(icb_ctx* ctx, size_t trace_need, size_t lines_need, int64_t pairs_need);
-    void release();
+    void release(icb_ctx* ctx);
 };
 
 // upper-cased character of the reference string as parasail sees it (RevComp applied when rc; util.cpp:13-38)

@@ -12,6 +12,7 @@
 // demands it (see index.cu), and consumed here in order.
 #include <algorithm>
 #include <chrono>
+#include <ctime>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -47,6 +48,13 @@ struct AlnKey {
 };
 
 enum Outcome { OUT_JOIN, OUT_NEW, OUT_NEED, OUT_NONE };
+
+double thread_cpu_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 struct Stopwatch {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -108,12 +116,12 @@ struct icb_clusterer {
 int icb_clusterer::ensure_scratch(int64_t words)
 {
     if (words <= scratch_words) return ICB_OK;
-    ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_scratch);
+    ICB_CUDA(ctx, ctx->wait());
+    icb_dfree(ctx, d_scratch);
     d_scratch = nullptr;
     scratch_words = 0;
     const int64_t want = words + words / 2;  // geometric: the index grows with every chunk
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_scratch, size_t(want) * 4));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_scratch, size_t(want) * 4));
     scratch_words = want;
     return ICB_OK;
 }
@@ -121,16 +129,16 @@ int icb_clusterer::ensure_scratch(int64_t words)
 int icb_clusterer::ensure_cands(int64_t n)
 {
     if (n > cands_cap) {
-	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	cudaFree(d_cands);
+	ICB_CUDA(ctx, ctx->wait());
+	icb_dfree(ctx, d_cands);
 	d_cands = nullptr;
 	cands_cap = 0;
 	const int64_t want = std::max<int64_t>(n + n / 2, 1 << 16);
-	ICB_CUDA(ctx, cudaMalloc((void**)&d_cands, size_t(want) * sizeof(IcbCand)));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_cands, size_t(want) * sizeof(IcbCand)));
 	cands_cap = want;
     }
     if (n > h_cands_cap) {
-	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ICB_CUDA(ctx, ctx->wait());
 	cudaFreeHost(h_cands);
 	h_cands = nullptr;
 	h_cands_cap = 0;
@@ -144,12 +152,12 @@ int icb_clusterer::ensure_cands(int64_t n)
 int icb_clusterer::init_buffers()
 {
     const int cs = chunk_cap;
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_nmax, sizeof(int32_t) * 225));
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_chunk_reads, sizeof(int32_t) * cs));
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_list, sizeof(int32_t) * cs));
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_ids, sizeof(int32_t) * cs));
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_hdr, sizeof(IcbQueryHeader) * cs));
-    ICB_CUDA(ctx, cudaMalloc((void**)&d_full_off, sizeof(int64_t) * (cs + 1)));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_nmax, sizeof(int32_t) * 225));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_chunk_reads, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_list, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_ids, sizeof(int32_t) * cs));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_hdr, sizeof(IcbQueryHeader) * cs));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_full_off, sizeof(int64_t) * (cs + 1)));
     ICB_CUDA(ctx, cudaMallocHost((void**)&h_i32, sizeof(int32_t) * (3 * cs + 256)));
     ICB_CUDA(ctx, cudaMallocHost((void**)&h_hdr, sizeof(IcbQueryHeader) * cs));
     ICB_CUDA(ctx, cudaMallocHost((void**)&h_off, sizeof(int64_t) * (cs + 1)));
@@ -159,7 +167,7 @@ int icb_clusterer::init_buffers()
     if (rc) return rc;
     rc = chunk_idx.create(ctx, 1u << 18, 1 << 17);
     if (rc) return rc;
-    ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ICB_CUDA(ctx, ctx->wait());
     return ICB_OK;
 }
 
@@ -167,15 +175,15 @@ void icb_clusterer::free_buffers()
 {
     main_idx.destroy();
     chunk_idx.destroy();
-    cudaFree(d_nmax);
-    cudaFree(d_cls_founder);
-    cudaFree(d_chunk_reads);
-    cudaFree(d_list);
-    cudaFree(d_ids);
-    cudaFree(d_hdr);
-    cudaFree(d_cands);
-    cudaFree(d_full_off);
-    cudaFree(d_scratch);
+    icb_dfree(ctx, d_nmax);
+    icb_dfree(ctx, d_cls_founder);
+    icb_dfree(ctx, d_chunk_reads);
+    icb_dfree(ctx, d_list);
+    icb_dfree(ctx, d_ids);
+    icb_dfree(ctx, d_hdr);
+    icb_dfree(ctx, d_cands);
+    icb_dfree(ctx, d_full_off);
+    icb_dfree(ctx, d_scratch);
     cudaFreeHost(h_i32);
     cudaFreeHost(h_hdr);
     cudaFreeHost(h_cands);
@@ -270,7 +278,7 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
     ICB_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, sizeof(IcbQueryHeader) * n_items, cudaMemcpyDeviceToHost, st));
     if (n_records > 0)
 	ICB_CUDA(ctx, cudaMemcpyAsync(h_cands, d_cands, sizeof(IcbCand) * n_records, cudaMemcpyDeviceToHost, st));
-    ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    ICB_CUDA(ctx, ctx->wait());
     return ICB_OK;
 }
 
@@ -304,7 +312,7 @@ int icb_clusterer::seed(const int32_t* rep_reads, int64_t n)
 	ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, h_i32 + chunk_cap, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, st));
 	rc = icb_index_insert(ctx, main_idx, rs, d_chunk_reads, d_ids, cnt);
 	if (rc) return rc;
-	ICB_CUDA(ctx, cudaStreamSynchronize(st));
+	ICB_CUDA(ctx, ctx->wait());
     }
     main_idx.nodes_upper += tot;
     return ICB_OK;
@@ -318,11 +326,11 @@ int icb_clusterer::upload_founders(int64_t from)
     if (n > cls_founder_cap) {
 	const int64_t ncap = std::max<int64_t>(cls_founder_cap * 2, n + 4096);
 	int32_t* nd = nullptr;
-	ICB_CUDA(ctx, cudaStreamSynchronize(st));
-	ICB_CUDA(ctx, cudaMalloc((void**)&nd, sizeof(int32_t) * ncap));
+	ICB_CUDA(ctx, ctx->wait());
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&nd, sizeof(int32_t) * ncap));
 	if (from > 0) ICB_CUDA(ctx, cudaMemcpyAsync(nd, d_cls_founder, sizeof(int32_t) * from, cudaMemcpyDeviceToDevice, st));
-	ICB_CUDA(ctx, cudaStreamSynchronize(st));
-	cudaFree(d_cls_founder);
+	ICB_CUDA(ctx, ctx->wait());
+	icb_dfree(ctx, d_cls_founder);
 	d_cls_founder = nd;
 	cls_founder_cap = ncap;
     }
@@ -331,7 +339,7 @@ int icb_clusterer::upload_founders(int64_t from)
 	const int64_t cnt = std::min<int64_t>(chunk_cap, n - done);
 	memcpy(stage, founder.data() + done, sizeof(int32_t) * cnt);
 	ICB_CUDA(ctx, cudaMemcpyAsync(d_cls_founder + done, stage, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, st));
-	if (done + cnt < n) ICB_CUDA(ctx, cudaStreamSynchronize(st));  // the staging block is reused by the next piece
+	if (done + cnt < n) ICB_CUDA(ctx, ctx->wait());  // the staging block is reused by the next piece
     }
     return ICB_OK;
 }
@@ -430,10 +438,12 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     // decision for the read at `pos` given the founders committed so far.  Returns OUT_NEED when device work is
     // missing (alignment pairs appended to needPairs, tie reads to needFull).
     bool usedAln = false, usedTie = false;
+    std::vector<IcbCand> v, cs;	 // scratch of decide(), reused across calls (no allocation in steady state)
+    std::vector<const IcbCand*> pass, tied;
     auto decide = [&](int pos, int& outCls, int& outStrand, std::vector<AlnKey>& needPairs, std::vector<int32_t>& needFull) -> Outcome {
 	usedAln = usedTie = false;
 	const int r = chunk[pos];
-	std::vector<IcbCand> v;
+	v.clear();
 	int top = hdr[pos].top_snap;
 	for (auto& c : cl[pos]) {
 	    if (c.id >= C0 && founder_cls[c.id - C0] < 0) continue;  // provisional founder that is no founder (yet)
@@ -447,14 +457,14 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	if (mappingMode && !(unsigned(top) < unsigned(P.min_shared))) {
 	    const int thr = int(double(unsigned(top)) * P.min_fraction);  // cluster.cpp:387
 	    // groups of equal count, best first
-	    std::vector<IcbCand> cs;
+	    cs.clear();
 	    for (auto& c : v)
 		if (!(c.count < thr)) cs.push_back(c);
 	    std::sort(cs.begin(), cs.end(), [](const IcbCand& a, const IcbCand& b) { return a.count > b.count; });
 	    size_t g = 0;
 	    while (g < cs.size()) {
 		size_t e = g;
-		std::vector<const IcbCand*> pass;
+		pass.clear();
 		while (e < cs.size() && cs[e].count == cs[g].count) {
 		    float mr = float(double(cs[e].tmapped) / double(size_t(hpc_len[r])));  // cluster.cpp:351,390
 		    if (mr >= P.mapped_threshold) pass.push_back(&cs[e]);
@@ -490,7 +500,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	if (unsigned(top) < unsigned(P.min_shared)) return OUT_NEW;  // cluster.cpp:553-556
 	if (P.mode == 1) return OUT_NEW;			      // fast: minimizers only
 	// getBestClusterAln: candidates tied with the top count, in order, first passing wins
-	std::vector<const IcbCand*> tied;
+	tied.clear();
 	for (auto& c : v)
 	    if (c.count == top) tied.push_back(&c);
 	bool missing = false;
@@ -504,7 +514,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	if (missing) return OUT_NEED;
 	usedAln = true;
 	const unsigned readLen = unsigned(rs->h_offs[r + 1] - rs->h_offs[r]);
-	std::vector<const IcbCand*> pass;
+	pass.clear();
 	for (auto* c : tied) {
 	    double ratio = double(aln[AlnKey{pos, c->id, c->strand}]) / readLen;  // cluster.cpp:458
 	    if (ratio >= P.aligned_threshold) pass.push_back(c);
@@ -538,10 +548,12 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	std::vector<AlnKey> needPairs;
 	std::vector<int32_t> needFull;
 	bool speculative = false;
+	std::vector<AlnKey> np;
+	std::vector<int32_t> nfull;
 	for (int pos = commit_pos; pos < N; pos++) {
 	    int c, s;
-	    std::vector<AlnKey> np;
-	    std::vector<int32_t> nfull;
+	    np.clear();
+	    nfull.clear();
 	    // a read already evaluated against the same set of founders, and not waiting for device work, cannot
 	    // contribute anything new while reads before it are still pending
 	    if (speculative && eval_version[pos] == version && eval_outcome[pos] != OUT_NEED) continue;
@@ -640,7 +652,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	rc = icb_index_insert(ctx, main_idx, rs, d_chunk_reads, d_ids, int(fr.size()));
 	if (rc) return rc;
 	main_idx.nodes_upper += tot;
-	ICB_CUDA(ctx, cudaStreamSynchronize(st));  // the pinned staging block is rewritten by the next chunk
+	ICB_CUDA(ctx, ctx->wait());  // the pinned staging block is rewritten by the next chunk
     }
     stats.ms_insert += sw.lap();
     return ICB_OK;
@@ -670,31 +682,26 @@ int icb_readset_prepare_host(icb_readset* rs)
     if (!rs->d_class) ICB_CUDA(ctx, cudaMalloc((void**)&rs->d_class, n + 16));
     int rc0 = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, rs->d_class);
     if (rc0) return rc0;
-    ICB_CUDA(ctx, cudaStreamSynchronize(st));
+    ICB_CUDA(ctx, ctx->wait());
     rs->max_m = 0;
     for (int64_t i = 0; i < n; i++) rs->max_m = std::max(rs->max_m, std::max(rs->h_nf[i], rs->h_nr[i]));
     rs->host_ready = true;
     return ICB_OK;
 }
 
-// a clusterer on an explicit context (the read set's own, or a worker's child context with its own stream);
-// errors are reported on `ctx`
-static int clusterer_create_on(icb_ctx* ctx, icb_readset* rs, const icb_cluster_params* p, icb_clusterer** out)
+// parameters of a clustering run -> clusterer (validated; the n_max table is evaluated with the HOST libm)
+static int clusterer_configure(icb_ctx* ctx, icb_clusterer* cl, icb_readset* rs, const icb_cluster_params* p)
 {
-    *out = nullptr;
     if (!rs->scored || !rs->sketched) return ctx->fail(ICB_ERR_STATE, "icb_clusterer_create needs scored and sketched reads");
     if (p->kmer_size != rs->sk_k || p->window_size != rs->sk_w)
 	return ctx->fail(ICB_ERR_ARG, "k / w differ from the ones the reads were sketched with");
     if (p->mode < 0 || p->mode > 2) return ctx->fail(ICB_ERR_ARG, "mode must be 0 (sahlin), 1 (fast) or 2 (furious)");
     if (!rs->host_ready) return ctx->fail(ICB_ERR_STATE, "read set host mirror missing");
     if (rs->max_m >= 32768) return ctx->fail(ICB_ERR_ARG, "a read has 32768 or more minimizers per strand");
-    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::unique_ptr<icb_clusterer> cl(new icb_clusterer);
     cl->ctx = ctx;
     cl->rs = rs;
     cl->P = *p;
     if (cl->P.chunk_size <= 0) cl->P.chunk_size = 256;
-    cl->chunk_cap = cl->P.chunk_size;
     // n_max table (cluster.cpp:335-349: pow(pError, n) >= minProbNoHits with the HOST libm; monotone in n)
     if (p->mode != 2) {
 	for (int c = 0; c < 225; c++) {
@@ -711,13 +718,47 @@ static int clusterer_create_on(icb_ctx* ctx, icb_readset* rs, const icb_cluster_
     }
     else
 	for (int c = 0; c < 225; c++) cl->nmax[c] = 0;
-    int rc = cl->init_buffers();
+    return ICB_OK;
+}
+
+// a clusterer on an explicit context (the read set's own, or a worker's child context with its own stream);
+// errors are reported on `ctx`
+static int clusterer_create_on(icb_ctx* ctx, icb_readset* rs, const icb_cluster_params* p, icb_clusterer** out)
+{
+    *out = nullptr;
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<icb_clusterer> cl(new icb_clusterer);
+    int rc = clusterer_configure(ctx, cl.get(), rs, p);
+    if (rc) return rc;
+    cl->chunk_cap = cl->P.chunk_size;
+    rc = cl->init_buffers();
     if (rc) {
 	cl->free_buffers();
 	return rc;
     }
     *out = cl.release();
     return ICB_OK;
+}
+
+// a pooled worker's clusterer for another run: new parameters / read set, same buffers
+static int clusterer_rebind(icb_clusterer* cl, icb_readset* rs, const icb_cluster_params* p)
+{
+    icb_ctx* ctx = cl->ctx;
+    int rc = clusterer_configure(ctx, cl, rs, p);
+    if (rc) return rc;
+    memcpy(cl->h_i32 + 3 * cl->chunk_cap, cl->nmax, sizeof(int32_t) * 225);
+    ICB_CUDA(ctx, cudaMemcpyAsync(cl->d_nmax, cl->h_i32 + 3 * cl->chunk_cap, sizeof(int32_t) * 225, cudaMemcpyHostToDevice, ctx->stream));
+    return cl->reset();
+}
+
+void icb_worker_pool_release(icb_ctx* ctx)
+{
+    for (size_t w = 0; w < ctx->pool_ctx.size(); w++) {
+	if (ctx->pool_cl[w]) icb_clusterer_destroy(ctx->pool_cl[w]);
+	icb_ctx_destroy_child(ctx, ctx->pool_ctx[w]);
+    }
+    ctx->pool_ctx.clear();
+    ctx->pool_cl.clear();
 }
 
 extern "C" {
@@ -764,25 +805,38 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	if (bounds[b] < 0 || bounds[b + 1] < bounds[b]) return ctx->fail(ICB_ERR_ARG, "batch bounds must be non-decreasing");
     int rc = icb_readset_prepare_host(rs);
     if (rc) return rc;
-    ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // scores / sketches are complete before other streams read them
-    int nw = n_workers > 0 ? n_workers : int(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u));
+    ICB_CUDA(ctx, ctx->wait());  // scores / sketches are complete before other streams read them
+    // a worker mostly sleeps on its stream (icb_ctx::wait), so several batches per host core are kept in flight
+    int nw = n_workers > 0 ? n_workers : int(std::min<unsigned>(std::max(8u, 3u * std::thread::hardware_concurrency()), 48u));
     nw = std::min(nw, int(n_batches));
     std::atomic<int> next(0), first_err(0);
-    std::vector<icb_ctx*> kids(nw, nullptr);
     std::vector<icb_cluster_stats> wstats(nw);
     std::vector<std::string> werr(nw);
+    // workers (child context = stream + alignment workspace, clusterer = index and staging buffers) are kept by the parent
+    // context between calls: nothing is allocated or freed while other workers' kernels are in flight
+    while (int(ctx->pool_ctx.size()) < nw) {
+	icb_ctx* kid = icb_ctx_create_child(ctx);
+	if (!kid) return ctx->fail(ICB_ERR_CUDA, "cannot create a worker stream");
+	ctx->pool_ctx.push_back(kid);
+	ctx->pool_cl.push_back(nullptr);
+    }
+    const int want_chunk = params->chunk_size > 0 ? params->chunk_size : 256;
     for (int w = 0; w < nw; w++) {
-	kids[w] = icb_ctx_create_child(ctx);
-	if (!kids[w]) {
-	    for (auto k : kids) icb_ctx_destroy_child(ctx, k);
-	    return ctx->fail(ICB_ERR_CUDA, "cannot create a worker stream");
+	icb_ctx* c = ctx->pool_ctx[w];
+	c->timing = ctx->timing;
+	c->trace_base = ctx->trace_base;
+	if (ctx->pool_cl[w] && ctx->pool_cl[w]->chunk_cap != want_chunk) {
+	    icb_clusterer_destroy(ctx->pool_cl[w]);
+	    ctx->pool_cl[w] = nullptr;
 	}
+	int rc = ctx->pool_cl[w] ? clusterer_rebind(ctx->pool_cl[w], rs, params) : clusterer_create_on(c, rs, params, &ctx->pool_cl[w]);
+	if (rc) return ctx->fail(rc, c->last_error);
     }
     auto work = [&](int w) {
-	icb_ctx* c = kids[w];
+	icb_ctx* c = ctx->pool_ctx[w];
 	cudaSetDevice(c->device);
-	icb_clusterer* cl = nullptr;
-	int rc = clusterer_create_on(c, rs, params, &cl);
+	icb_clusterer* cl = ctx->pool_cl[w];
+	int rc = ICB_OK;
 	while (!rc) {
 	    const int b = next.fetch_add(1);
 	    if (b >= n_batches || first_err.load()) break;
@@ -796,14 +850,13 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    t.chunks += s.chunks; t.rounds += s.rounds; t.reads_queried += s.reads_queried; t.aln_invoked += s.aln_invoked;
 	    t.pairs_aligned += s.pairs_aligned; t.cells_aligned += s.cells_aligned; t.tie_fallbacks += s.tie_fallbacks;
 	    t.decisions += s.decisions; t.ms_query += s.ms_query; t.ms_full += s.ms_full; t.ms_align += s.ms_align;
-	    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host;
+	    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host; t.ms_cpu += s.ms_cpu;
 	}
 	if (rc) {
 	    int z = 0;
 	    first_err.compare_exchange_strong(z, rc);
 	    werr[w] = c->last_error;
 	}
-	if (cl) icb_clusterer_destroy(cl);
     };
     if (nw == 1) work(0);
     else {
@@ -818,9 +871,11 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    stats->aln_invoked += s.aln_invoked; stats->pairs_aligned += s.pairs_aligned; stats->cells_aligned += s.cells_aligned;
 	    stats->tie_fallbacks += s.tie_fallbacks; stats->decisions += s.decisions; stats->ms_query += s.ms_query;
 	    stats->ms_full += s.ms_full; stats->ms_align += s.ms_align; stats->ms_insert += s.ms_insert; stats->ms_host += s.ms_host;
+	    stats->ms_cpu += s.ms_cpu;
 	}
-	icb_ctx_destroy_child(ctx, kids[w]);  // folds the worker's kernel timers and launch count into the parent
+	icb_ctx_fold_child(ctx, ctx->pool_ctx[w]);  // the worker's kernel timers and launch count -> parent
     }
+    if (first_err.load()) icb_worker_pool_release(ctx);  // a failed worker's buffers are in an unknown state
     if (first_err.load()) {
 	for (auto& e : werr)
 	    if (!e.empty()) return ctx->fail(first_err.load(), e);
@@ -837,6 +892,11 @@ int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_
     const icb_cluster_params& P = cl->P;
     std::vector<int32_t> chunk;
     std::vector<int64_t> slots;
+    struct CpuClock {
+	icb_cluster_stats& st;
+	double t0 = thread_cpu_ms();
+	~CpuClock() { st.ms_cpu += thread_cpu_ms() - t0; }
+    } cpu_clock{cl->stats};
     for (int64_t s = 0; s < n; s++) {
 	cluster_of[s] = -1;
 	strand_of[s] = 0;

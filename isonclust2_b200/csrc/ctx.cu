@@ -1,6 +1,8 @@
 // Context, error reporting, kernel timers and the device-resident read set.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "align.cuh"
 
@@ -16,6 +18,15 @@ int icb_ctx::fail(int code, const std::string& msg)
 {
     last_error = msg;
     return code;
+}
+
+cudaError_t icb_ctx::wait()
+{
+    if (!blocking_wait) return cudaStreamSynchronize(stream);
+    cudaError_t e;
+    if (!wait_event && (e = cudaEventCreateWithFlags(&wait_event, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(wait_event, stream)) != cudaSuccess) return e;
+    return cudaEventSynchronize(wait_event);
 }
 
 cudaEvent_t icb_ctx::get_event()
@@ -44,13 +55,30 @@ void icb_ctx::timer_end(const char* name)
     cudaEventRecord(t.pending.back().second, stream);
 }
 
+// development aid: ICB_TRACE=<file> appends one line "kernel stream start_ms end_ms" per timed launch (times relative to the
+// moment timing was switched on), from which the overlap of the worker streams can be reconstructed
+static std::mutex g_trace_mutex;
+
 void icb_ctx::timers_collect()
 {
     cudaStreamSynchronize(stream);
+    FILE* tf = nullptr;
+    const char* tpath = trace_base ? getenv("ICB_TRACE") : nullptr;
+    std::unique_lock<std::mutex> lock(g_trace_mutex, std::defer_lock);
+    if (tpath && *tpath) {
+	lock.lock();
+	tf = fopen(tpath, "a");
+    }
     for (auto& kv : timers) {
 	for (auto& p : kv.second.pending) {
 	    float ms = 0.f;
 	    cudaEventElapsedTime(&ms, p.first, p.second);
+	    if (tf) {
+		float a = 0.f, b = 0.f;
+		cudaEventElapsedTime(&a, trace_base, p.first);
+		cudaEventElapsedTime(&b, trace_base, p.second);
+		fprintf(tf, "%s %p %.4f %.4f\n", kv.first.c_str(), (void*)stream, a, b);
+	    }
 	    kv.second.launches++;
 	    kv.second.total_ms += ms;
 	    event_pool.push_back(p.first);
@@ -58,6 +86,7 @@ void icb_ctx::timers_collect()
 	}
 	kv.second.pending.clear();
     }
+    if (tf) fclose(tf);
 }
 
 icb_ctx* icb_ctx_create_child(icb_ctx* parent)
@@ -66,6 +95,8 @@ icb_ctx* icb_ctx_create_child(icb_ctx* parent)
     ctx->device = parent->device;
     ctx->sm_count = parent->sm_count;
     ctx->timing = parent->timing;
+    ctx->trace_base = parent->trace_base;
+    ctx->blocking_wait = true;
     if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
 	delete ctx;
 	return nullptr;
@@ -73,22 +104,31 @@ icb_ctx* icb_ctx_create_child(icb_ctx* parent)
     return ctx;
 }
 
-void icb_ctx_destroy_child(icb_ctx* parent, icb_ctx* child)
+void icb_ctx_fold_child(icb_ctx* parent, icb_ctx* child)
 {
-    if (!child) return;
-    cudaSetDevice(child->device);
     child->timers_collect();
     for (auto& kv : child->timers) {
 	auto& t = parent->timers[kv.first];
 	t.launches += kv.second.launches;
 	t.total_ms += kv.second.total_ms;
     }
+    child->timers.clear();
     parent->launch_count += child->launch_count;
+    child->launch_count = 0;
+}
+
+void icb_ctx_destroy_child(icb_ctx* parent, icb_ctx* child)
+{
+    if (!child) return;
+    cudaSetDevice(child->device);
+    icb_ctx_fold_child(parent, child);
     for (auto e : child->event_pool) cudaEventDestroy(e);
+    if (child->wait_event) cudaEventDestroy(child->wait_event);
     if (child->align_ws) {
-	child->align_ws->release();
+	child->align_ws->release(child);
 	delete child->align_ws;
     }
+    cudaStreamSynchronize(child->stream);
     cudaStreamDestroy(child->stream);
     delete child;
 }
@@ -109,6 +149,9 @@ int icb_ctx_create(int device, icb_ctx** out)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return ICB_ERR_CUDA;  // no CPU fallback: fail loudly
     if (device < 0 || device >= n) return ICB_ERR_ARG;
+    // many worker streams: without this they share 8 hardware queues and wait behind each other's kernels (only effective
+    // if the process has not initialised CUDA yet; bench.py and the CLI also set it)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     auto ctx = new icb_ctx;
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -116,6 +159,14 @@ int icb_ctx_create(int device, icb_ctx** out)
 	return ICB_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {
+	// memory returned to the stream-ordered pool stays cached in it (no trimming at synchronisation points)
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+	    uint64_t keep = UINT64_MAX;
+	    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
+    }
     *out = ctx;
     return ICB_OK;
 }
@@ -126,10 +177,13 @@ void icb_ctx_destroy(icb_ctx* ctx)
     cudaSetDevice(ctx->device);
     ctx->timers_collect();
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
+    icb_worker_pool_release(ctx);
     if (ctx->align_ws) {
-	ctx->align_ws->release();
+	ctx->align_ws->release(ctx);
 	delete ctx->align_ws;
     }
+    cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -161,6 +215,11 @@ int icb_ctx_timing(icb_ctx* ctx, int enable)
 {
     ctx->timers_collect();
     ctx->timing = enable != 0;
+    if (ctx->timing && getenv("ICB_TRACE") && !ctx->trace_base) {
+	ICB_CUDA(ctx, cudaEventCreate(&ctx->trace_base));
+	ICB_CUDA(ctx, cudaEventRecord(ctx->trace_base, ctx->stream));
+	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return ICB_OK;
 }
 

@@ -29,7 +29,17 @@ struct icb_ctx {
     int64_t launch_count = 0;
     std::map<std::string, icb_kernel_timer> timers;
     std::vector<cudaEvent_t> event_pool;
+    // icb_cluster_batches keeps its workers (child context + clusterer with all its buffers) for the next call
+    std::vector<icb_ctx*> pool_ctx;
+    std::vector<icb_clusterer*> pool_cl;
+    // worker contexts sleep in wait() (blocking-sync event) instead of spinning: more batches are kept in flight than
+    // the host has cores, and a spinning waiter would take a core from a worker that has decisions to make
+    cudaEvent_t trace_base = nullptr;  // ICB_TRACE=<file>: launch intervals relative to this event are appended to the file
+    bool blocking_wait = false;
+    cudaEvent_t wait_event = nullptr;
 
+    // host waits until everything queued on `stream` has finished
+    cudaError_t wait();
     int fail_cuda(cudaError_t e, const char* what, const char* file, int line);
     int fail(int code, const std::string& msg);
     cudaEvent_t get_event();
@@ -37,6 +47,12 @@ struct icb_ctx {
     void timer_end(const char* name);
     void timers_collect();
 };
+
+// Device buffers of the clustering loop come from the stream-ordered allocator (the device's default memory pool with the
+// release threshold raised, icb_ctx_create): growing or dropping one worker's buffer is ordered on that worker's stream
+// only, where cudaFree would wait for the whole device and stall every other worker's launches meanwhile.
+inline cudaError_t icb_dmalloc(icb_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream); }
+inline cudaError_t icb_dfree(icb_ctx* ctx, void* p) { return p ? cudaFreeAsync(p, ctx->stream) : cudaSuccess; }
 
 #define ICB_CUDA(ctx, call)                                                   \
     do {                                                                      \
@@ -96,7 +112,9 @@ struct icb_readset {
 
 // a worker's context: same device, own stream and timers; destroy folds timers / launch count into the parent
 icb_ctx* icb_ctx_create_child(icb_ctx* parent);
+void icb_ctx_fold_child(icb_ctx* parent, icb_ctx* child);  // timers / launch count -> parent, child's reset
 void icb_ctx_destroy_child(icb_ctx* parent, icb_ctx* child);
+void icb_worker_pool_release(icb_ctx* ctx);  // cluster.cu
 int icb_readset_prepare_host(icb_readset* rs);
 
 // stage launchers (defined in score.cu / sketch.cu)

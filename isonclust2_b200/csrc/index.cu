@@ -354,10 +354,10 @@ int IcbIndex::create(icb_ctx* c, uint32_t cap_pow2, int64_t node_cap)
     capacity = cap_pow2;
     node_capacity = node_cap;
     nodes_upper = 0;
-    ICB_CUDA(ctx, cudaMalloc((void**)&v.keys, sizeof(uint32_t) * (size_t(capacity) + 1)));
-    ICB_CUDA(ctx, cudaMalloc((void**)&v.heads, sizeof(uint32_t) * (size_t(capacity) + 1)));
-    ICB_CUDA(ctx, cudaMalloc((void**)&v.nodes, sizeof(uint2) * size_t(node_capacity)));
-    ICB_CUDA(ctx, cudaMalloc((void**)&v.node_count, sizeof(uint32_t) * 2));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&v.keys, sizeof(uint32_t) * (size_t(capacity) + 1)));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&v.heads, sizeof(uint32_t) * (size_t(capacity) + 1)));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&v.nodes, sizeof(uint2) * size_t(node_capacity)));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&v.node_count, sizeof(uint32_t) * 2));
     v.mask = capacity - 1;
     return clear();
 }
@@ -378,10 +378,10 @@ int IcbIndex::reserve(int64_t extra)
 	int64_t nc = node_capacity;
 	while (nc < need) nc *= 2;
 	uint2* nn = nullptr;
-	ICB_CUDA(ctx, cudaMalloc((void**)&nn, sizeof(uint2) * size_t(nc)));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&nn, sizeof(uint2) * size_t(nc)));
 	ICB_CUDA(ctx, cudaMemcpyAsync(nn, v.nodes, sizeof(uint2) * size_t(nodes_upper), cudaMemcpyDeviceToDevice, ctx->stream));
-	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	cudaFree(v.nodes);
+	ICB_CUDA(ctx, ctx->wait());
+	icb_dfree(ctx, v.nodes);
 	v.nodes = nn;
 	node_capacity = nc;
     }
@@ -391,14 +391,14 @@ int IcbIndex::reserve(int64_t extra)
 	if (ncap > (1ull << 31)) return ctx->fail(ICB_ERR_NOMEM, "minimizer index too large");
 	IcbIndexView nv = v;
 	nv.mask = uint32_t(ncap - 1);
-	ICB_CUDA(ctx, cudaMalloc((void**)&nv.keys, sizeof(uint32_t) * (size_t(ncap) + 1)));
-	ICB_CUDA(ctx, cudaMalloc((void**)&nv.heads, sizeof(uint32_t) * (size_t(ncap) + 1)));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&nv.keys, sizeof(uint32_t) * (size_t(ncap) + 1)));
+	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&nv.heads, sizeof(uint32_t) * (size_t(ncap) + 1)));
 	ICB_CUDA(ctx, cudaMemsetAsync(nv.keys, 0xff, sizeof(uint32_t) * (size_t(ncap) + 1), ctx->stream));
 	ICB_CUDA(ctx, cudaMemsetAsync(nv.heads, 0xff, sizeof(uint32_t) * (size_t(ncap) + 1), ctx->stream));
 	ICB_LAUNCH(ctx, "index_rehash", icb_k_index_rehash<<<unsigned((size_t(capacity) + 1 + 255) / 256), 256, 0, ctx->stream>>>(v, nv));
-	ICB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	cudaFree(v.keys);
-	cudaFree(v.heads);
+	ICB_CUDA(ctx, ctx->wait());
+	icb_dfree(ctx, v.keys);
+	icb_dfree(ctx, v.heads);
 	v = nv;
 	capacity = uint32_t(ncap);
     }
@@ -407,10 +407,10 @@ int IcbIndex::reserve(int64_t extra)
 
 void IcbIndex::destroy()
 {
-    cudaFree(v.keys);
-    cudaFree(v.heads);
-    cudaFree(v.nodes);
-    cudaFree(v.node_count);
+    icb_dfree(ctx, v.keys);
+    icb_dfree(ctx, v.heads);
+    icb_dfree(ctx, v.nodes);
+    icb_dfree(ctx, v.node_count);
     v = IcbIndexView{};
 }
 

@@ -6,6 +6,10 @@ import ctypes as C
 import os
 import re
 
+# one CUDA stream per batch in flight (icb_cluster_batches): give them their own hardware queues.  Read by the driver when
+# the process initialises CUDA, so it is set at import time (a value the user exported wins).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libisonclust2_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "isonclust2_b200.h")
