@@ -154,6 +154,8 @@ typedef struct {
     int64_t decisions;	   /* evaluations of the per-read decision (>= reads: speculative re-evaluations) */
     double ms_query, ms_full, ms_align, ms_insert, ms_host; /* host wall-clock split of icb_cluster_reads */
     double ms_cpu; /* CPU time (CLOCK_THREAD_CPUTIME_ID) the calling threads spent inside icb_cluster_reads */
+    double ms_order;	 /* part of ms_host spent reproducing the reference's candidate order for tie reads */
+    int64_t order_calls; /* evaluations of that order */
 } icb_cluster_stats;
 
 typedef struct icb_clusterer icb_clusterer;

@@ -25,17 +25,11 @@
 
 #include "align.cuh"
 #include "index.cuh"
+#include "ref_order.h"
 
 namespace {
 
-struct PairHash {  // minimizer.h:53-58 StrandedClsHash
-    std::size_t operator()(const std::pair<int, int>& u) const { return std::size_t(int(u.first * u.second)); }
-};
-struct SortedCand {
-    unsigned Size;
-    unsigned Cls;
-    int Strand;
-};
+typedef IcbSortedCand SortedCand;
 
 struct AlnKey {
     int pos, id, strand;
@@ -93,6 +87,7 @@ struct icb_clusterer {
     int64_t scratch_words = 0;
     int chunk_cap = 0;
     icb_cluster_stats stats{};
+    IcbRefOrderScratch ro_scratch;
     // pinned host staging (asynchronous copies, no hidden stream synchronisation on pageable memory)
     int32_t* h_i32 = nullptr;	 // 3 * chunk_cap: chunk reads / ids / list
     IcbQueryHeader* h_hdr = nullptr;
@@ -409,30 +404,24 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     auto real_id = [&](int id) { return id < C0 ? id : founder_cls[id - C0]; };
     auto rep_read = [&](int id) { return id < C0 ? founder[id] : chunk[id - C0]; };
 
-    // exact candidate order of the reference for one read, restricted to real clusters
-    auto reference_order = [&](int pos, const std::vector<IcbCand>& all) {
-	std::vector<IcbCand> v;
+    // exact candidate order of the reference for one read, restricted to real clusters (ref_order.h); `all` is the device's
+    // full list, ascending by id — the map provisional id -> real id is monotone, so the order survives it
+    std::vector<IcbCand> ro_real;
+    std::vector<SortedCand> ro_out;
+    auto reference_order = [&](int pos, const std::vector<IcbCand>& all) -> const std::vector<SortedCand>& {
+	ro_real.clear();
 	for (auto& c : all) {
 	    int rid = real_id(c.id);
 	    if (rid < 0) continue;
-	    IcbCand d = c;
-	    d.id = rid;
-	    v.push_back(d);
+	    ro_real.push_back(c);
+	    ro_real.back().id = rid;
 	}
-	// insertion order of GetMinimizerHits: forward strand first, keys by (first hit rank, cluster id)
-	std::sort(v.begin(), v.end(), [](const IcbCand& a, const IcbCand& b) {
-	    if (a.strand != b.strand) return a.strand > b.strand;
-	    if (a.tmapped != b.tmapped) return a.tmapped < b.tmapped;
-	    return a.id < b.id;
-	});
 	const int r = chunk[pos];
-	std::unordered_map<std::pair<int, int>, unsigned, PairHash> m(20 * (size_t(nf[r]) + size_t(nr[r])));
-	for (auto& c : v) m[std::make_pair(c.id, c.strand)] = unsigned(c.count);
-	std::vector<SortedCand> order;
-	order.reserve(m.size());
-	for (auto& kv : m) order.push_back(SortedCand{kv.second, unsigned(kv.first.first), kv.first.second});
-	std::sort(order.begin(), order.end(), [](const SortedCand& a, const SortedCand& b) { return a.Size > b.Size; });
-	return order;
+	Stopwatch t;
+	icb_reference_order(ro_real.data(), int(ro_real.size()), 20 * (size_t(nf[r]) + size_t(nr[r])), ro_scratch, ro_out);
+	stats.ms_order += t.lap();
+	stats.order_calls++;
+	return ro_out;
     };
 
     // decision for the read at `pos` given the founders committed so far.  Returns OUT_NEED when device work is
@@ -483,7 +472,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 			return OUT_NEED;
 		    }
 		    usedTie = true;
-		    auto order = reference_order(pos, it->second);
+		    const auto& order = reference_order(pos, it->second);
 		    for (auto& o : order) {
 			for (auto* p : pass)
 			    if (unsigned(real_id(p->id)) == o.Cls && p->strand == o.Strand) {
@@ -531,7 +520,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    return OUT_NEED;
 	}
 	usedTie = true;
-	auto order = reference_order(pos, it->second);
+	const auto& order = reference_order(pos, it->second);
 	for (auto& o : order) {
 	    for (auto* p : pass)
 		if (unsigned(real_id(p->id)) == o.Cls && p->strand == o.Strand) {
@@ -850,7 +839,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    t.chunks += s.chunks; t.rounds += s.rounds; t.reads_queried += s.reads_queried; t.aln_invoked += s.aln_invoked;
 	    t.pairs_aligned += s.pairs_aligned; t.cells_aligned += s.cells_aligned; t.tie_fallbacks += s.tie_fallbacks;
 	    t.decisions += s.decisions; t.ms_query += s.ms_query; t.ms_full += s.ms_full; t.ms_align += s.ms_align;
-	    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host; t.ms_cpu += s.ms_cpu;
+	    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host; t.ms_cpu += s.ms_cpu; t.ms_order += s.ms_order; t.order_calls += s.order_calls;
 	}
 	if (rc) {
 	    int z = 0;
@@ -871,7 +860,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    stats->aln_invoked += s.aln_invoked; stats->pairs_aligned += s.pairs_aligned; stats->cells_aligned += s.cells_aligned;
 	    stats->tie_fallbacks += s.tie_fallbacks; stats->decisions += s.decisions; stats->ms_query += s.ms_query;
 	    stats->ms_full += s.ms_full; stats->ms_align += s.ms_align; stats->ms_insert += s.ms_insert; stats->ms_host += s.ms_host;
-	    stats->ms_cpu += s.ms_cpu;
+	    stats->ms_cpu += s.ms_cpu; stats->ms_order += s.ms_order; stats->order_calls += s.order_calls;
 	}
 	icb_ctx_fold_child(ctx, ctx->pool_ctx[w]);  // the worker's kernel timers and launch count -> parent
     }

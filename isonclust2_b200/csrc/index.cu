@@ -222,22 +222,42 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
 	}
 	IcbQueryHeader* hdr = a.hdr + item;
 	if (a.mode == 1) {
+	    // records in ascending id order (the host's counting sort relies on it): thread t owns a contiguous id range and
+	    // its output offset is the exclusive prefix of the live keys before that range
 	    IcbCand* out = a.cands + a.full_off[item];
-	    for (int i = tid; i < Ctot; i += Q_THREADS) {
-		uint32_t v = cnt[i];
+	    const int per = (Ctot + Q_THREADS - 1) / Q_THREADS;
+	    const int lo = min(Ctot, tid * per), hi = min(Ctot, lo + per);
+	    int mine = 0;
+	    for (int i = lo; i < hi; i++) {
+		const uint32_t v = cnt[i];
+		mine += ((v & 0xffffu) != 0) + ((v >> 16) != 0);
+	    }
+	    int inc = mine;
+#pragma unroll
+	    for (int d = 1; d < 32; d <<= 1) {
+		const int t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) inc += t;
+	    }
+	    __syncthreads();  // s_red was read above
+	    if (lane == 31) s_red[warp] = inc;
+	    __syncthreads();
+	    int slot = inc - mine;
+	    for (int w = 0; w < warp; w++) slot += s_red[w];
+	    for (int i = lo; i < hi; i++) {
+		const uint32_t v = cnt[i];
 		for (int half = 0; half < 2; half++) {
-		    int c = half ? int(v >> 16) : int(v & 0xffff);
+		    const int c = half ? int(v >> 16) : int(v & 0xffff);
 		    if (c > 0) {
-			int slot = atomicAdd(&s_n, 1);
 			IcbCand cd;
 			cd.id = i;
 			cd.strand = half ? -1 : 1;
 			cd.count = c;
 			cd.tmapped = int(first[2 * i + half]);
-			out[slot] = cd;
+			out[slot++] = cd;
 		    }
 		}
 	    }
+	    if (tid == Q_THREADS - 1) s_n = slot;
 	    __syncthreads();
 	    if (tid == 0) {
 		hdr->top_snap = top;

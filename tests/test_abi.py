@@ -29,3 +29,16 @@ def test_pemp_table_shipped():
     t = pemp.load_p_shared(11, 15)
     assert t.shape == (15, 15) and (t == t.T).all() and (t > 0).all() and (t < 1).all()
     assert os.path.getsize(pemp._DATA) == 12 + 41880 * 12
+
+
+def test_reference_order_emulation(tmp_path):
+    """csrc/ref_order.h (candidate order of the reference among equally scored candidates) against the real libstdc++
+    container + std::sort on 3000 random cases (host-only C++, tests/cpp/test_ref_order.cpp)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_ref_order")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(root, "isonclust2_b200", "csrc"), "-o", exe,
+                    os.path.join(root, "tests", "cpp", "test_ref_order.cpp")], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout

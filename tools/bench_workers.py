@@ -39,7 +39,7 @@ for nw in sweep:
         ts.append(time.perf_counter() - t0)
     st = res["stats"]
     print(f"workers={nw:3d}  {min(ts):7.3f} s  {n / min(ts):9.0f} reads/s  rounds={st['rounds']} pairs={st['pairs_aligned']} "
-          f"ms: query={st['ms_query']:.0f} full={st['ms_full']:.0f} align={st['ms_align']:.0f} insert={st['ms_insert']:.0f} host={st['ms_host']:.0f} cpu={st['ms_cpu']:.0f}",
+          f"ms: query={st['ms_query']:.0f} full={st['ms_full']:.0f} align={st['ms_align']:.0f} insert={st['ms_insert']:.0f} host={st['ms_host']:.0f} cpu={st['ms_cpu']:.0f} order={st['ms_order']:.0f}/{st['order_calls']} decisions={st['decisions']}",
           flush=True)
 if profile:
     torch.cuda.profiler.stop()
