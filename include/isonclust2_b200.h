@@ -156,6 +156,7 @@ typedef struct {
     double ms_cpu; /* CPU time (CLOCK_THREAD_CPUTIME_ID) the calling threads spent inside icb_cluster_reads */
     double ms_order;	 /* part of ms_host spent reproducing the reference's candidate order for tie reads */
     int64_t order_calls; /* evaluations of that order */
+    int64_t aln_calls_ref; /* DP problems the reference solves for the same reads (getBestClusterAln stops at the first pass) */
 } icb_cluster_stats;
 
 typedef struct icb_clusterer icb_clusterer;

@@ -1,0 +1,840 @@
+// isONclust2 (B200 build) — the `sort` / `cluster` / `info` subcommands of the reference's CLI (main.cpp, args.cpp) on top
+// of the C ABI in include/isonclust2_b200.h.  Same flags, same output files, byte-identical `.cer` batches; the
+// data-parallel work (quality scores, sketches, candidate queries, alignments) runs on the device, the host keeps the
+// FASTQ / `.cer` I/O and the order-dependent bookkeeping (cer.cpp).  There is no CPU fallback: without a CUDA device every
+// subcommand that computes exits 1.
+//
+// Reference call sites mirrored here: mainSort main.cpp:74-202, mainCluster main.cpp:238-392, mainInfo main.cpp:394-409,
+// ParseArgsSort args.cpp:11-151, ParseArgsCluster args.cpp:154-259, SequencesPToFastq / WriteScores output.cpp:30-91.
+#include <getopt.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "cer.hpp"
+#include "isonclust2_b200.h"
+
+using namespace icb;
+using std::cerr;
+using std::endl;
+
+#ifndef ICB_VERSION
+#define ICB_VERSION "v2.4-b200"
+#endif
+
+static bool VERBOSE = false;
+
+// ---------------------------------------------------------------- help (args.cpp:318-424)
+static void print_help_sort()
+{
+    std::cout << "\nsort - sort reads and write out batches:\n"
+		 "\t-B --batch-size        Batch size in kilobases (default: 50000).\n"
+		 "\t-M --batch-max-seq     Maximum number of sequences per batch (default: 30000).\n"
+		 "\t-k --kmer-size         Kmer size (default: 11).\n"
+		 "\t-w --window-size       Window size (default: 15).\n"
+		 "\t-m --min-shared        Minimum number of minimizers shared between read and cluster (default: 5).\n"
+		 "\t-q --min-qual          Minimum average quality value (default: 7.0).\n"
+		 "\t-x --mode  Clustering mode:\n"
+		 "\t           * sahlin (default): use minimizers first, alignment second \n"
+		 "\t           * fast: use minimizers only\n"
+		 "\t           * furious: use alignment only\n"
+		 "\t-g --low-cons-size     Use all sequences for consensus below this size (default: 50).\n"
+		 "\t-c --max-cons-size     Maximum number of sequences used for consensus (default: -150, disabled).\n"
+		 "\t-P --cons-period       Do not recalculate consensus after this many seqeunces added (default: 500).\n"
+		 "\t-r --mapped-threshold  Minimum mapped fraction of read to be included in cluster (default: 0.65).\n"
+		 "\t-a --aligned-threshold Minimum aligned fraction of read to be included in cluster (default: 0.2).\n"
+		 "\t-f --min-fraction      Minimum fraction of minimizers shared compared to best hit, in order to continue "
+		 "mapping (default: 0.8).\n"
+		 "\t-p --min-prob-no-hits  Minimum probability for i consecutive \tminimizers to be different between read and "
+		 "representative (default: 0.1)\n"
+		 "\t-F --min-cls-size      Skip clusters smaller than this in the left batch (default: 3).\n"
+		 "\t-o --outfolder         Output folder (default: \t./isONclust2_batches).\n"
+		 "\t-h --help              Print help.\n"
+		 "\t-v --verbose           Verbose output.\n"
+		 "\t-d --debug             Print debug info.\n"
+		 "\t[positional argument]  Input fastq file (required).\n";
+}
+static void print_help_cluster()
+{
+    std::cout << "\ncluster - cluster and/or merge batches:\n"
+		 "\t-l --left-batch        Left input batch (mandatory).\n"
+		 "\t-r --right-batch       Right input batch (optional).\n"
+		 "\t-o --outfile           Output batch.\n"
+		 "\t-x --mode  Clustering mode:\n"
+		 "\t           * sahlin (default): use minimizers first, alignment second \n"
+		 "\t           * fast: use minimizers only\n"
+		 "\t           * furious: use alignment only\n"
+		 "\t-A --spoa-algo  spoa alignment algorithm:\n"
+		 "\t           * 0 (default): local\n"
+		 "\t           * 1 : global\n"
+		 "\t           * 2 : semi-global\n"
+		 "\t-z --min-purge         Purge minimizer database from output batch.\n"
+		 "\t-j --keep-seq          Do not purge non-representative sequences from output batches.\n"
+		 "\t-F --min-cls-size      Skip clusters smaller than this in the left batch.\n"
+		 "\t-v --verbose           Verbose output.\n"
+		 "\t-Q --quiet             Supress progress bar.\n"
+		 "\t-d --debug             Print debug info.\n"
+		 "\t-h --help              Print help.\n";
+}
+static void print_help_info()
+{
+    std::cout << "\ninfo:\n"
+		 "\t-h --help              Print help.\n"
+		 "\t[positional argument]  Input serialized batch (required).\n";
+}
+static void print_help()
+{
+    std::cout << "Available subcommands: sort, cluster, info, version, help (B200 build; `dump` is served by the reference binary)" << endl;
+    print_help_sort();
+    print_help_cluster();
+    print_help_info();
+}
+
+// ---------------------------------------------------------------- argument parsing
+static bool parse_mode(const char* s, int* mode)
+{
+    std::string m = s ? s : "";
+    if (m == "sahlin")
+	*mode = Sahlin;
+    else if (m == "fast")
+	*mode = Fast;
+    else if (m == "furious")
+	*mode = Furious;
+    else {
+	cerr << "Illegal clustering mode: " << m << endl;
+	print_help_sort();
+	return false;
+    }
+    return true;
+}
+
+static CmdArgs parse_args_sort(int argc, char** argv)
+{
+    static const struct option longopts[] = {
+	{"version", no_argument, 0, 'V'},	   {"verbose", no_argument, 0, 'v'},
+	{"debug", no_argument, 0, 'd'},		   {"mode", optional_argument, 0, 'x'},
+	{"help", no_argument, 0, 'h'},		   {"kmer-size", required_argument, 0, 'k'},
+	{"window-size", required_argument, 0, 'w'}, {"min-shared", required_argument, 0, 'm'},
+	{"mapped-threshold", required_argument, 0, 'r'}, {"aligned-threshold", required_argument, 0, 'a'},
+	{"min-fraction", required_argument, 0, 'f'}, {"min-prob-no-hits", required_argument, 0, 'p'},
+	{"min-qual", required_argument, 0, 'q'},	   {"min-cls-size", required_argument, 0, 'F'},
+	{"low-cons-size", required_argument, 0, 'g'}, {"max-cons-size", required_argument, 0, 'c'},
+	{"cons-period", required_argument, 0, 'P'}, {"outfolder", required_argument, 0, 'o'},
+	{"batch-size", required_argument, 0, 'B'},  {"batch-max-seq", required_argument, 0, 'M'},
+	{0, 0, 0, 0},
+    };
+    CmdArgs res;
+    argc--;
+    argv++;  // getopt sees "sort" as the program name
+    int iarg = 0, index;
+    while ((iarg = getopt_long(argc, argv, "k:w:dhvo:m:r:a:f:p:q:B:x:g:c:M:P:F:", longopts, &index)) != -1) {
+	switch (iarg) {
+	    case 'h': print_help_sort(); exit(0);
+	    case 'k': res.KmerSize = atoi(optarg); break;
+	    case 'm': res.MinShared = atoi(optarg); break;
+	    case 'r': res.MappedThreshold = atof(optarg); break;
+	    case 'a': res.AlignedThreshold = atof(optarg); break;
+	    case 'f': res.MinFraction = atof(optarg); break;
+	    case 'p': res.MinProbNoHits = atof(optarg); break;
+	    case 'q': res.MinQual = atof(optarg); break;
+	    case 'w': res.WindowSize = atoi(optarg); break;
+	    case 'B': res.BatchSize = atoi(optarg); break;
+	    case 'M': res.BatchMaxSeq = atoi(optarg); break;
+	    case 'P': res.ConsPeriod = atoi(optarg); break;
+	    case 'g': res.ConsMinSize = atoi(optarg); break;
+	    case 'c': res.ConsMaxSize = atoi(optarg); break;
+	    case 'F': res.MinClsSize = atoi(optarg); break;
+	    case 'o': res.BatchOutFolder = optarg; break;
+	    case 'v': res.Verbose = true; break;
+	    case 'd': res.Debug = true; break;
+	    case 'x':
+		if (!parse_mode(optarg, &res.Mode)) exit(1);
+		break;
+	    default: break;
+	}
+    }
+    if (argc - optind != 1) {
+	cerr << "Please specify one input fastq file!" << endl;
+	exit(1);
+    }
+    if (res.KmerSize > 31) {
+	cerr << "Maximum supported kmer size is 31!" << endl;
+	exit(1);
+    }
+    if (res.KmerSize < 10) {
+	cerr << "Minimum supported kmer size is 10!" << endl;
+	exit(1);
+    }
+    if (res.KmerSize > res.WindowSize) {
+	cerr << "Kmer size cannot be larger than the window size!" << endl;
+	exit(1);
+    }
+    res.InFastq = argv[optind];
+    return res;
+}
+
+struct CmdArgsCluster {
+    bool Verbose = false, Quiet = false, Debug = false, MinPurge = false, SeqPurge = false;
+    int MinClsSize = -1;
+    std::string LeftCereal, RightCereal, OutCereal;
+    int Mode = None;
+    int SpoaAlgo = 2;
+};
+
+static CmdArgsCluster parse_args_cluster(int argc, char** argv)
+{
+    static const struct option longopts[] = {
+	{"quiet", no_argument, 0, 'Q'},		 {"version", no_argument, 0, 'V'},
+	{"verbose", no_argument, 0, 'v'},	 {"min-purge", no_argument, 0, 'z'},
+	{"min-cls-size", required_argument, 0, 'F'}, {"keep-seq", no_argument, 0, 'j'},
+	{"debug", no_argument, 0, 'd'},		 {"spoa-algo", optional_argument, 0, 'A'},
+	{"mode", optional_argument, 0, 'x'},	 {"help", no_argument, 0, 'h'},
+	{"outfile", required_argument, 0, 'o'},	 {"left-batch", required_argument, 0, 'l'},
+	{"right-batch", optional_argument, 0, 'r'}, {0, 0, 0, 0},
+    };
+    CmdArgsCluster res;
+    argc--;
+    argv++;
+    int iarg = 0, index;
+    while ((iarg = getopt_long(argc, argv, "Vdhvo:l:r:Qx:A:zjF:", longopts, &index)) != -1) {
+	switch (iarg) {
+	    case 'h': print_help_cluster(); exit(0);
+	    case 'o': res.OutCereal = optarg; break;
+	    case 'l': res.LeftCereal = optarg; break;
+	    case 'r': res.RightCereal = optarg ? optarg : ""; break;
+	    case 'v': res.Verbose = true; break;
+	    case 'Q': res.Quiet = true; break;
+	    case 'd': res.Debug = true; break;
+	    case 'A': res.SpoaAlgo = optarg ? atoi(optarg) : res.SpoaAlgo; break;
+	    case 'z': res.MinPurge = true; break;
+	    case 'j': res.SeqPurge = true; break;
+	    case 'F': res.MinClsSize = atoi(optarg); break;
+	    case 'x':
+		if (!parse_mode(optarg, &res.Mode)) exit(1);
+		break;
+	    default: break;
+	}
+    }
+    if (res.LeftCereal == "") {
+	cerr << "Specifying left input batch is mandatory!" << endl;
+	print_help();
+	exit(1);
+    }
+    if (res.OutCereal == "") {
+	cerr << "Specifying output batch file is mandatory!" << endl;
+	print_help();
+	exit(1);
+    }
+    return res;
+}
+
+// ---------------------------------------------------------------- small helpers
+static int dir_exists(const std::string& path)
+{
+    struct stat info;
+    if (stat(path.c_str(), &info) != 0) return 0;
+    return (info.st_mode & S_IFDIR) ? 1 : 0;
+}
+static void create_outdir(const std::string& d)  // output.cpp:110-123
+{
+    if (dir_exists(d)) {
+	cerr << "Warning: reusing existing output directory: " << d << endl;
+	return;
+    }
+    int result = mkdir(d.c_str(), 0755);
+    if (result != 0) {
+	cerr << "Failed to create output directory!"
+	     << "Error: " << result << endl;
+	exit(1);
+    }
+}
+static FILE* create_file(const std::string& p)
+{
+    FILE* f = fopen(p.c_str(), "wb");
+    if (!f) {
+	cerr << "Failed to open " + p + "!" << endl;
+	exit(1);
+    }
+    setvbuf(f, nullptr, _IOFBF, 1 << 22);
+    return f;
+}
+
+static void die_icb(icb_ctx* ctx, int rc, const char* what)
+{
+    const char* msg = ctx ? icb_last_error(ctx) : "";
+    if (rc == ICB_ERR_INVALID_BASE) {
+	// the reference: RevComp throws a std::string (util.cpp:31-33), nobody catches it -> terminate
+	cerr << "terminate called after throwing an instance of 'std::string' (a read holds a base outside ACGT)" << endl;
+	abort();
+    }
+    cerr << "isONclust2 (B200): " << what << " failed: [" << rc << "] " << ((msg && *msg) ? msg : icb_strerror(rc)) << endl;
+    exit(1);
+}
+#define ICB_DO(ctx, call)                   \
+    do {                                    \
+	int rc__ = (call);                  \
+	if (rc__) die_icb(ctx, rc__, #call); \
+    } while (0)
+
+static icb_ctx* open_device()
+{
+    const char* dev = getenv("ICB_DEVICE");
+    icb_ctx* ctx = nullptr;
+    int rc = icb_ctx_create(dev ? atoi(dev) : 0, &ctx);
+    if (rc) {
+	cerr << "isONclust2 (B200): no usable CUDA device (" << icb_strerror(rc) << "); this build has no CPU path." << endl;
+	exit(1);
+    }
+    return ctx;
+}
+
+// ---------------------------------------------------------------- FASTQ (bioparser FastqParser semantics, fastq_parser.hpp:27-118:
+// names cut at the first white space, multi-line sequences/qualities joined, gzip or plain input through zlib)
+struct Fastq {
+    std::vector<std::string> names;
+    std::string seq, qual;
+    std::vector<int64_t> offs{0};
+};
+
+static void invalid_fastq()
+{
+    cerr << "terminate called after throwing an instance of 'std::invalid_argument'\n  what():  [bioparser::FastqParser] error: invalid file format" << endl;
+    abort();
+}
+
+static void parse_fastq(const std::string& path, Fastq& fq)
+{
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) {
+	cerr << "terminate called after throwing an instance of 'std::invalid_argument'\n  what():  [bioparser::Parser::Create] error: unable to open file " << path << endl;
+	abort();
+    }
+    gzbuffer(f, 1 << 20);
+    std::vector<char> buf(size_t(4) << 20);
+    enum { NAME, DATA, COMMENT, QUALITY } st = NAME;
+    std::string name;
+    size_t data0 = fq.seq.size(), qual0 = fq.qual.size();
+    bool any = false;
+    auto finish = [&]() {
+	size_t nl = 0;
+	while (nl < name.size() && !isspace(static_cast<unsigned char>(name[nl]))) nl++;
+	const size_t dl = fq.seq.size() - data0, ql = fq.qual.size() - qual0;
+	if (nl <= 1 || name[0] != '@' || dl == 0 || ql == 0 || dl != ql) invalid_fastq();
+	fq.names.emplace_back(name.data() + 1, nl - 1);
+	fq.offs.push_back(int64_t(fq.seq.size()));
+	name.clear();
+	data0 = fq.seq.size();
+	qual0 = fq.qual.size();
+	any = false;
+	st = NAME;
+    };
+    for (;;) {
+	int n = gzread(f, buf.data(), unsigned(buf.size()));
+	if (n <= 0) break;
+	for (int i = 0; i < n; i++) {
+	    const char c = buf[i];
+	    if (c == '\n') {
+		if (st == NAME) {
+		    st = DATA;
+		}
+		else if (st == COMMENT) {
+		    st = QUALITY;
+		}
+		else if (st == QUALITY && fq.qual.size() - qual0 >= fq.seq.size() - data0) {
+		    finish();
+		}
+		continue;
+	    }
+	    any = true;
+	    switch (st) {
+		case NAME: name.push_back(c); break;
+		case DATA:
+		    if (c == '+')
+			st = COMMENT;
+		    else if (!isspace(static_cast<unsigned char>(c)))
+			fq.seq.push_back(c);
+		    break;
+		case COMMENT: break;
+		case QUALITY:
+		    if (!isspace(static_cast<unsigned char>(c))) fq.qual.push_back(c);
+		    break;
+	    }
+	}
+    }
+    gzclose(f);
+    if (any) {
+	if (st != QUALITY) invalid_fastq();
+	finish();
+    }
+}
+
+// ---------------------------------------------------------------- sort (main.cpp:74-202)
+static int main_sort(int argc, char** argv)
+{
+    CmdArgs args = parse_args_sort(argc, argv);
+    VERBOSE = args.Verbose;
+    if (VERBOSE) {
+	cerr << "isONclust2 version: " << ICB_VERSION << endl;
+	cerr << "Batches output directory: " << args.BatchOutFolder << endl;
+	cerr << "Minimum batch size: " << args.BatchSize << " kilobases" << endl;
+	cerr << "Kmer size: " << args.KmerSize << endl;
+	cerr << "Window size: " << args.WindowSize << endl;
+	cerr << "Consensus period: " << args.ConsPeriod << endl;
+	cerr << "Minimum cluster size for consensus: " << args.ConsMinSize << endl;
+	cerr << "Maximum cluster size for consensus: " << args.ConsMaxSize << endl;
+	cerr << "Minimum average quality: " << args.MinQual << endl;
+	cerr << "Minimum shared minimizers: " << args.MinShared << endl;
+	cerr << "Minimum fraction of top minimizer hit: " << args.MinFraction << endl;
+	cerr << "Mapping threshold: " << args.MappedThreshold << endl;
+	cerr << "Alignment threshold: " << args.AlignedThreshold << endl;
+	cerr << "Minimum probability no hit: " << args.MinProbNoHits << endl;
+	cerr << "Minimum cluster size in left batches: " << args.MinClsSize << endl;
+	cerr << "Debug output: " << (args.Debug ? "on" : "off") << endl;
+    }
+    const std::string batchDir = args.BatchOutFolder + "/batches";
+    create_outdir(args.BatchOutFolder);
+    create_outdir(batchDir);
+
+    Fastq fq;
+    parse_fastq(args.InFastq, fq);
+    const int64_t n = int64_t(fq.names.size());
+    if (VERBOSE) cerr << "Parsed " << n << " sequences." << endl;
+
+    // FillQualScores + SortByQualScores
+    double qualTab[129], qualTabNomin[129];
+    icb_init_qual_tab(qualTab, 0);
+    icb_init_qual_tab(qualTabNomin, 1);
+    icb_ctx* ctx = open_device();
+    icb_readset* rs = nullptr;
+    ICB_DO(ctx, icb_readset_create(ctx, fq.seq.data(), fq.qual.data(), fq.offs.data(), n, &rs));
+    const size_t un = static_cast<size_t>(n);
+    std::vector<double> score(un, 0.0), err(un, 0.0);
+    std::vector<int32_t> order(un, 0);
+    if (n) {
+	ICB_DO(ctx, icb_score_reads(rs, args.KmerSize, qualTab, qualTabNomin));
+	ICB_DO(ctx, icb_scores_download(rs, score.data(), err.data()));
+	ICB_DO(ctx, icb_sort_by_score(score.data(), n, order.data()));
+    }
+    if (VERBOSE) cerr << "Finished sorting sequences." << endl;
+
+    // SequencesPToFastq + WriteScores (output.cpp:30-91)
+    const std::string sortedFastq = args.BatchOutFolder + "/sorted_reads.fastq";
+    {
+	FILE* out = create_file(sortedFastq);
+	FILE* tsv = create_file(args.BatchOutFolder + "/sorted_reads_idx.tsv");
+	fputs("Id\tPos\n", tsv);
+	unsigned long long seeker = 0;
+	for (int64_t s = 0; s < n; s++) {
+	    const int32_t r = order[s];
+	    if (score[r] < 0) continue;
+	    const std::string& name = fq.names[r];
+	    const int64_t o = fq.offs[r], len = fq.offs[r + 1] - o;
+	    fprintf(tsv, "%s\t%llu\n", name.c_str(), seeker);
+	    fputc('@', out);
+	    fwrite(name.data(), 1, name.size(), out);
+	    fputc('\n', out);
+	    fwrite(fq.seq.data() + o, 1, size_t(len), out);
+	    fputs("\n+\n", out);
+	    fwrite(fq.qual.data() + o, 1, size_t(len), out);
+	    fputc('\n', out);
+	    seeker += unsigned(name.length() + size_t(len) + size_t(len) + 6);	// WriteFastqRecord returns unsigned
+	}
+	fclose(out);
+	fclose(tsv);
+	save_sorted_idx(sortedFastq, args.BatchOutFolder + "/sorted_reads_idx.cer");
+    }
+    if (VERBOSE) cerr << "Sorted sequences written to: " << sortedFastq << endl;
+    const std::string scoresTsv = args.BatchOutFolder + "/scores.tsv";
+    {
+	FILE* out = create_file(scoresTsv);
+	for (int64_t s = 0; s < n; s++) fprintf(out, "%s\t%g\n", fq.names[order[s]].c_str(), score[order[s]]);  // default ostream precision
+	fclose(out);
+    }
+    if (VERBOSE) {
+	cerr << "Scores written to: " << scoresTsv << endl;
+	cerr << "Preparing batches:" << endl;
+    }
+
+    // PrepareSortedBatch for every read at once (the per-read work does not depend on the batch it lands in)
+    std::vector<uint8_t> skip(un, 0);
+    std::vector<int32_t> status(un, 0), hpc_len(un, 0);
+    std::vector<double> hpc_err(un, 0.0);
+    std::vector<char> hpc_seq, hpc_qual;
+    std::vector<Minimizer> mins, rev;
+    std::vector<int64_t> min_offs(un + 1, 0), rev_offs(un + 1, 0);
+    if (n) {
+	ICB_DO(ctx, icb_quality_filter(err.data(), n, args.MinQual, skip.data()));
+	ICB_DO(ctx, icb_sketch_reads(rs, args.KmerSize, args.WindowSize, qualTabNomin, skip.data()));
+	int64_t nf = 0, nr = 0;
+	ICB_DO(ctx, icb_sketch_sizes(rs, &nf, &nr));
+	hpc_seq.resize(fq.seq.size() + 1);
+	hpc_qual.resize(fq.seq.size() + 1);
+	mins.resize(size_t(nf) + 1);
+	rev.resize(size_t(nr) + 1);
+	ICB_DO(ctx, icb_sketch_download(rs, status.data(), hpc_len.data(), hpc_err.data(), hpc_seq.data(), hpc_qual.data(),
+					reinterpret_cast<icb_minimizer*>(mins.data()), min_offs.data(),
+					reinterpret_cast<icb_minimizer*>(rev.data()), rev_offs.data()));
+    }
+    icb_readset_destroy(rs);
+    icb_ctx_destroy(ctx);
+
+    FlatReads R{fq.seq.data(), fq.qual.data(), fq.offs.data(), fq.names.data(), score.data(), err.data(),
+		status.data(), hpc_len.data(), hpc_err.data(), hpc_seq.data(), hpc_qual.data(), mins.data(),
+		min_offs.data(), rev.data(), rev_offs.data()};
+    // the batch windows of main.cpp:149-199
+    unsigned long batchBases = 0;
+    int batchSeqs = 0, nrBatches = 0, batchStart = 0;
+    int64_t i = 0;
+    auto emit = [&](int64_t last) {
+	const std::string outFile = batchDir + "/isONbatch_" + std::to_string(nrBatches) + ".cer";
+	save_sorted_batch(outFile, nrBatches, uint64_t(batchStart), uint64_t(last), batchBases, args, R, order.data());
+	if (VERBOSE)
+	    cerr << "\tWritten batch " << nrBatches << " with " << (i - batchStart + 1) << " sequences and "
+		 << int(double(batchBases) / 1000.0) << " kilobases." << endl;
+    };
+    for (i = 0; i < n; i++) {
+	batchBases += static_cast<unsigned long>(fq.offs[order[i] + 1] - fq.offs[order[i]]);
+	batchSeqs++;
+	if ((args.BatchSize > 0) &&
+	    ((batchBases > static_cast<unsigned long>(args.BatchSize * 1000)) || ((args.BatchMaxSeq > 0) && batchSeqs >= args.BatchMaxSeq))) {
+	    emit(i);
+	    batchBases = 0;
+	    batchSeqs = 0;
+	    batchStart = int(i + 1);
+	    nrBatches++;
+	}
+    }
+    if (batchStart < int(n)) emit(n - 1);
+    return 0;
+}
+
+// ---------------------------------------------------------------- info (main.cpp:394-422)
+static void print_batch_info(const Batch& b)
+{
+    cerr << "\tBatch number: " << b.BatchNr << endl;
+    cerr << "\tBatch range: [" << b.BatchStart << "," << b.BatchEnd << "]" << endl;
+    cerr << "\tDepth: " << b.Depth << endl;
+    cerr << "\tNr sequences: " << b.BatchEnd - b.BatchStart + 1 << endl;
+    cerr << "\tNr bases: " << b.BatchBases << endl;
+    cerr << "\tNr clusters: " << nr_clusters(b) << endl;
+    cerr << "\tNr nontrivial clusters: " << nr_nontrivial_clusters(b) << endl;
+    cerr << "\tMinimizers in database: " << int(b.MinDB.size()) << endl;
+}
+
+static std::unique_ptr<Batch> load_or_die(const std::string& path)
+{
+    try {
+	return load_batch(path);
+    }
+    catch (const std::runtime_error& e) {  // serialize.cpp:19-24
+	cerr << "Failed to load batch " << path << ":" << e.what() << endl;
+	exit(1);
+    }
+}
+
+static int main_info(int argc, char** argv)
+{
+    if (argc <= 2 || std::string(argv[2]) == "-h") {
+	print_help_info();
+	exit(0);
+    }
+    auto b = load_or_die(argv[2]);
+    cerr << "Loaded batch from " << argv[2] << ":" << endl;
+    print_batch_info(*b);
+    return 0;
+}
+
+// ---------------------------------------------------------------- p_shared grid (InitMinSharedMap, p_emp_prob.cpp:22-47)
+static std::string exe_dir()
+{
+    char buf[4096];
+    ssize_t n = readlink("/proc/self/exe", buf, sizeof(buf) - 1);
+    if (n <= 0) return ".";
+    buf[n] = 0;
+    std::string p(buf);
+    size_t s = p.rfind('/');
+    return s == std::string::npos ? "." : p.substr(0, s);
+}
+
+static void load_p_shared(int k, int w, double out[225])
+{
+    for (int i = 0; i < 225; i++) out[i] = std::numeric_limits<double>::quiet_NaN();
+    const char* env = getenv("ICB_PEMP_TABLE");
+    std::string path = env ? env : exe_dir() + "/../data/p_emp_prob.bin";
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) {
+	cerr << "isONclust2 (B200): cannot open the empirical probability table " << path << " (set ICB_PEMP_TABLE)" << endl;
+	exit(1);
+    }
+    char magic[8];
+    uint32_t n = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "ICBPEMP1", 8) != 0 || fread(&n, 4, 1, f) != 1) {
+	cerr << "isONclust2 (B200): bad table file " << path << endl;
+	exit(1);
+    }
+    struct __attribute__((packed)) Row {
+	uint8_t k, w, c1, c2;
+	double p;
+    };
+    std::vector<Row> rows(n);
+    if (fread(rows.data(), sizeof(Row), n, f) != n) {
+	cerr << "isONclust2 (B200): truncated table file " << path << endl;
+	exit(1);
+    }
+    fclose(f);
+    for (const Row& r : rows) {	 // file order: later rows overwrite
+	if (int(r.k) != k || std::abs(int(r.w) - w) > 2) continue;
+	if (r.c1 < 1 || r.c1 > 15 || r.c2 < 1 || r.c2 > 15) continue;
+	out[(r.c1 - 1) * 15 + (r.c2 - 1)] = r.p;
+	out[(r.c2 - 1) * 15 + (r.c1 - 1)] = r.p;
+    }
+}
+
+// ---------------------------------------------------------------- cluster (main.cpp:238-392 + cluster.cpp:67-322)
+static int main_cluster(int argc, char** argv)
+{
+    CmdArgsCluster cmd = parse_args_cluster(argc, argv);
+    VERBOSE = cmd.Verbose;
+    const bool SINGLE = cmd.RightCereal == "";
+    auto left = load_or_die(cmd.LeftCereal);
+    if (VERBOSE) {
+	cerr << "Loaded input batch from " << cmd.LeftCereal << ":" << endl;
+	print_batch_info(*left);
+    }
+    std::unique_ptr<Batch> right;
+    if (!SINGLE) {
+	right = load_or_die(cmd.RightCereal);
+	cerr << "Loaded input batch from " << cmd.RightCereal << ":" << endl;
+	right->MinDB = MinimizerDB(0, UnsignedHash());
+	print_batch_info(*right);
+    }
+    else {
+	right = create_pseudo_batch(*left);
+	if (VERBOSE) {
+	    cerr << "Created pseudo-batch for single clustering:" << endl;
+	    print_batch_info(*right);
+	    cerr << "Resetting input clusters." << endl;
+	}
+	left->Cls.clear();
+	if (left->Depth > 0) left->Depth = -left->Depth;
+	left->NrCls = 0;
+	left->MinDB = MinimizerDB(MIN_DB_RESERVE, UnsignedHash());
+    }
+    if (left->SortArgs.Mode != cmd.Mode) left->SortArgs.Mode = cmd.Mode;
+    if (right->SortArgs.Mode != cmd.Mode) right->SortArgs.Mode = cmd.Mode;
+    if (VERBOSE && left->SortArgs.ConsMaxSize > 0) cerr << "Generating consensus using spoa algorithm: " << cmd.SpoaAlgo << endl;
+    if (cmd.MinClsSize > 0) left->SortArgs.MinClsSize = cmd.MinClsSize;
+    if (VERBOSE) {
+	cerr << "Clustering mode: ";
+	switch (left->SortArgs.Mode) {
+	    case None: cerr << "Invalid clustering mode: " << int(None) << endl; exit(1);
+	    case Sahlin: cerr << "sahlin"; break;
+	    case Fast: cerr << "fast"; break;
+	    case Furious: cerr << "furious"; break;
+	}
+	cerr << endl;
+    }
+    // ---- ClusterSortedReads: the checks of cluster.cpp:70-95
+    if (!same_sort_args(left->SortArgs, right->SortArgs)) {
+	cerr << "The left and right batches have been sorted with different parameters! " << endl;
+	cerr << "Refusing to carry on with clustering as results would not make sense! " << endl;
+	exit(1);
+    }
+    const CmdArgs args = left->SortArgs;
+    if (right->Depth > 0 && right->BatchStart != (left->BatchEnd + 1)) {
+	cerr << "Trying to merge non-consecutive batches! Giving up!" << endl;
+	exit(1);
+    }
+    if (left->Depth > 0 && right->Depth > left->Depth) {
+	cerr << "The left input batch must have higher depth!" << endl;
+	exit(1);
+    }
+    if (args.ConsMaxSize > 0) {
+	cerr << "isONclust2 (B200): consensus generation (-c " << args.ConsMaxSize
+	     << ") is not part of this build; sort with the default -c (disabled)." << endl;
+	exit(1);
+    }
+    if (left->MinDB.size() == 0) left->MinDB = MinimizerDB(MIN_DB_RESERVE, UnsignedHash());
+    right->MinDB = MinimizerDB(0, UnsignedHash());
+
+    // ---- the reads the device sees: representatives of the existing (left) clusters, then the eligible right reads
+    const size_t nl = left->Cls.size(), nright = right->Cls.size();
+    unsigned sizeFiltered = 0;
+    std::vector<int32_t> best(nright, -2), strand(nright, 0);
+    std::vector<size_t> eligible;
+    for (size_t i = 0; i < nright; i++)
+	if (right_is_eligible(*left, *right, i, &sizeFiltered)) eligible.push_back(i);
+
+    if (args.Mode == None || eligible.empty()) {
+	// getBestCluster with Mode None returns (-1, 0) for every read (cluster.cpp:545-567): every eligible read founds a cluster
+	for (size_t i : eligible) best[i] = -1;
+    }
+    else {
+	std::string seq, qual;
+	std::vector<int64_t> offs{0};
+	auto push = [&](const SeqRec& s) {
+	    seq += s.seq;
+	    qual += s.qual;
+	    offs.push_back(int64_t(seq.size()));
+	};
+	for (size_t c = 0; c < nl; c++) {
+	    const auto& cl = left->Cls[c];
+	    if (!cl || cl->empty() || !cl->at(0) || !cl->at(0)->raw || !cl->at(0)->hpc) {
+		cerr << "isONclust2 (B200): left cluster " << c << " has no representative sequence" << endl;
+		exit(1);
+	    }
+	    push(*cl->at(0)->raw);
+	}
+	for (size_t i : eligible) push(*right->Cls[i]->at(0)->raw);
+	const int64_t n = int64_t(offs.size()) - 1;
+
+	double qualTab[129], qualTabNomin[129];
+	icb_init_qual_tab(qualTab, 0);
+	icb_init_qual_tab(qualTabNomin, 1);
+	icb_ctx* ctx = open_device();
+	icb_readset* rs = nullptr;
+	ICB_DO(ctx, icb_readset_create(ctx, seq.data(), qual.data(), offs.data(), n, &rs));
+	ICB_DO(ctx, icb_score_reads(rs, args.KmerSize, qualTab, qualTabNomin));
+	ICB_DO(ctx, icb_sketch_reads(rs, args.KmerSize, args.WindowSize, qualTabNomin, nullptr));
+	{  // the sketches in the batch files must be the ones this k / w produce (they are what the reference would query)
+	    const size_t un = static_cast<size_t>(n);
+	    std::vector<int32_t> status(un, 0);
+	    std::vector<int64_t> mo(un + 1, 0), ro(un + 1, 0);
+	    int64_t nf = 0, nr = 0;
+	    ICB_DO(ctx, icb_sketch_sizes(rs, &nf, &nr));
+	    std::vector<Minimizer> mins(static_cast<size_t>(nf) + 1), rev(static_cast<size_t>(nr) + 1);
+	    ICB_DO(ctx, icb_sketch_download(rs, status.data(), nullptr, nullptr, nullptr, nullptr, reinterpret_cast<icb_minimizer*>(mins.data()),
+					    mo.data(), reinterpret_cast<icb_minimizer*>(rev.data()), ro.data()));
+	    for (int64_t r = 0; r < n; r++) {
+		const ProcSeq& p = size_t(r) < nl ? *left->Cls[size_t(r)]->at(0) : *right->Cls[eligible[size_t(r) - nl]]->at(0);
+		const bool same = status[r] == 1 && size_t(mo[r + 1] - mo[r]) == p.mins.size() && size_t(ro[r + 1] - ro[r]) == p.rev.size() &&
+				  (p.mins.empty() || memcmp(p.mins.data(), mins.data() + mo[r], p.mins.size() * sizeof(Minimizer)) == 0) &&
+				  (p.rev.empty() || memcmp(p.rev.data(), rev.data() + ro[r], p.rev.size() * sizeof(Minimizer)) == 0);
+		if (!same) {
+		    cerr << "isONclust2 (B200): the stored minimizers of " << p.id << " are not those of k=" << args.KmerSize
+			 << " w=" << args.WindowSize << " on its stored sequence; refusing to cluster an inconsistent batch." << endl;
+		    exit(1);
+		}
+	    }
+	}
+	icb_cluster_params P;
+	memset(&P, 0, sizeof(P));
+	P.kmer_size = args.KmerSize;
+	P.window_size = args.WindowSize;
+	P.mode = args.Mode;
+	P.min_shared = args.MinShared;
+	P.mapped_threshold = args.MappedThreshold;
+	P.aligned_threshold = args.AlignedThreshold;
+	P.min_fraction = args.MinFraction;
+	P.min_prob_no_hits = args.MinProbNoHits;
+	P.min_qual = args.MinQual;
+	load_p_shared(args.KmerSize, args.WindowSize, P.p_shared);
+	const char* chunk = getenv("ICB_CHUNK");
+	P.chunk_size = chunk ? atoi(chunk) : 0;
+	icb_clusterer* cl = nullptr;
+	{
+	    int rc = icb_clusterer_create(rs, &P, &cl);
+	    if (rc == ICB_ERR_NO_PEMP) {  // GetPMinShared throws std::invalid_argument (p_emp_prob.cpp:88), uncaught in the reference
+		cerr << "terminate called after throwing an instance of 'std::invalid_argument'\n  what():  Empirical probability lookup failure!" << endl;
+		abort();
+	    }
+	    if (rc) die_icb(ctx, rc, "icb_clusterer_create");
+	}
+	std::vector<int32_t> ids(static_cast<size_t>(n), 0);
+	for (int64_t r = 0; r < n; r++) ids[size_t(r)] = int32_t(r);
+	if (nl) ICB_DO(ctx, icb_clusterer_seed(cl, ids.data(), int64_t(nl)));
+	const int64_t ne = int64_t(eligible.size());
+	std::vector<int32_t> cluster_of(static_cast<size_t>(ne), -1), strand_of(static_cast<size_t>(ne), 0);
+	ICB_DO(ctx, icb_cluster_reads(cl, ids.data() + nl, ne, cluster_of.data(), strand_of.data()));
+	int32_t ncls = int32_t(nl);
+	for (int64_t t = 0; t < ne; t++) {
+	    const int32_t c = cluster_of[size_t(t)];
+	    if (c < 0) {
+		cerr << "isONclust2 (B200): device and host disagree on whether " << right->Cls[eligible[size_t(t)]]->at(0)->id << " is clustered" << endl;
+		exit(1);
+	    }
+	    if (c == ncls) {
+		best[eligible[size_t(t)]] = -1;
+		ncls++;
+	    }
+	    else {
+		best[eligible[size_t(t)]] = c;
+		strand[eligible[size_t(t)]] = strand_of[size_t(t)];
+	    }
+	}
+	if (VERBOSE) {
+	    icb_cluster_stats st;
+	    icb_clusterer_stats(cl, &st);
+	    cerr << "Finished clustering!" << endl;
+	    cerr << "Alignment invocation count: " << st.aln_invoked << " (" << (nright ? 100.0 * double(st.aln_invoked) / double(nright) : 0.0) << "%)" << endl;
+	    cerr << "Consensus invocation count: 0 (0%)" << endl;
+	}
+	icb_clusterer_destroy(cl);
+	icb_readset_destroy(rs);
+	icb_ctx_destroy(ctx);
+    }
+    apply_decisions(*left, *right, best, strand, cmd.SeqPurge);
+    if (VERBOSE) {
+	std::cout << std::endl;	 // cluster.cpp:312
+	if (left->SortArgs.MinClsSize > 1)
+	    cerr << "Filtered out " << sizeFiltered << " input clusters smaller than " << left->SortArgs.MinClsSize << "." << endl;
+	unsigned count = 0;
+	for (auto& c : left->Cls)
+	    if (c->size() > 1) count++;
+	cerr << "Number of clusters larger than 1: " << count << endl;
+	cerr << "Output batch statistics:" << endl;
+	print_batch_info(*left);
+    }
+    left->LeftLeaf = cmd.LeftCereal;
+    left->RightLeaf = cmd.RightCereal;
+    if (cmd.MinPurge) {
+	cerr << "Purging minimizer database in output batch!" << endl;
+	left->MinDB = MinimizerDB(0, UnsignedHash());
+    }
+    save_batch(*left, cmd.OutCereal);
+    if (VERBOSE) cerr << "Output batch written to: " << cmd.OutCereal << endl;
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc == 1) {
+	print_help();
+	exit(0);
+    }
+    const std::string sub = argv[1];
+    try {
+	if (sub == "sort") return main_sort(argc, argv);
+	if (sub == "cluster") return main_cluster(argc, argv);
+	if (sub == "info") return main_info(argc, argv);
+	if (sub == "version") {
+	    std::cout << "isONclust2 version: " << ICB_VERSION << endl;
+	    return 0;
+	}
+	if (sub == "help" || sub == "-h" || sub == "--help") {
+	    print_help();
+	    return 0;
+	}
+	if (sub == "dump") {
+	    cerr << "isONclust2 (B200): `dump` is not part of this build (it reads the same .cer files: use the reference binary)." << endl;
+	    return 1;
+	}
+    }
+    catch (const std::exception& e) {
+	cerr << "isONclust2 (B200): " << e.what() << endl;
+	return 1;
+    }
+    cerr << "Invalid subcommand: " << sub << endl;
+    cerr << "Valid subcommands are: sort, cluster, dump, info, version, help" << endl;
+    cerr << "Inkove \"isONclust2 help\" for more details." << endl;
+    return 1;
+}

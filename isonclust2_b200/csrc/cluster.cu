@@ -408,7 +408,10 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     // full list, ascending by id — the map provisional id -> real id is monotone, so the order survives it
     std::vector<IcbCand> ro_real;
     std::vector<SortedCand> ro_out;
+    std::map<int, std::pair<int, std::vector<SortedCand>>> order_cache;	 // pos -> (version it was computed for, order)
     auto reference_order = [&](int pos, const std::vector<IcbCand>& all) -> const std::vector<SortedCand>& {
+	auto& slot = order_cache[pos];
+	if (slot.first == version + 1) return slot.second;  // same set of committed founders as last time
 	ro_real.clear();
 	for (auto& c : all) {
 	    int rid = real_id(c.id);
@@ -421,16 +424,20 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	icb_reference_order(ro_real.data(), int(ro_real.size()), 20 * (size_t(nf[r]) + size_t(nr[r])), ro_scratch, ro_out);
 	stats.ms_order += t.lap();
 	stats.order_calls++;
-	return ro_out;
+	slot.first = version + 1;
+	slot.second = ro_out;
+	return slot.second;
     };
 
     // decision for the read at `pos` given the founders committed so far.  Returns OUT_NEED when device work is
     // missing (alignment pairs appended to needPairs, tie reads to needFull).
     bool usedAln = false, usedTie = false;
+    int alnCalls = 0;  // DP calls the reference makes for the read being decided (getBestClusterAln stops at the first pass)
     std::vector<IcbCand> v, cs;	 // scratch of decide(), reused across calls (no allocation in steady state)
     std::vector<const IcbCand*> pass, tied;
     auto decide = [&](int pos, int& outCls, int& outStrand, std::vector<AlnKey>& needPairs, std::vector<int32_t>& needFull) -> Outcome {
 	usedAln = usedTie = false;
+	alnCalls = 0;
 	const int r = chunk[pos];
 	v.clear();
 	int top = hdr[pos].top_snap;
@@ -488,31 +495,29 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	}
 	if (unsigned(top) < unsigned(P.min_shared)) return OUT_NEW;  // cluster.cpp:553-556
 	if (P.mode == 1) return OUT_NEW;			      // fast: minimizers only
-	// getBestClusterAln: candidates tied with the top count, in order, first passing wins
+	// getBestClusterAln: candidates tied with the top count, in the reference's order, first passing wins
+	// (cluster.cpp:480-512).  Like the reference, a candidate is only aligned once every candidate before it failed:
+	// with several tied candidates the order is needed BEFORE the first alignment, so the full list is fetched first.
 	tied.clear();
 	for (auto& c : v)
 	    if (c.count == top) tied.push_back(&c);
-	bool missing = false;
-	for (auto* c : tied) {
-	    AlnKey key{pos, c->id, c->strand};
-	    if (aln.find(key) == aln.end()) {
-		needPairs.push_back(key);
-		missing = true;
-	    }
-	}
-	if (missing) return OUT_NEED;
-	usedAln = true;
 	const unsigned readLen = unsigned(rs->h_offs[r + 1] - rs->h_offs[r]);
-	pass.clear();
-	for (auto* c : tied) {
-	    double ratio = double(aln[AlnKey{pos, c->id, c->strand}]) / readLen;  // cluster.cpp:458
-	    if (ratio >= P.aligned_threshold) pass.push_back(c);
-	}
-	if (pass.empty()) return OUT_NEW;
-	if (pass.size() == 1 || tied.size() == 1) {
-	    outCls = real_id(pass[0]->id);
-	    outStrand = pass[0]->strand;
-	    return OUT_JOIN;
+	if (tied.size() == 1) {
+	    const IcbCand* c = tied[0];
+	    const AlnKey key{pos, c->id, c->strand};
+	    auto ia = aln.find(key);
+	    if (ia == aln.end()) {
+		needPairs.push_back(key);
+		return OUT_NEED;
+	    }
+	    usedAln = true;
+	    alnCalls = 1;
+	    if (double(ia->second) / readLen >= P.aligned_threshold) {	// cluster.cpp:458, 503
+		outCls = real_id(c->id);
+		outStrand = c->strand;
+		return OUT_JOIN;
+	    }
+	    return OUT_NEW;
 	}
 	auto it = full.find(pos);
 	if (it == full.end()) {
@@ -521,15 +526,32 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	}
 	usedTie = true;
 	const auto& order = reference_order(pos, it->second);
+	alnCalls = 0;
 	for (auto& o : order) {
-	    for (auto* p : pass)
+	    if (int(o.Size) != top) break;  // sorted by Size, descending: the tied candidates come first
+	    const IcbCand* c = nullptr;
+	    for (auto* p : tied)
 		if (unsigned(real_id(p->id)) == o.Cls && p->strand == o.Strand) {
-		    outCls = int(o.Cls);
-		    outStrand = o.Strand;
-		    return OUT_JOIN;
+		    c = p;
+		    break;
 		}
+	    if (!c) continue;
+	    const AlnKey key{pos, c->id, c->strand};
+	    auto ia = aln.find(key);
+	    if (ia == aln.end()) {
+		needPairs.push_back(key);
+		return OUT_NEED;
+	    }
+	    alnCalls++;
+	    if (double(ia->second) / readLen >= P.aligned_threshold) {
+		usedAln = true;
+		outCls = int(o.Cls);
+		outStrand = o.Strand;
+		return OUT_JOIN;
+	    }
 	}
-	return OUT_NEW;	 // unreachable
+	usedAln = true;
+	return OUT_NEW;
     };
 
     while (commit_pos < N) {
@@ -558,7 +580,10 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    }
 	    if (speculative) continue;
 	    // commit in order
-	    if (usedAln) stats.aln_invoked++;
+	    if (usedAln) {
+		stats.aln_invoked++;
+		stats.aln_calls_ref += alnCalls;
+	    }
 	    if (usedTie) stats.tie_fallbacks++;
 	    if (o == OUT_NEW) {
 		founder_cls[pos] = nextCls;
@@ -840,6 +865,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    t.pairs_aligned += s.pairs_aligned; t.cells_aligned += s.cells_aligned; t.tie_fallbacks += s.tie_fallbacks;
 	    t.decisions += s.decisions; t.ms_query += s.ms_query; t.ms_full += s.ms_full; t.ms_align += s.ms_align;
 	    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host; t.ms_cpu += s.ms_cpu; t.ms_order += s.ms_order; t.order_calls += s.order_calls;
+		t.aln_calls_ref += s.aln_calls_ref;
 	}
 	if (rc) {
 	    int z = 0;
@@ -861,6 +887,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    stats->tie_fallbacks += s.tie_fallbacks; stats->decisions += s.decisions; stats->ms_query += s.ms_query;
 	    stats->ms_full += s.ms_full; stats->ms_align += s.ms_align; stats->ms_insert += s.ms_insert; stats->ms_host += s.ms_host;
 	    stats->ms_cpu += s.ms_cpu; stats->ms_order += s.ms_order; stats->order_calls += s.order_calls;
+	    stats->aln_calls_ref += s.aln_calls_ref;
 	}
 	icb_ctx_fold_child(ctx, ctx->pool_ctx[w]);  // the worker's kernel timers and launch count -> parent
     }

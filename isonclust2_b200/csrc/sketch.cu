@@ -432,12 +432,16 @@ __global__ void __launch_bounds__(SK_THREADS) icb_k_sketch(SketchArgs a)
 //      one atomicAdd and lane j writes minimizer j: fully coalesced 12-byte records.
 constexpr int SW_WARPS = 8;
 constexpr int SW_THREADS = SW_WARPS * 32;
-constexpr int SW_LMAX = 3072;		    // longest raw read on this path
-constexpr int SW_HBUF = SW_LMAX + 32;	    // bytes per compressed buffer: 16-byte phase of the global slot + slack
-constexpr int SW_NWORD = SW_LMAX / 16 + 4;  // packed words per stream
-constexpr int SW_LIST = SW_HBUF / 2;	    // argmin positions (uint16) per strand that fit the reused buffers
-constexpr int SW_PER_WARP = 2 * SW_HBUF + 2 * SW_NWORD * 4;
+// Two compiled shapes: reads up to 2688 bases with 64 registers -> 4 CTAs (32 warps) per SM, the default; reads up to 3072
+// bases with 72 registers -> 3 CTAs per SM (ICB_SKETCH_CTAS=3).  Longer reads go to the CTA kernel either way.
 constexpr int SW_TICKET = 4;		    // reads taken per ticket
+template <int LMAX>
+struct SwShape {
+    static constexpr int HBUF = LMAX + 32;	 // bytes per compressed buffer: 16-byte phase of the global slot + slack
+    static constexpr int NWORD = LMAX / 16 + 4;	 // packed words per stream
+    static constexpr int LIST = HBUF / 2;	 // argmin positions (uint16) per strand that fit the reused buffers
+    static constexpr int PER_WARP = 2 * HBUF + 2 * NWORD * 4;
+};
 
 __device__ __forceinline__ uint32_t sw_prmt(uint32_t a, uint32_t b, uint32_t s)
 {
@@ -452,9 +456,11 @@ __device__ __forceinline__ uint32_t sw_nonzero_bytes(uint32_t x)
     return (t * 0x00204081u) >> 28;
 }
 
-template <int W>
-__global__ void __launch_bounds__(SW_THREADS, 3) icb_k_sketch_warp(SketchArgs a)
+template <int W, int SW_LMAX, int MIN_CTAS>
+__global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(SketchArgs a)
 {
+    constexpr int SW_HBUF = SwShape<SW_LMAX>::HBUF, SW_NWORD = SwShape<SW_LMAX>::NWORD, SW_LIST = SwShape<SW_LMAX>::LIST,
+		  SW_PER_WARP = SwShape<SW_LMAX>::PER_WARP;
     extern __shared__ __align__(16) uint8_t sw_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* hs = sw_smem + warp * SW_PER_WARP;
@@ -861,8 +867,13 @@ int icb_launch_sketch(icb_readset* rs, int k, int w, const uint8_t* d_skip)
     // ---- stage 1: warp-per-read kernel (keys of 2k + 5 bits, compiled window widths)
     const bool warp_path = 2 * k + 5 <= 32 && k >= 2 && (W == 5 || W == 8);
     if (warp_path) {
-	const size_t smem = size_t(SW_WARPS) * SW_PER_WARP;
-	auto kern = W == 5 ? icb_k_sketch_warp<5> : icb_k_sketch_warp<8>;
+	static const int want_ctas = [] {
+	    const char* e = getenv("ICB_SKETCH_CTAS");
+	    return e && atoi(e) == 3 ? 3 : 4;
+	}();
+	const size_t smem = size_t(SW_WARPS) * (want_ctas == 3 ? SwShape<3072>::PER_WARP : SwShape<2688>::PER_WARP);
+	auto kern = want_ctas == 3 ? (W == 5 ? icb_k_sketch_warp<5, 3072, 3> : icb_k_sketch_warp<8, 3072, 3>)
+				   : (W == 5 ? icb_k_sketch_warp<5, 2688, 4> : icb_k_sketch_warp<8, 2688, 4>);
 	ICB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 	int per_sm = 0;
 	ICB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SW_THREADS, smem));

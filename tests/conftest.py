@@ -26,6 +26,11 @@ def _built():
             raise
     if not os.path.exists(g.LIB):
         g.build_cuda()
+    try:
+        g.build_cli()
+    except Exception:
+        if not os.path.exists(os.path.join(ROOT, "isonclust2_b200", "bin", "isONclust2")):
+            raise
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,122 @@
+"""Merge-tree scheduler (isonclust2_b200/tree.py): plan properties, world_size-2 sharding over gloo on CPU (with the
+reference binary as the job executable, so the reference's own consistency checks — consecutive ranges, left depth >=
+right depth, cluster.cpp:80-90 — police the plan), and on the GPU the same tree through the drop-in CLI."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "isONclust2")
+OUR_BIN = os.path.join(ROOT, "isonclust2_b200", "bin", "isONclust2")
+
+
+def test_plan_properties():
+    from isonclust2_b200 import tree
+    assert tree.plan(0) == ([], None)
+    for n in range(1, 70):
+        levels, root = tree.plan(n, "w")
+        assert (root.lo, root.hi) == (0, n - 1)
+        done = set()
+        for li, jobs in enumerate(levels):
+            for j in jobs:
+                if li == 0:
+                    assert j.left is None and j.lo == j.hi and j.depth == 0
+                else:
+                    a, b = j.left, j.right
+                    assert a.path in done and b.path in done  # inputs come from earlier levels only
+                    assert b.lo == a.hi + 1 and a.depth >= b.depth and j.depth == a.depth + 1
+                    assert (j.lo, j.hi) == (a.lo, b.hi)
+            done |= {j.path for j in jobs}
+        assert len(levels[0]) == n and sum(len(l) for l in levels[1:]) == n - 1
+        # round-robin sharding partitions every level
+        for world in (1, 2, 3, 8):
+            for jobs in levels:
+                parts = [tree.shard(jobs, r, world) for r in range(world)]
+                assert sorted(j.path for p in parts for j in p) == sorted(j.path for j in jobs)
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from isonclust2_b200 import tree
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+log = []
+def runner(cmd, env):
+    import subprocess
+    log.append(" ".join(cmd[1:]))
+    r = subprocess.run(cmd, cwd={cwd!r}, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, (cmd, r.stderr[-1500:])
+root = tree.run_tree({n}, "srt/batches", "par", "sahlin", rank, world, dist.barrier, runner=runner, cli={cli!r})
+gathered = [None] * world
+dist.all_gather_object(gathered, log)
+if rank == 0:
+    assert all(len(g) > 0 for g in gathered), gathered
+    assert sum(len(g) for g in gathered) == 2 * {n} - 1
+    print("ROOT", root.path)
+dist.destroy_process_group()
+"""
+
+
+def _sorted_batches(tmp_path, exe, n_reads=1000, per_batch=200):
+    from isonclust2_b200 import synth
+    seq, qual, offs = synth.make_reads(n_reads, seed=11)
+    synth.write_fastq(str(tmp_path / "reads.fq"), seq, qual, offs)
+    r = subprocess.run([exe, "sort", "-M", str(per_batch), "-o", "srt", "reads.fq"], cwd=tmp_path, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    from isonclust2_b200 import tree
+    return tree.count_batches(str(tmp_path / "srt" / "batches"))
+
+
+def _serial_tree(tmp_path, exe, n, outdir):
+    from isonclust2_b200 import tree
+    os.makedirs(tmp_path / outdir, exist_ok=True)
+
+    def runner(cmd, env):
+        r = subprocess.run(cmd, cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, (cmd, r.stderr[-1500:])
+    return tree.run_tree(n, "srt/batches", outdir, "sahlin", runner=runner, cli=exe)
+
+
+def _same_from_mindb(a, b):
+    """Leaf names (LeftLeaf / RightLeaf) hold the work directory; everything from the MinDB on must be identical."""
+    import cerfile
+    pa, pb = cerfile.parse(a), cerfile.parse(b)
+    keys = ("BatchNr", "BatchStart", "BatchEnd", "BatchBases", "NrCls", "Depth")
+    return all(pa[k] == pb[k] for k in keys) and pa["bytes"][pa["mindb_span"][0]:] == pb["bytes"][pb["mindb_span"][0]:]
+
+
+def test_two_ranks_gloo_tree_equals_serial_tree(tmp_path):
+    """world_size 2 over gloo on CPU: ranks split every level, barriers order the levels, the root `.cer` equals the one a
+    single process builds.  The jobs run the reference binary (CPU), which also enforces the merge constraints."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/isONclust2 not built (needs /root/reference)")
+    n = _sorted_batches(tmp_path, REF_BIN)
+    assert n == 5
+    root = _serial_tree(tmp_path, REF_BIN, n, "ser")
+    os.makedirs(tmp_path / "par")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, cwd=str(tmp_path), n=n, cli=REF_BIN))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", str(script)], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "ROOT par/m_0_4.cer" in r.stdout
+    assert _same_from_mindb(str(tmp_path / root.path), str(tmp_path / "par" / "m_0_4.cer"))
+
+
+@pytest.mark.gpu
+def test_tree_through_the_cli_matches_reference_tree(tmp_path):
+    """The whole pipeline (sort, 5 leaf jobs, 4 merges) through the B200 CLI == the same tree through the reference."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/isONclust2 not built")
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "our").mkdir()
+    n = _sorted_batches(tmp_path / "ref", REF_BIN)
+    assert _sorted_batches(tmp_path / "our", OUR_BIN) == n == 5
+    a = _serial_tree(tmp_path / "ref", REF_BIN, n, "t")
+    b = _serial_tree(tmp_path / "our", OUR_BIN, n, "t")
+    assert open(tmp_path / "ref" / a.path, "rb").read() == open(tmp_path / "our" / b.path, "rb").read()
