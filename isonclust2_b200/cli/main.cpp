@@ -1,8 +1,8 @@
-// isONclust2 (B200 build) — the `sort` / `cluster` / `info` subcommands of the reference's CLI (main.cpp, args.cpp) on top
+// isONclust2 (B200 build) — the `sort` / `cluster` / `dump` / `info` subcommands of the reference's CLI (main.cpp, args.cpp) on top
 // of the C ABI in include/isonclust2_b200.h.  Same flags, same output files, byte-identical `.cer` batches; the
 // data-parallel work (quality scores, sketches, candidate queries, alignments) runs on the device, the host keeps the
 // FASTQ / `.cer` I/O and the order-dependent bookkeeping (cer.cpp).  There is no CPU fallback: without a CUDA device every
-// subcommand that computes exits 1.
+// subcommand that computes exits 1 (`dump` and `info` only read files and need no device).
 //
 // Reference call sites mirrored here: mainSort main.cpp:74-202, mainCluster main.cpp:238-392, mainInfo main.cpp:394-409,
 // ParseArgsSort args.cpp:11-151, ParseArgsCluster args.cpp:154-259, SequencesPToFastq / WriteScores output.cpp:30-91.
@@ -11,6 +11,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include <iostream>
 #include <limits>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "cer.hpp"
@@ -91,12 +93,25 @@ static void print_help_info()
 		 "\t-h --help              Print help.\n"
 		 "\t[positional argument]  Input serialized batch (required).\n";
 }
+static void print_help_dump()
+{
+    std::cout << "\ndump - dump clustered batch:\n"
+		 "\t-o --outdir            Output directory.\n"
+		 "\t-i --index             Index of sorted reads.\n"
+		 "\t-v --verbose           Verbose output.\n"
+		 "\t-d --debug             Print debug info.\n"
+		 "\t-h --help              Print help.\n";
+}
 static void print_help()
 {
-    std::cout << "Available subcommands: sort, cluster, info, version, help (B200 build; `dump` is served by the reference binary)" << endl;
+    std::cout << "isONclust2 version: " << ICB_VERSION << endl;
+    std::cout << "Available subcommands: sort, cluster, dump, info, help, version" << endl;
     print_help_sort();
     print_help_cluster();
+    print_help_dump();
     print_help_info();
+    std::cout << "\nhelp - print help message\n";
+    std::cout << "\nversion - print version\n";
 }
 
 // ---------------------------------------------------------------- argument parsing
@@ -553,6 +568,196 @@ static int main_info(int argc, char** argv)
     return 0;
 }
 
+// ---------------------------------------------------------------- dump (mainDump main.cpp:204-236, dumpBatchInfo / dumpClusters
+// main.cpp:414-457, WriteClusters output.cpp:151-275, ParseArgsDump args.cpp:260-311).  Host only: it reads the final
+// `.cer` and the sorted FASTQ that `sort` wrote, no device work.
+static std::string rev_comp_or_die(const std::string& s)  // RevComp util.cpp:13-38
+{
+    std::string o(s.rbegin(), s.rend());
+    for (char& c : o) {
+	switch (c) {
+	    case 'A': c = 'T'; break;
+	    case 'C': c = 'G'; break;
+	    case 'G': c = 'C'; break;
+	    case 'T': c = 'A'; break;
+	    default:
+		// the reference throws a std::string nobody catches -> terminate
+		cerr << "terminate called after throwing an instance of 'std::string' (Invalid base encountered: " << c << ")" << endl;
+		abort();
+	}
+    }
+    return o;
+}
+
+static int main_dump(int argc, char** argv)
+{
+    static const struct option longopts[] = {
+	{"verbose", no_argument, 0, 'v'},      {"debug", no_argument, 0, 'd'},	      {"help", no_argument, 0, 'h'},
+	{"outdir", required_argument, 0, 'o'}, {"index", required_argument, 0, 'i'}, {0, 0, 0, 0},
+    };
+    std::string outDir, index;
+    bool verbose = false;
+    int sargc = argc - 1;
+    char** sargv = argv + 1;
+    int iarg = 0, li = 0;
+    while (iarg != -1) {
+	iarg = getopt_long(sargc, sargv, "dhvo:i:", longopts, &li);
+	switch (iarg) {
+	    case 'h': print_help_dump(); exit(0);
+	    case 'o': outDir = optarg; break;
+	    case 'i': index = optarg; break;
+	    case 'v': verbose = true; break;
+	    case 'd': break;
+	}
+    }
+    if (outDir.empty()) {
+	cerr << "Specifying output directory is mandatory!" << endl;
+	print_help();
+	exit(1);
+    }
+    if (optind >= sargc) {	// the reference dereferences a null pointer here
+	cerr << "isONclust2 (B200): dump needs the clustered batch as positional argument" << endl;
+	exit(1);
+    }
+    VERBOSE = verbose;
+    const std::string inCereal = sargv[optind];
+    if (VERBOSE) cerr << "Loading batch..." << endl;
+    auto b = load_or_die(inCereal);
+    if (VERBOSE) {
+	cerr << "Loaded batch from " << inCereal << ":" << endl;
+	print_batch_info(*b);
+    }
+    b->MinDB = MinimizerDB(0, UnsignedHash());
+    b->ConsGs.clear();
+    b->ConsGsValid.clear();
+    create_outdir(outDir);
+    {  // dumpBatchInfo, after the MinDB was dropped (main.cpp:217-219)
+	FILE* f = create_file(outDir + "/batch_info.tsv");
+	fprintf(f, "Name\tValue\nBatchNumber\t%d\nBatchStart\t%llu\nBatchEnd\t%llu\nDepth\t%d\nNrBases\t%llu\nNrClusters\t%d\nNrNontrivialCls\t%d\nMinDBsize\t%d\n",
+		b->BatchNr, (unsigned long long)b->BatchStart, (unsigned long long)b->BatchEnd, b->Depth, (unsigned long long)b->BatchBases,
+		nr_clusters(*b), nr_nontrivial_clusters(*b), int(b->MinDB.size()));
+	fclose(f);
+    }
+    std::string sortedFastq;
+    try {  // LoadIndex output.cpp:94-108
+	Reader r(index);
+	sortedFastq = r.str();
+    }
+    catch (const std::runtime_error& e) {
+	cerr << "Failed to load index " << index << ":" << e.what() << endl;
+	exit(1);
+    }
+    if (VERBOSE) {
+	cerr << "Loaded index from " << index << ":" << endl;
+	cerr << "Sorting clusters by size." << endl;
+    }
+    if (!b->Cls.empty()) {
+	for (size_t i = 0; i < b->Cls.size(); i++) {
+	    if (!b->Cls[i] || b->Cls[i]->empty() || !b->Cls[i]->at(0) || !b->Cls[i]->at(0)->raw) {
+		cerr << "Null pointer instead of cluster rep sequence at index: " << i << endl;
+		exit(1);
+	    }
+	}
+	// SortClustersBySize cluster.cpp:570-580: std::sort (unstable) — the same algorithm on the same comparisons
+	std::sort(b->Cls.begin(), b->Cls.end(), [](const std::shared_ptr<Cluster> x, const std::shared_ptr<Cluster> y) {
+	    if (x->size() == y->size()) return x->at(0)->raw->score > y->at(0)->raw->score;
+	    return x->size() > y->size();
+	});
+	// dumpClusters main.cpp:430-457
+	struct IdInfo {
+	    unsigned Cls;
+	    int Strand;
+	};
+	std::unordered_map<std::string, IdInfo> idToCls;
+	FILE* info = create_file(outDir + "/clusters_info.tsv");
+	create_outdir(outDir + "/cluster_fastq");
+	fputs("ClusterId\tSize\n", info);
+	for (size_t i = 0; i < b->Cls.size(); i++) {
+	    fprintf(info, "%zu\t%zu\n", i, b->Cls[i]->size() - 1);
+	    for (auto& cc : *b->Cls[i]) idToCls[cc->id] = IdInfo{unsigned(i), cc->strand};
+	}
+	fclose(info);
+	// WriteClusters output.cpp:151-275
+	FILE* infq = fopen(sortedFastq.c_str(), "rb");
+	if (!infq) {
+	    cerr << "Failed to open " + sortedFastq + "!" << endl;
+	    exit(1);
+	}
+	FILE* tsv = create_file(outDir + "/clusters.tsv");
+	FILE* cons = create_file(outDir + "/cluster_cons.fq");
+	fputs("ClusterId\tStrand\tRead\n", tsv);
+	if (VERBOSE) cerr << "Writing out cluster information:" << endl;
+	for (size_t i = 0; i < b->Cls.size(); i++) {
+	    const ProcSeq& rep = *b->Cls[i]->at(0);
+	    const SeqRec& s = *rep.raw;
+	    if (s.score < 0) continue;
+	    std::string seq = s.seq;
+	    if (rep.strand == -1) seq = rev_comp_or_die(seq);
+	    // the quality line is the stored one even on the minus strand (the reference's FIXME, output.cpp:200)
+	    fprintf(cons, "@cluster_%zu origin=%s:%d length=%zu size=%zu\n", i, s.name.c_str(), rep.strand, seq.size(), b->Cls[i]->size() - 1);
+	    fwrite(seq.data(), 1, seq.size(), cons);
+	    fputs("\n+\n", cons);
+	    fwrite(s.qual.data(), 1, s.qual.size(), cons);
+	    fputc('\n', cons);
+	}
+	fclose(cons);
+	if (VERBOSE) cerr << endl;
+	b->Cls = Clusters();
+	if (VERBOSE) cerr << "Loading fastq records:" << endl;
+	// cluster id -> its records in file order; the reference keeps them in an unordered_map and writes one file per key
+	std::unordered_map<unsigned, std::vector<std::string>> seqCache;
+	{
+	    char* line = nullptr;
+	    size_t cap = 0;
+	    std::string rec[4];
+	    for (;;) {
+		// GetRecords output.cpp:128-141: four getline calls; a header read that hits EOF ends the file
+		ssize_t n = getline(&line, &cap, infq);
+		if (n <= 0) break;
+		const bool hadNl = line[n - 1] == '\n';
+		rec[0].assign(line, size_t(hadNl ? n - 1 : n));
+		if (!hadNl) break;  // std::getline sets eofbit when no newline ends the last line
+		for (int q = 1; q < 4; q++) {
+		    n = getline(&line, &cap, infq);
+		    if (n <= 0) rec[q].clear();
+		    else rec[q].assign(line, size_t(line[n - 1] == '\n' ? n - 1 : n));
+		}
+		const std::string readId = rec[0].empty() ? std::string() : rec[0].substr(1);
+		auto v = idToCls.find(readId);
+		if (v == idToCls.end()) continue;
+		if (v->second.Strand == -1) {
+		    rec[1] = rev_comp_or_die(rec[1]);
+		    std::reverse(rec[3].begin(), rec[3].end());
+		}
+		fprintf(tsv, "%u\t%d\t%s\n", v->second.Cls, v->second.Strand, readId.c_str());
+		std::string out;
+		out.reserve(rec[0].size() + rec[1].size() + rec[2].size() + rec[3].size() + 4);
+		for (int q = 0; q < 4; q++) {
+		    out += rec[q];
+		    out += '\n';
+		}
+		seqCache[v->second.Cls].push_back(std::move(out));
+	    }
+	    free(line);
+	}
+	fclose(infq);
+	fclose(tsv);
+	if (VERBOSE) cerr << endl << "Writing out cluster fastqs:" << endl;
+	for (auto& c : seqCache) {
+	    FILE* f = fopen((outDir + "/cluster_fastq/" + std::to_string(c.first) + ".fq").c_str(), "wb");
+	    if (!f) {
+		cerr << "Failed to open " + outDir + "/cluster_fastq/" + std::to_string(c.first) + ".fq!" << endl;
+		exit(1);
+	    }
+	    for (auto& r : c.second) fwrite(r.data(), 1, r.size(), f);
+	    fclose(f);
+	}
+	if (VERBOSE) cerr << endl;
+    }
+    if (VERBOSE) cerr << "Dump complete." << endl;
+    return 0;
+}
+
 // ---------------------------------------------------------------- p_shared grid (InitMinSharedMap, p_emp_prob.cpp:22-47)
 static std::string exe_dir()
 {
@@ -824,10 +1029,7 @@ int main(int argc, char** argv)
 	    print_help();
 	    return 0;
 	}
-	if (sub == "dump") {
-	    cerr << "isONclust2 (B200): `dump` is not part of this build (it reads the same .cer files: use the reference binary)." << endl;
-	    return 1;
-	}
+	if (sub == "dump") return main_dump(argc, argv);
     }
     catch (const std::exception& e) {
 	cerr << "isONclust2 (B200): " << e.what() << endl;

@@ -144,3 +144,39 @@ def test_chain_graph_matches_reference_graphs(refrun):
         assert num_codes == len(set(members[0]["raw"]["seq"]))
         (n_nodes,) = struct.unpack_from("<Q", g, 4 + 2 * (8 + 1024))
         assert n_nodes == n
+
+
+# ---------------------------------------------------------------- `dump` (host only: no device needed)
+OUR_BIN = os.path.join(ROOT, "isonclust2_b200", "bin", "isONclust2")
+
+
+def _tree(d):
+    out = {}
+    for base, _, files in os.walk(d):
+        for f in files:
+            p = os.path.join(base, f)
+            out[os.path.relpath(p, d)] = open(p, "rb").read()
+    return out
+
+
+@pytest.mark.parametrize("name", ["m012.cer", "c0.cer", "f0.cer", "n2.cer"])
+def test_dump_matches_reference(refrun, name):
+    """`isONclust2 dump` (mainDump main.cpp:204-236, WriteClusters output.cpp:151-275): every output file — batch_info.tsv,
+    clusters_info.tsv, clusters.tsv, cluster_cons.fq, cluster_fastq/<id>.fq — byte-identical to the reference binary's."""
+    d = refrun["dir"]
+    tag = name.replace(".cer", "")
+    run([REF_BIN, "dump", "-i", "srt/sorted_reads_idx.cer", "-o", f"dump_ref_{tag}", name], cwd=d)
+    run([OUR_BIN, "dump", "-i", "srt/sorted_reads_idx.cer", "-o", f"dump_our_{tag}", name], cwd=d)
+    a, b = _tree(d / f"dump_ref_{tag}"), _tree(d / f"dump_our_{tag}")
+    assert sorted(a) == sorted(b) and len(a) > 4
+    for k in a:
+        assert a[k] == b[k], k
+
+
+def test_dump_argument_errors(refrun):
+    d = refrun["dir"]
+    for exe in (REF_BIN, OUR_BIN):
+        r = subprocess.run([exe, "dump", "m012.cer"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "Specifying output directory is mandatory!" in r.stderr
+        r = subprocess.run([exe, "dump", "-o", "dump_bad", "-i", "nope.cer", "m012.cer"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1 and "Failed to load index nope.cer" in r.stderr
