@@ -157,6 +157,8 @@ typedef struct {
     double ms_order;	 /* part of ms_host spent reproducing the reference's candidate order for tie reads */
     int64_t order_calls; /* evaluations of that order */
     int64_t aln_calls_ref; /* DP problems the reference solves for the same reads (getBestClusterAln stops at the first pass) */
+    double ms_batch_max;   /* icb_cluster_batches: wall clock of the slowest batch */
+    double ms_wall;	   /* icb_cluster_batches: wall clock of the whole call */
 } icb_cluster_stats;
 
 typedef struct icb_clusterer icb_clusterer;

@@ -81,7 +81,7 @@ class ClusterStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("chunks", "rounds", "reads_queried", "aln_invoked", "pairs_aligned", "cells_aligned",
                                          "tie_fallbacks", "decisions")] + \
                [(n, C.c_double) for n in ("ms_query", "ms_full", "ms_align", "ms_insert", "ms_host", "ms_cpu", "ms_order")] + \
-               [("order_calls", C.c_int64), ("aln_calls_ref", C.c_int64)]
+               [("order_calls", C.c_int64), ("aln_calls_ref", C.c_int64), ("ms_batch_max", C.c_double), ("ms_wall", C.c_double)]
 
 
 MODES = {"sahlin": 0, "fast": 1, "furious": 2}
@@ -322,19 +322,30 @@ def run_pipeline(ctx, seq, qual, offs, k=11, w=15, mode="sahlin", min_qual=7.0, 
     own = rs is None
     if own:
         rs = ctx.upload(seq, qual, offs)
+    import time
+    t = [time.perf_counter()]
+    lap = lambda: (t.append(time.perf_counter()), (t[-1] - t[-2]) * 1e3)[1]
+    if own:
+        ctx.sync()
+    phases = {"upload": lap()}
     try:
         rs.score_async(k)
         score, err = rs.scores()
+        phases["score"] = lap()
         skip = quality_filtered(err, min_qual)
         order = sort_by_qual_scores(score)
+        phases["sort"] = lap()
         rs.sketch_async(k, w, skip=skip)
         lengths = np.diff(rs.offs)
         batches = split_batches(order, lengths, batch_kb, batch_max_seq)
         bounds = np.array([a for a, _ in batches] + [batches[-1][1] if batches else 0], dtype=np.int64)
+        phases["sketch_split"] = lap()
         cluster, strand, ncl, tot = cluster_batches(rs, order, bounds, k, w, n_workers=n_workers, mode=mode, min_qual=min_qual,
                                                     chunk_size=chunk_size, **cluster_kw)
+        phases["cluster"] = lap()
         ncl = [int(x) for x in ncl]
-        return dict(order=order, batches=batches, cluster=cluster, strand=strand, n_clusters=ncl, stats=tot, score=score, err=err)
+        return dict(order=order, batches=batches, cluster=cluster, strand=strand, n_clusters=ncl, stats=tot, score=score, err=err,
+                    phases_ms=phases)
     finally:
         if own and not keep:
             rs.close()

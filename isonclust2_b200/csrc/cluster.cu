@@ -392,14 +392,35 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 
     stats.ms_query += sw.lap();
     std::vector<int> founder_cls(N, -1);  // provisional founder -> real cluster id once committed
-    std::vector<int> eval_version(N, -1);  // founders committed in this chunk when the read was last evaluated
+    // A read's decision is a function of (its candidate lists, which of the provisional founders IN those lists are
+    // committed, the alignment results it asked for).  Decisions are cached and only re-evaluated when one of the read's own
+    // provisional candidates is committed (`dirty`) or device work it waited for has arrived (outcome OUT_NEED).
+    struct Decision {
+	int cls = -1, strand = 0, alnCalls = 0;
+	bool usedAln = false, usedTie = false;
+    };
+    std::vector<Decision> dec(N);
     std::vector<char> eval_outcome(N, OUT_NONE);
-    int version = 0;
+    std::vector<char> dirty(N, 1);
+    std::vector<std::vector<int32_t>> dependents(N);  // provisional founder -> later reads that list it as a candidate
     std::vector<char> committed(N, 0);
-    std::map<AlnKey, int> aln;		   // alignment results (aligned window count)
-    std::map<int, std::vector<IcbCand>> full;  // full candidate lists for tie reads
+    // alignment results per read: (provisional id, strand) -> aligned window count; a read asks for one or two pairs
+    struct AlnRes {
+	int id, strand, aligned;
+    };
+    std::vector<std::vector<AlnRes>> aln(N);
+    auto aln_find = [&](int pos, int id, int strand) -> const AlnRes* {
+	for (auto& a : aln[pos])
+	    if (a.id == id && a.strand == strand) return &a;
+	return nullptr;
+    };
+    std::vector<std::vector<IcbCand>> full(N);	// full candidate lists of tie reads
+    std::vector<char> have_full(N, 0);
     int nextCls = C0;
     int commit_pos = 0;
+    for (int i = 0; i < N; i++)
+	for (auto& c : cl[i])
+	    if (c.id >= C0) dependents[c.id - C0].push_back(i);
 
     auto real_id = [&](int id) { return id < C0 ? id : founder_cls[id - C0]; };
     auto rep_read = [&](int id) { return id < C0 ? founder[id] : chunk[id - C0]; };
@@ -408,10 +429,8 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     // full list, ascending by id — the map provisional id -> real id is monotone, so the order survives it
     std::vector<IcbCand> ro_real;
     std::vector<SortedCand> ro_out;
-    std::map<int, std::pair<int, std::vector<SortedCand>>> order_cache;	 // pos -> (version it was computed for, order)
+    std::vector<std::pair<int, std::vector<SortedCand>>> order_cache(N, std::make_pair(-1, std::vector<SortedCand>()));
     auto reference_order = [&](int pos, const std::vector<IcbCand>& all) -> const std::vector<SortedCand>& {
-	auto& slot = order_cache[pos];
-	if (slot.first == version + 1) return slot.second;  // same set of committed founders as last time
 	ro_real.clear();
 	for (auto& c : all) {
 	    int rid = real_id(c.id);
@@ -419,12 +438,15 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    ro_real.push_back(c);
 	    ro_real.back().id = rid;
 	}
+	// founders are only ever added while a chunk is processed: the same number of real candidates = the same set
+	auto& slot = order_cache[pos];
+	if (slot.first == int(ro_real.size())) return slot.second;
 	const int r = chunk[pos];
 	Stopwatch t;
 	icb_reference_order(ro_real.data(), int(ro_real.size()), 20 * (size_t(nf[r]) + size_t(nr[r])), ro_scratch, ro_out);
 	stats.ms_order += t.lap();
 	stats.order_calls++;
-	slot.first = version + 1;
+	slot.first = int(ro_real.size());
 	slot.second = ro_out;
 	return slot.second;
     };
@@ -473,13 +495,12 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 		}
 		if (pass.size() > 1) {
 		    // several equally scored candidates pass: the reference takes the first in ITS order
-		    auto it = full.find(pos);
-		    if (it == full.end()) {
+		    if (!have_full[pos]) {
 			needFull.push_back(pos);
 			return OUT_NEED;
 		    }
 		    usedTie = true;
-		    const auto& order = reference_order(pos, it->second);
+		    const auto& order = reference_order(pos, full[pos]);
 		    for (auto& o : order) {
 			for (auto* p : pass)
 			    if (unsigned(real_id(p->id)) == o.Cls && p->strand == o.Strand) {
@@ -505,27 +526,26 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	if (tied.size() == 1) {
 	    const IcbCand* c = tied[0];
 	    const AlnKey key{pos, c->id, c->strand};
-	    auto ia = aln.find(key);
-	    if (ia == aln.end()) {
+	    const AlnRes* ia = aln_find(pos, c->id, c->strand);
+	    if (!ia) {
 		needPairs.push_back(key);
 		return OUT_NEED;
 	    }
 	    usedAln = true;
 	    alnCalls = 1;
-	    if (double(ia->second) / readLen >= P.aligned_threshold) {	// cluster.cpp:458, 503
+	    if (double(ia->aligned) / readLen >= P.aligned_threshold) {	// cluster.cpp:458, 503
 		outCls = real_id(c->id);
 		outStrand = c->strand;
 		return OUT_JOIN;
 	    }
 	    return OUT_NEW;
 	}
-	auto it = full.find(pos);
-	if (it == full.end()) {
+	if (!have_full[pos]) {
 	    needFull.push_back(pos);
 	    return OUT_NEED;
 	}
 	usedTie = true;
-	const auto& order = reference_order(pos, it->second);
+	const auto& order = reference_order(pos, full[pos]);
 	alnCalls = 0;
 	for (auto& o : order) {
 	    if (int(o.Size) != top) break;  // sorted by Size, descending: the tied candidates come first
@@ -537,13 +557,13 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 		}
 	    if (!c) continue;
 	    const AlnKey key{pos, c->id, c->strand};
-	    auto ia = aln.find(key);
-	    if (ia == aln.end()) {
+	    const AlnRes* ia = aln_find(pos, c->id, c->strand);
+	    if (!ia) {
 		needPairs.push_back(key);
 		return OUT_NEED;
 	    }
 	    alnCalls++;
-	    if (double(ia->second) / readLen >= P.aligned_threshold) {
+	    if (double(ia->aligned) / readLen >= P.aligned_threshold) {
 		usedAln = true;
 		outCls = int(o.Cls);
 		outStrand = o.Strand;
@@ -562,16 +582,27 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	std::vector<AlnKey> np;
 	std::vector<int32_t> nfull;
 	for (int pos = commit_pos; pos < N; pos++) {
-	    int c, s;
-	    np.clear();
-	    nfull.clear();
-	    // a read already evaluated against the same set of founders, and not waiting for device work, cannot
-	    // contribute anything new while reads before it are still pending
-	    if (speculative && eval_version[pos] == version && eval_outcome[pos] != OUT_NEED) continue;
-	    Outcome o = decide(pos, c, s, np, nfull);
-	    stats.decisions++;
-	    eval_version[pos] = version;
-	    eval_outcome[pos] = char(o);
+	    Outcome o;
+	    if (!dirty[pos] && eval_outcome[pos] != OUT_NEED) {
+		// none of this read's provisional candidates changed since its decision was taken: it stands
+		if (speculative) continue;
+		o = Outcome(eval_outcome[pos]);
+	    }
+	    else {
+		int c, s;
+		np.clear();
+		nfull.clear();
+		o = decide(pos, c, s, np, nfull);
+		stats.decisions++;
+		dirty[pos] = 0;
+		eval_outcome[pos] = char(o);
+		Decision& d = dec[pos];
+		d.cls = c;
+		d.strand = s;
+		d.alnCalls = alnCalls;
+		d.usedAln = usedAln;
+		d.usedTie = usedTie;
+	    }
 	    if (o == OUT_NEED) {
 		speculative = true;  // later reads are only scanned for the device work they will need
 		needPairs.insert(needPairs.end(), np.begin(), np.end());
@@ -580,22 +611,23 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    }
 	    if (speculative) continue;
 	    // commit in order
-	    if (usedAln) {
+	    const Decision& d = dec[pos];
+	    if (d.usedAln) {
 		stats.aln_invoked++;
-		stats.aln_calls_ref += alnCalls;
+		stats.aln_calls_ref += d.alnCalls;
 	    }
-	    if (usedTie) stats.tie_fallbacks++;
+	    if (d.usedTie) stats.tie_fallbacks++;
 	    if (o == OUT_NEW) {
 		founder_cls[pos] = nextCls;
-		version++;
+		for (int32_t dep : dependents[pos]) dirty[dep] = 1;
 		founder.push_back(chunk[pos]);
 		cluster_of[slots[pos]] = nextCls;
 		strand_of[slots[pos]] = 1;
 		nextCls++;
 	    }
 	    else {
-		cluster_of[slots[pos]] = c;
-		strand_of[slots[pos]] = s;
+		cluster_of[slots[pos]] = d.cls;
+		strand_of[slots[pos]] = d.strand;
 	    }
 	    committed[pos] = 1;
 	    commit_pos = pos + 1;
@@ -610,8 +642,14 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    for (size_t t = 0; t < needFull.size(); t++) live[t] = hdr[needFull[t]].n_total;
 	    rc = query(chunk, C0, &needFull, 1, 0, &live);
 	    if (rc) return rc;
-	    for (size_t t = 0; t < needFull.size(); t++)
-		full[needFull[t]].assign(h_cands + h_off[t], h_cands + h_off[t] + h_hdr[t].n_cand);
+	    for (size_t t = 0; t < needFull.size(); t++) {
+		const int pos = needFull[t];
+		full[pos].assign(h_cands + h_off[t], h_cands + h_off[t] + h_hdr[t].n_cand);
+		have_full[pos] = 1;
+		// the candidate ORDER depends on every real candidate of the full list, however few hits it has
+		for (auto& c : full[pos])
+		    if (c.id >= C0 && founder_cls[c.id - C0] < 0) dependents[c.id - C0].push_back(pos);
+	    }
 	    stats.ms_full += sw.lap();
 	}
 	if (!needPairs.empty()) {
@@ -638,7 +676,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    if (rc) return rc;
 	    stats.pairs_aligned += int64_t(pairs.size());
 	    for (size_t t = 0; t < needPairs.size(); t++) {
-		aln[needPairs[t]] = res[t].aligned;
+		aln[needPairs[t].pos].push_back(AlnRes{needPairs[t].id, needPairs[t].strand, res[t].aligned});
 		stats.cells_aligned += int64_t(rs->h_offs[pairs[t].read + 1] - rs->h_offs[pairs[t].read]) *
 				       int64_t(rs->h_offs[pairs[t].rep + 1] - rs->h_offs[pairs[t].rep]);
 	    }
@@ -814,6 +852,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
     ICB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (stats) *stats = icb_cluster_stats{};
     if (n_batches == 0) return ICB_OK;
+    Stopwatch wall;
     if (!rs->scored || !rs->sketched) return ctx->fail(ICB_ERR_STATE, "icb_cluster_batches needs scored and sketched reads");
     for (int b = 0; b < n_batches; b++)
 	if (bounds[b] < 0 || bounds[b + 1] < bounds[b]) return ctx->fail(ICB_ERR_ARG, "batch bounds must be non-decreasing");
@@ -846,6 +885,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	int rc = ctx->pool_cl[w] ? clusterer_rebind(ctx->pool_cl[w], rs, params) : clusterer_create_on(c, rs, params, &ctx->pool_cl[w]);
 	if (rc) return ctx->fail(rc, c->last_error);
     }
+    static const bool batch_log = getenv("ICB_BATCH_LOG") != nullptr;
     auto work = [&](int w) {
 	icb_ctx* c = ctx->pool_ctx[w];
 	cudaSetDevice(c->device);
@@ -854,10 +894,21 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	while (!rc) {
 	    const int b = next.fetch_add(1);
 	    if (b >= n_batches || first_err.load()) break;
+	    Stopwatch bw;
 	    rc = cl->reset();
 	    if (rc) break;
 	    rc = icb_cluster_reads(cl, order + bounds[b], bounds[b + 1] - bounds[b], cluster_of + bounds[b], strand_of + bounds[b]);
 	    if (rc) break;
+	    const double bms = bw.lap();
+	    wstats[w].ms_batch_max = std::max(wstats[w].ms_batch_max, bms);
+	    if (batch_log) {
+		const icb_cluster_stats& q = cl->stats;
+		fprintf(stderr, "[icb] batch %d worker %d reads %lld: %.0f ms (query %.0f full %.0f align %.0f insert %.0f host %.0f order %.0f cpu %.0f) "
+				"chunks %lld rounds %lld pairs %lld ties %lld decisions %lld order_calls %lld clusters %zu\n",
+			b, w, (long long)(bounds[b + 1] - bounds[b]), bms, q.ms_query, q.ms_full, q.ms_align, q.ms_insert, q.ms_host, q.ms_order,
+			q.ms_cpu, (long long)q.chunks, (long long)q.rounds, (long long)q.pairs_aligned, (long long)q.tie_fallbacks,
+			(long long)q.decisions, (long long)q.order_calls, cl->founder.size());
+	    }
 	    if (n_clusters) n_clusters[b] = int64_t(cl->founder.size());
 	    const icb_cluster_stats& s = cl->stats;
 	    icb_cluster_stats& t = wstats[w];
@@ -888,9 +939,11 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    stats->ms_full += s.ms_full; stats->ms_align += s.ms_align; stats->ms_insert += s.ms_insert; stats->ms_host += s.ms_host;
 	    stats->ms_cpu += s.ms_cpu; stats->ms_order += s.ms_order; stats->order_calls += s.order_calls;
 	    stats->aln_calls_ref += s.aln_calls_ref;
+	    stats->ms_batch_max = std::max(stats->ms_batch_max, s.ms_batch_max);
 	}
 	icb_ctx_fold_child(ctx, ctx->pool_ctx[w]);  // the worker's kernel timers and launch count -> parent
     }
+    if (stats) stats->ms_wall = wall.lap();
     if (first_err.load()) icb_worker_pool_release(ctx);  // a failed worker's buffers are in an unknown state
     if (first_err.load()) {
 	for (auto& e : werr)
