@@ -21,10 +21,12 @@
 #include <unordered_map>
 
 #include <atomic>
+#include <functional>
 #include <thread>
 
 #include "align.cuh"
 #include "index.cuh"
+#include "helpers.h"
 #include "ref_order.h"
 
 namespace {
@@ -42,6 +44,20 @@ struct AlnKey {
 };
 
 enum Outcome { OUT_JOIN, OUT_NEW, OUT_NEED, OUT_NONE };
+
+// per-thread scratch of the decision function (no allocation in steady state) + what it reports besides the outcome
+struct DecideScratch {
+    std::vector<IcbCand> ro_real, v, cs;
+    std::vector<SortedCand> ro_out;
+    std::vector<const IcbCand*> pass, tied;
+    IcbRefOrderScratch ro;
+    std::vector<AlnKey> needPairs;
+    std::vector<int32_t> needFull;
+    bool usedAln = false, usedTie = false;
+    int alnCalls = 0;  // DP calls the reference makes for the read being decided (getBestClusterAln stops at the first pass)
+    double ms_order = 0;
+    int64_t order_calls = 0, decisions = 0;
+};
 
 double thread_cpu_ms()
 {
@@ -87,7 +103,7 @@ struct icb_clusterer {
     int64_t scratch_words = 0;
     int chunk_cap = 0;
     icb_cluster_stats stats{};
-    IcbRefOrderScratch ro_scratch;
+    std::vector<std::unique_ptr<DecideScratch>> scratch;  // [0] the batch worker itself, [1..] tasks handed to the helper pool
     // pinned host staging (asynchronous copies, no hidden stream synchronisation on pageable memory)
     int32_t* h_i32 = nullptr;	 // 3 * chunk_cap: chunk reads / ids / list
     IcbQueryHeader* h_hdr = nullptr;
@@ -425,39 +441,49 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     auto real_id = [&](int id) { return id < C0 ? id : founder_cls[id - C0]; };
     auto rep_read = [&](int id) { return id < C0 ? founder[id] : chunk[id - C0]; };
 
-    // exact candidate order of the reference for one read, restricted to real clusters (ref_order.h); `all` is the device's
-    // full list, ascending by id — the map provisional id -> real id is monotone, so the order survives it
-    std::vector<IcbCand> ro_real;
-    std::vector<SortedCand> ro_out;
-    std::vector<std::pair<int, std::vector<SortedCand>>> order_cache(N, std::make_pair(-1, std::vector<SortedCand>()));
-    auto reference_order = [&](int pos, const std::vector<IcbCand>& all) -> const std::vector<SortedCand>& {
-	ro_real.clear();
+    // exact candidate order of the reference for one read, restricted to real clusters (ref_order.h) and to the group of
+    // candidates with `target` hits; `all` is the device's full list, ascending by id — the map provisional id -> real id
+    // is monotone, so the order survives it
+    struct OrderSlot {
+	int n_real = -1, target = -1;
+	std::vector<SortedCand> order;
+    };
+    std::vector<OrderSlot> order_cache(N);
+    auto reference_order = [&](DecideScratch& T, int pos, const std::vector<IcbCand>& all, int target) -> const std::vector<SortedCand>& {
+	T.ro_real.clear();
 	for (auto& c : all) {
 	    int rid = real_id(c.id);
 	    if (rid < 0) continue;
-	    ro_real.push_back(c);
-	    ro_real.back().id = rid;
+	    T.ro_real.push_back(c);
+	    T.ro_real.back().id = rid;
 	}
 	// founders are only ever added while a chunk is processed: the same number of real candidates = the same set
-	auto& slot = order_cache[pos];
-	if (slot.first == int(ro_real.size())) return slot.second;
+	OrderSlot& slot = order_cache[pos];
+	if (slot.n_real == int(T.ro_real.size()) && slot.target == target) return slot.order;
 	const int r = chunk[pos];
 	Stopwatch t;
-	icb_reference_order(ro_real.data(), int(ro_real.size()), 20 * (size_t(nf[r]) + size_t(nr[r])), ro_scratch, ro_out);
-	stats.ms_order += t.lap();
-	stats.order_calls++;
-	slot.first = int(ro_real.size());
-	slot.second = ro_out;
-	return slot.second;
+	icb_reference_order_group(T.ro_real.data(), int(T.ro_real.size()), 20 * (size_t(nf[r]) + size_t(nr[r])), uint32_t(target), T.ro,
+				  T.ro_out);
+	T.ms_order += t.lap();
+	T.order_calls++;
+	slot.n_real = int(T.ro_real.size());
+	slot.target = target;
+	slot.order = T.ro_out;
+	return slot.order;
     };
 
     // decision for the read at `pos` given the founders committed so far.  Returns OUT_NEED when device work is
-    // missing (alignment pairs appended to needPairs, tie reads to needFull).
-    bool usedAln = false, usedTie = false;
-    int alnCalls = 0;  // DP calls the reference makes for the read being decided (getBestClusterAln stops at the first pass)
-    std::vector<IcbCand> v, cs;	 // scratch of decide(), reused across calls (no allocation in steady state)
-    std::vector<const IcbCand*> pass, tied;
-    auto decide = [&](int pos, int& outCls, int& outStrand, std::vector<AlnKey>& needPairs, std::vector<int32_t>& needFull) -> Outcome {
+    // missing (alignment pairs appended to T.needPairs, tie reads to T.needFull).  Reads shared state only; writes
+    // T and the read's own order_cache slot, so different reads may be decided concurrently.
+    auto decide = [&](DecideScratch& T, int pos, int& outCls, int& outStrand) -> Outcome {
+	bool& usedAln = T.usedAln;
+	bool& usedTie = T.usedTie;
+	int& alnCalls = T.alnCalls;
+	std::vector<IcbCand>&v = T.v, &cs = T.cs;
+	std::vector<const IcbCand*>&pass = T.pass, &tied = T.tied;
+	std::vector<AlnKey>& needPairs = T.needPairs;
+	std::vector<int32_t>& needFull = T.needFull;
+	T.decisions++;
 	usedAln = usedTie = false;
 	alnCalls = 0;
 	const int r = chunk[pos];
@@ -500,7 +526,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 			return OUT_NEED;
 		    }
 		    usedTie = true;
-		    const auto& order = reference_order(pos, full[pos]);
+		    const auto& order = reference_order(T, pos, full[pos], cs[g].count);
 		    for (auto& o : order) {
 			for (auto* p : pass)
 			    if (unsigned(real_id(p->id)) == o.Cls && p->strand == o.Strand) {
@@ -545,7 +571,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    return OUT_NEED;
 	}
 	usedTie = true;
-	const auto& order = reference_order(pos, full[pos]);
+	const auto& order = reference_order(T, pos, full[pos], top);
 	alnCalls = 0;
 	for (auto& o : order) {
 	    if (int(o.Size) != top) break;  // sorted by Size, descending: the tied candidates come first
@@ -574,43 +600,36 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	return OUT_NEW;
     };
 
+    if (scratch.empty()) scratch.emplace_back(new DecideScratch);
+    IcbHelperPool& pool = IcbHelperPool::get();
+    std::vector<int32_t> todo;
+    // (re)decides the read if one of its provisional candidates was committed since, or if it waited for device work
+    auto evaluate = [&](DecideScratch& T, int pos) -> Outcome {
+	if (!dirty[pos] && eval_outcome[pos] != OUT_NEED) return Outcome(eval_outcome[pos]);
+	int c, s;
+	const Outcome o = decide(T, pos, c, s);
+	dirty[pos] = 0;
+	eval_outcome[pos] = char(o);
+	Decision& d = dec[pos];
+	d.cls = c;
+	d.strand = s;
+	d.alnCalls = T.alnCalls;
+	d.usedAln = T.usedAln;
+	d.usedTie = T.usedTie;
+	return o;
+    };
     while (commit_pos < N) {
 	stats.rounds++;
 	std::vector<AlnKey> needPairs;
 	std::vector<int32_t> needFull;
-	bool speculative = false;
-	std::vector<AlnKey> np;
-	std::vector<int32_t> nfull;
-	for (int pos = commit_pos; pos < N; pos++) {
-	    Outcome o;
-	    if (!dirty[pos] && eval_outcome[pos] != OUT_NEED) {
-		// none of this read's provisional candidates changed since its decision was taken: it stands
-		if (speculative) continue;
-		o = Outcome(eval_outcome[pos]);
-	    }
-	    else {
-		int c, s;
-		np.clear();
-		nfull.clear();
-		o = decide(pos, c, s, np, nfull);
-		stats.decisions++;
-		dirty[pos] = 0;
-		eval_outcome[pos] = char(o);
-		Decision& d = dec[pos];
-		d.cls = c;
-		d.strand = s;
-		d.alnCalls = alnCalls;
-		d.usedAln = usedAln;
-		d.usedTie = usedTie;
-	    }
-	    if (o == OUT_NEED) {
-		speculative = true;  // later reads are only scanned for the device work they will need
-		needPairs.insert(needPairs.end(), np.begin(), np.end());
-		needFull.insert(needFull.end(), nfull.begin(), nfull.end());
-		continue;
-	    }
-	    if (speculative) continue;
-	    // commit in order
+	DecideScratch& T0 = *scratch[0];
+	T0.needPairs.clear();
+	T0.needFull.clear();
+	// ---- in order: commit until the first read that waits for device work
+	int pos = commit_pos;
+	for (; pos < N; pos++) {
+	    const Outcome o = evaluate(T0, pos);
+	    if (o == OUT_NEED) break;
 	    const Decision& d = dec[pos];
 	    if (d.usedAln) {
 		stats.aln_invoked++;
@@ -631,6 +650,47 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    }
 	    committed[pos] = 1;
 	    commit_pos = pos + 1;
+	}
+	// ---- behind the frontier: the set of founders is frozen now; every later read that has to be (re)decided is
+	// evaluated only for the device work it will need — independent of each other, shared with the helper pool
+	if (pos < N) {
+	    todo.clear();
+	    for (int q = pos + 1; q < N; q++)
+		if (dirty[q] || eval_outcome[q] == OUT_NEED) todo.push_back(q);
+	    const int per_task = 6;
+	    int n_tasks = std::min((int(todo.size()) + per_task - 1) / per_task, pool.helpers() + 1);
+	    if (n_tasks <= 1) {
+		for (int32_t q : todo) evaluate(T0, q);
+	    }
+	    else {
+		while (int(scratch.size()) < n_tasks + 1) scratch.emplace_back(new DecideScratch);
+		for (int t = 1; t <= n_tasks; t++) {
+		    scratch[t]->needPairs.clear();
+		    scratch[t]->needFull.clear();
+		}
+		std::atomic<int> cursor(0);
+		const std::function<void(int)> fn = [&](int t) {
+		    DecideScratch& T = *scratch[t + 1];
+		    for (;;) {
+			const int i0 = cursor.fetch_add(per_task);
+			if (i0 >= int(todo.size())) break;
+			const int i1 = std::min(i0 + per_task, int(todo.size()));
+			for (int i = i0; i < i1; i++) evaluate(T, todo[i]);
+		    }
+		};
+		pool.parallel_for(n_tasks, fn);
+	    }
+	}
+	for (auto& T : scratch) {
+	    needPairs.insert(needPairs.end(), T->needPairs.begin(), T->needPairs.end());
+	    needFull.insert(needFull.end(), T->needFull.begin(), T->needFull.end());
+	    T->needPairs.clear();
+	    T->needFull.clear();
+	    stats.ms_order += T->ms_order;
+	    stats.order_calls += T->order_calls;
+	    stats.decisions += T->decisions;
+	    T->ms_order = 0;
+	    T->order_calls = T->decisions = 0;
 	}
 	stats.ms_host += sw.lap();
 	if (commit_pos >= N) break;

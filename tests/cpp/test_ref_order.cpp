@@ -13,8 +13,8 @@ int main()
 {
     std::mt19937 rng(12345);
     IcbRefOrderScratch S;
-    std::vector<IcbSortedCand> got;
-    int bad = 0;
+    std::vector<IcbSortedCand> got, grp;
+    int bad = 0, bad_group = 0;
     for (int it = 0; it < 3000; it++) {
 	const int ncls = 1 + int(rng() % (it % 7 == 0 ? 9000 : 700));
 	const int nf = 1 + int(rng() % 600), nr = 1 + int(rng() % 600);
@@ -42,7 +42,94 @@ int main()
 	    bad++;
 	    if (bad < 5) fprintf(stderr, "case %d differs (n=%zu hint=%zu)\n", it, v.size(), hint);
 	}
+	// the group-only variant: for every count value, the members of that group in the order of `want`
+	for (unsigned target = 1; target <= 6; target++) {
+	    if (it % 3 && target != 6 && target != unsigned(1 + it % 6)) continue;
+	    icb_reference_order_group(v.data(), int(v.size()), hint, target, S, grp);
+	    size_t q = 0;
+	    bool ok = true;
+	    for (auto& w : want)
+		if (w.Size == target) {
+		    ok = ok && q < grp.size() && grp[q].Size == w.Size && grp[q].Cls == w.Cls && grp[q].Strand == w.Strand;
+		    q++;
+		}
+	    ok = ok && q == grp.size();
+	    if (!ok) {
+		bad_group++;
+		if (bad_group < 5) fprintf(stderr, "case %d group %u differs (n=%zu hint=%zu)\n", it, target, v.size(), hint);
+	    }
+	}
     }
-    printf("%s: %d of 3000 cases differ\n", bad ? "FAIL" : "ok", bad);
-    return bad ? 1 : 0;
+    // skewed count distributions (few large values, like real candidate lists), adversarial patterns for the depth budget
+    for (int it = 0; it < 4000; it++) {
+	const int n = 1 + int(rng() % (it % 5 == 0 ? 6000 : 1500));
+	const int nf = 300 + int(rng() % 300), nr = 300 + int(rng() % 300);
+	const size_t hint = size_t(20) * size_t(nf + nr);
+	std::vector<Cand> v;
+	unsigned top = 0;
+	for (int id = 0; v.size() < size_t(n); id++)
+	    for (int s = 0; s < 2; s++)
+		if (rng() % 2) {
+		    int cnt = 1;
+		    if (it % 4 == 3) cnt = 1 + (id % 7 == 0 ? int(rng() % 3) : 0) + (it % 8 == 7 ? id % 50 : 0);
+		    else while (cnt < 9 && rng() % 3 == 0) cnt++;
+		    top = std::max(top, unsigned(cnt));
+		    v.push_back(Cand{id, s ? -1 : 1, cnt, int(rng() % (s ? nr : nf))});
+		}
+	icb_reference_order(v.data(), int(v.size()), hint, S, got);
+	for (unsigned target : {top, top > 1 ? top - 1 : 1u, 1u}) {
+	    icb_reference_order_group(v.data(), int(v.size()), hint, target, S, grp);
+	    size_t q = 0;
+	    bool ok = true;
+	    for (auto& w : got)
+		if (w.Size == target) {
+		    ok = ok && q < grp.size() && grp[q].Cls == w.Cls && grp[q].Strand == w.Strand;
+		    q++;
+		}
+	    ok = ok && q == grp.size();
+	    if (!ok) {
+		bad_group++;
+		if (bad_group < 5) fprintf(stderr, "skewed case %d group %u differs (n=%zu)\n", it, target, v.size());
+	    }
+	}
+    }
+    // Musser's median-of-three killer (drives std::sort into its heap-sort fallback), with and without ties: the pruned
+    // introsort loop against the real std::sort on the same keys
+    for (int it = 0; it < 300; it++) {
+	using namespace icb_introsort;
+	int n = (200 + int(rng() % 3000)) & ~1;
+	std::vector<uint32_t> sz(n);
+	const int h = n / 2;
+	for (int i = 1; i <= h; i++) {
+	    if (i & 1) {
+		sz[i - 1] = i;
+		sz[i] = h + i;
+	    }
+	    sz[h + i - 1] = 2 * i;
+	}
+	const int coarse = 1 + (it % 4 == 0 ? 0 : int(rng() % 8));
+	std::vector<Key> a(n), b;
+	for (int i = 0; i < n; i++) {
+	    uint32_t v = sz[i] / coarse + 1;
+	    if (it & 1) v = n + 2 - v;
+	    a[i] = uint64_t(v) << 32 | uint32_t(i);
+	}
+	b = a;
+	std::sort(b.begin(), b.end(), [](Key x, Key y) { return gt(x, y); });
+	for (int q = 0; q < 4; q++) {
+	    const uint32_t target = q == 0 ? uint32_t(b[0] >> 32) : uint32_t(b[rng() % n] >> 32);
+	    std::vector<Key> c = a;
+	    long lg = 0;
+	    for (size_t v = n; v > 1; v >>= 1) lg++;
+	    loop(c.data(), c.data() + n, 2 * lg, target);
+	    std::vector<uint32_t> g1, g2;
+	    for (auto x : c)
+		if (uint32_t(x >> 32) == target) g1.push_back(uint32_t(x));
+	    for (auto x : b)
+		if (uint32_t(x >> 32) == target) g2.push_back(uint32_t(x));
+	    if (g1 != g2) bad_group++;
+	}
+    }
+    printf("%s: %d of 3000 cases differ, %d group queries differ\n", (bad || bad_group) ? "FAIL" : "ok", bad, bad_group);
+    return (bad || bad_group) ? 1 : 0;
 }
