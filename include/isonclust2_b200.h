@@ -159,6 +159,7 @@ typedef struct {
     int64_t aln_calls_ref; /* DP problems the reference solves for the same reads (getBestClusterAln stops at the first pass) */
     double ms_batch_max;   /* icb_cluster_batches: wall clock of the slowest batch */
     double ms_wall;	   /* icb_cluster_batches: wall clock of the whole call */
+    int64_t hyp_decisions; /* decisions re-taken under predicted founders, only to request device work one round trip earlier */
 } icb_cluster_stats;
 
 typedef struct icb_clusterer icb_clusterer;

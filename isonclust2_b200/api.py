@@ -81,7 +81,7 @@ class ClusterStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("chunks", "rounds", "reads_queried", "aln_invoked", "pairs_aligned", "cells_aligned",
                                          "tie_fallbacks", "decisions")] + \
                [(n, C.c_double) for n in ("ms_query", "ms_full", "ms_align", "ms_insert", "ms_host", "ms_cpu", "ms_order")] + \
-               [("order_calls", C.c_int64), ("aln_calls_ref", C.c_int64), ("ms_batch_max", C.c_double), ("ms_wall", C.c_double)]
+               [("order_calls", C.c_int64), ("aln_calls_ref", C.c_int64), ("ms_batch_max", C.c_double), ("ms_wall", C.c_double), ("hyp_decisions", C.c_int64)]
 
 
 MODES = {"sahlin": 0, "fast": 1, "furious": 2}

@@ -56,7 +56,7 @@ struct DecideScratch {
     bool usedAln = false, usedTie = false;
     int alnCalls = 0;  // DP calls the reference makes for the read being decided (getBestClusterAln stops at the first pass)
     double ms_order = 0;
-    int64_t order_calls = 0, decisions = 0;
+    int64_t order_calls = 0, decisions = 0, hyp_decisions = 0;
 };
 
 double thread_cpu_ms()
@@ -438,28 +438,37 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	for (auto& c : cl[i])
 	    if (c.id >= C0) dependents[c.id - C0].push_back(i);
 
-    auto real_id = [&](int id) { return id < C0 ? id : founder_cls[id - C0]; };
+    // `fmap` below is the map provisional founder -> cluster id a decision is taken under: founder_cls itself (the committed
+    // founders: the decision counts), or founder_hyp (committed + predicted founders: only the device work the decision
+    // would ask for is kept, see the speculative pass of the main loop)
+    std::vector<int> founder_hyp;
+    auto real_id_in = [&](const std::vector<int>& fmap, int id) { return id < C0 ? id : fmap[id - C0]; };
     auto rep_read = [&](int id) { return id < C0 ? founder[id] : chunk[id - C0]; };
 
     // exact candidate order of the reference for one read, restricted to real clusters (ref_order.h) and to the group of
     // candidates with `target` hits; `all` is the device's full list, ascending by id — the map provisional id -> real id
     // is monotone, so the order survives it
     struct OrderSlot {
+	uint64_t set_hash = 0;
 	int n_real = -1, target = -1;
 	std::vector<SortedCand> order;
     };
-    std::vector<OrderSlot> order_cache(N);
-    auto reference_order = [&](DecideScratch& T, int pos, const std::vector<IcbCand>& all, int target) -> const std::vector<SortedCand>& {
+    std::vector<OrderSlot> order_cache(2 * size_t(N));	// per read: [0] under the committed founders, [1] under the predicted ones
+    auto reference_order = [&](DecideScratch& T, const std::vector<int>& fmap, int bank, int pos, const std::vector<IcbCand>& all,
+			       int target) -> const std::vector<SortedCand>& {
 	T.ro_real.clear();
+	uint64_t h = 0x9E3779B97F4A7C15ull;
 	for (auto& c : all) {
-	    int rid = real_id(c.id);
+	    int rid = real_id_in(fmap, c.id);
 	    if (rid < 0) continue;
 	    T.ro_real.push_back(c);
 	    T.ro_real.back().id = rid;
+	    h = (h ^ (uint64_t(uint32_t(c.id)) << 32 | uint32_t(rid))) * 0xD1B54A32D192ED03ull;
+	    h ^= h >> 29;
 	}
-	// founders are only ever added while a chunk is processed: the same number of real candidates = the same set
-	OrderSlot& slot = order_cache[pos];
-	if (slot.n_real == int(T.ro_real.size()) && slot.target == target) return slot.order;
+	// the order is a function of the real candidates (which provisional ones count, and under which id)
+	OrderSlot& slot = order_cache[2 * size_t(pos) + bank];
+	if (slot.n_real == int(T.ro_real.size()) && slot.target == target && slot.set_hash == h) return slot.order;
 	const int r = chunk[pos];
 	Stopwatch t;
 	icb_reference_order_group(T.ro_real.data(), int(T.ro_real.size()), 20 * (size_t(nf[r]) + size_t(nr[r])), uint32_t(target), T.ro,
@@ -467,6 +476,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	T.ms_order += t.lap();
 	T.order_calls++;
 	slot.n_real = int(T.ro_real.size());
+	slot.set_hash = h;
 	slot.target = target;
 	slot.order = T.ro_out;
 	return slot.order;
@@ -475,7 +485,8 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     // decision for the read at `pos` given the founders committed so far.  Returns OUT_NEED when device work is
     // missing (alignment pairs appended to T.needPairs, tie reads to T.needFull).  Reads shared state only; writes
     // T and the read's own order_cache slot, so different reads may be decided concurrently.
-    auto decide = [&](DecideScratch& T, int pos, int& outCls, int& outStrand) -> Outcome {
+    auto decide = [&](DecideScratch& T, const std::vector<int>& fmap, int bank, int pos, int& outCls, int& outStrand) -> Outcome {
+	auto real_id = [&](int id) { return real_id_in(fmap, id); };
 	bool& usedAln = T.usedAln;
 	bool& usedTie = T.usedTie;
 	int& alnCalls = T.alnCalls;
@@ -490,7 +501,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	v.clear();
 	int top = hdr[pos].top_snap;
 	for (auto& c : cl[pos]) {
-	    if (c.id >= C0 && founder_cls[c.id - C0] < 0) continue;  // provisional founder that is no founder (yet)
+	    if (c.id >= C0 && fmap[c.id - C0] < 0) continue;  // provisional founder that is no founder (yet)
 	    v.push_back(c);
 	    top = std::max(top, c.count);
 	}
@@ -526,7 +537,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 			return OUT_NEED;
 		    }
 		    usedTie = true;
-		    const auto& order = reference_order(T, pos, full[pos], cs[g].count);
+		    const auto& order = reference_order(T, fmap, bank, pos, full[pos], cs[g].count);
 		    for (auto& o : order) {
 			for (auto* p : pass)
 			    if (unsigned(real_id(p->id)) == o.Cls && p->strand == o.Strand) {
@@ -571,7 +582,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    return OUT_NEED;
 	}
 	usedTie = true;
-	const auto& order = reference_order(T, pos, full[pos], top);
+	const auto& order = reference_order(T, fmap, bank, pos, full[pos], top);
 	alnCalls = 0;
 	for (auto& o : order) {
 	    if (int(o.Size) != top) break;  // sorted by Size, descending: the tied candidates come first
@@ -603,11 +614,13 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     if (scratch.empty()) scratch.emplace_back(new DecideScratch);
     IcbHelperPool& pool = IcbHelperPool::get();
     std::vector<int32_t> todo;
+    std::vector<char> hyp_mark(N, 0);
+    static const bool speculate_founders = !(getenv("ICB_NO_FOUNDER_SPECULATION"));
     // (re)decides the read if one of its provisional candidates was committed since, or if it waited for device work
     auto evaluate = [&](DecideScratch& T, int pos) -> Outcome {
 	if (!dirty[pos] && eval_outcome[pos] != OUT_NEED) return Outcome(eval_outcome[pos]);
 	int c, s;
-	const Outcome o = decide(T, pos, c, s);
+	const Outcome o = decide(T, founder_cls, 0, pos, c, s);
 	dirty[pos] = 0;
 	eval_outcome[pos] = char(o);
 	Decision& d = dec[pos];
@@ -681,7 +694,50 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 		pool.parallel_for(n_tasks, fn);
 	    }
 	}
+	// ---- one step further: reads behind the frontier that will found a cluster if nothing before them changes are
+	// taken as founders already (with the ids they would get), and every later read that lists one of them is decided
+	// once more under that assumption — only to collect the alignments / full lists it would ask for, so that they are
+	// on the device's to-do list of THIS round trip instead of the one after the founder is committed.  Nothing of these
+	// decisions is kept; results of the requested work are valid whatever happens (they are keyed by provisional id).
+	if (pos < N && speculate_founders) {
+	    founder_hyp = founder_cls;
+	    int hyp_next = nextCls, n_pred = 0;
+	    std::fill(hyp_mark.begin(), hyp_mark.end(), 0);
+	    for (int q = pos + 1; q < N; q++)
+		if (eval_outcome[q] == OUT_NEW) {
+		    founder_hyp[q] = hyp_next++;
+		    n_pred++;
+		    for (int32_t dep : dependents[q]) hyp_mark[dep] = 1;
+		}
+	    todo.clear();
+	    if (n_pred)
+		for (int q = pos + 1; q < N; q++)
+		    if (hyp_mark[q]) todo.push_back(q);
+	    if (!todo.empty()) {
+		const int per_task = 6;
+		const int n_tasks = std::max(1, std::min((int(todo.size()) + per_task - 1) / per_task, pool.helpers() + 1));
+		while (int(scratch.size()) < n_tasks + 1) scratch.emplace_back(new DecideScratch);
+		std::atomic<int> cursor(0);
+		const std::function<void(int)> fn = [&](int t) {
+		    DecideScratch& T = *scratch[t + 1];
+		    for (;;) {
+			const int i0 = cursor.fetch_add(per_task);
+			if (i0 >= int(todo.size())) break;
+			const int i1 = std::min(i0 + per_task, int(todo.size()));
+			for (int i = i0; i < i1; i++) {
+			    int c, s;
+			    decide(T, founder_hyp, 1, todo[i], c, s);
+			    T.decisions--;  // not a decision of the greedy loop
+			    T.hyp_decisions++;
+			}
+		    }
+		};
+		pool.parallel_for(n_tasks, fn);
+	    }
+	}
 	for (auto& T : scratch) {
+	    stats.hyp_decisions += T->hyp_decisions;
+	    T->hyp_decisions = 0;
 	    needPairs.insert(needPairs.end(), T->needPairs.begin(), T->needPairs.end());
 	    needFull.insert(needFull.end(), T->needFull.begin(), T->needFull.end());
 	    T->needPairs.clear();
@@ -976,7 +1032,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    t.pairs_aligned += s.pairs_aligned; t.cells_aligned += s.cells_aligned; t.tie_fallbacks += s.tie_fallbacks;
 	    t.decisions += s.decisions; t.ms_query += s.ms_query; t.ms_full += s.ms_full; t.ms_align += s.ms_align;
 	    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host; t.ms_cpu += s.ms_cpu; t.ms_order += s.ms_order; t.order_calls += s.order_calls;
-		t.aln_calls_ref += s.aln_calls_ref;
+		t.aln_calls_ref += s.aln_calls_ref; t.hyp_decisions += s.hyp_decisions;
 	}
 	if (rc) {
 	    int z = 0;
@@ -999,6 +1055,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	    stats->ms_full += s.ms_full; stats->ms_align += s.ms_align; stats->ms_insert += s.ms_insert; stats->ms_host += s.ms_host;
 	    stats->ms_cpu += s.ms_cpu; stats->ms_order += s.ms_order; stats->order_calls += s.order_calls;
 	    stats->aln_calls_ref += s.aln_calls_ref;
+	    stats->hyp_decisions += s.hyp_decisions;
 	    stats->ms_batch_max = std::max(stats->ms_batch_max, s.ms_batch_max);
 	}
 	icb_ctx_fold_child(ctx, ctx->pool_ctx[w]);  // the worker's kernel timers and launch count -> parent

@@ -35,7 +35,7 @@ for cs in sweep:
     print(f"chunk={cs:5d}  {min(ts):7.3f} s  {n / min(ts):9.0f} reads/s  same_result={same} chunks={st['chunks']} rounds={st['rounds']} "
           f"pairs={st['pairs_aligned']} per-batch ms: query={st['ms_query'] / nb:.0f} full={st['ms_full'] / nb:.0f} align={st['ms_align'] / nb:.0f} "
           f"insert={st['ms_insert'] / nb:.0f} host={st['ms_host'] / nb:.0f} order={st['ms_order'] / nb:.0f} cpu={st['ms_cpu'] / nb:.0f} "
-          f"decisions={st['decisions']} order_calls={st['order_calls']} slowest_batch={st['ms_batch_max']:.0f} cluster_wall={st['ms_wall']:.0f} "
+          f"decisions={st["decisions"]} hyp={st["hyp_decisions"]} order_calls={st['order_calls']} slowest_batch={st['ms_batch_max']:.0f} cluster_wall={st['ms_wall']:.0f} "
           f"phases={ {k: round(v) for k, v in res['phases_ms'].items()} }", flush=True)
 rs.close()
 ctx.close()
