@@ -147,7 +147,7 @@ def run_ours(args):
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
-        api.run_pipeline(ctx, seq, qual, offs, **pipe)
+        res_e2e = api.run_pipeline(ctx, seq, qual, offs, **pipe)
         ctx.sync()
         barrier()
         e2e_times.append((time.perf_counter() - t0) * 1e3)
@@ -182,7 +182,9 @@ def run_ours(args):
                    "clusters": int(sum(res["n_clusters"])), "reads_clustered": clustered,
                    "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"reads sharded x{world}, no collective"},
         "e2e": {"value": world * n_reads / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": 2 * n_bases + 8 * (n_reads + 1) + n_reads, "d2h_bytes_per_step": 16 * n_reads + 24 * n_reads},
+                "h2d_bytes_per_step": 2 * n_bases + 8 * (n_reads + 1) + n_reads, "d2h_bytes_per_step": 16 * n_reads + 24 * n_reads,
+                "phases_ms_last_step": {k: round(v, 1) for k, v in res_e2e["phases_ms"].items()}},
+        "phases_ms_last_step": {k: round(v, 1) for k, v in res["phases_ms"].items()},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "icb_k_sketch (sketch_reads)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,

@@ -847,7 +847,7 @@ int icb_readset_prepare_host(icb_readset* rs)
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_score.data(), rs->d_score, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_err.data(), rs->d_err, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     }
-    if (!rs->d_class) ICB_CUDA(ctx, cudaMalloc((void**)&rs->d_class, n + 16));
+    if (!rs->d_class) ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&rs->d_class, n + 16));
     int rc0 = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, rs->d_class);
     if (rc0) return rc0;
     ICB_CUDA(ctx, ctx->wait());

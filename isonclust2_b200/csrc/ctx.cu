@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
 
 #include "align.cuh"
@@ -185,6 +186,11 @@ void icb_ctx_destroy(icb_ctx* ctx)
     }
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
+    {
+	// hand the memory the pool cached for this context's read sets and workers back to the device
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     delete ctx;
 }
 
@@ -277,7 +283,7 @@ int icb_readset_create(icb_ctx* ctx, const char* seq, const char* qual, const in
     int64_t nb = rs->n_bases;
     cudaError_t e;
 #define RS_ALLOC(ptr, bytes)                                           \
-    if ((e = cudaMalloc((void**)&(ptr), (size_t)(bytes))) != cudaSuccess) { \
+    if ((e = icb_dmalloc(ctx, (void**)&(ptr), (size_t)(bytes))) != cudaSuccess) { \
 	icb_readset_destroy(rs);                                       \
 	return ctx->fail_cuda(e, "cudaMalloc " #ptr, __FILE__, __LINE__);  \
     }
@@ -305,24 +311,14 @@ void icb_readset_destroy(icb_readset* rs)
     if (!rs) return;
     cudaSetDevice(rs->ctx->device);
     cudaStreamSynchronize(rs->ctx->stream);
-    cudaFree(rs->d_seq);
-    cudaFree(rs->d_qual);
-    cudaFree(rs->d_offs);
-    cudaFree(rs->d_score);
-    cudaFree(rs->d_err);
-    cudaFree(rs->d_status);
-    cudaFree(rs->d_hpc_len);
-    cudaFree(rs->d_hpc_err);
-    cudaFree(rs->d_hpc_seq);
-    cudaFree(rs->d_hpc_qual);
-    cudaFree(rs->d_mins);
-    cudaFree(rs->d_min_off);
-    cudaFree(rs->d_nf);
-    cudaFree(rs->d_nr);
-    cudaFree(rs->d_counters);
-    cudaFree(rs->d_long_list);
-    cudaFree(rs->d_long_scratch);
-    cudaFree(rs->d_class);
+    // stream-ordered frees (the device pool keeps the memory for the next read set: a pipeline that uploads one read set
+    // after the other pays the driver's map / unmap of gigabytes only once)
+    icb_ctx* ctx = rs->ctx;
+    for (void* q : {(void*)rs->d_seq, (void*)rs->d_qual, (void*)rs->d_offs, (void*)rs->d_score, (void*)rs->d_err, (void*)rs->d_status,
+		    (void*)rs->d_hpc_len, (void*)rs->d_hpc_err, (void*)rs->d_hpc_seq, (void*)rs->d_hpc_qual, (void*)rs->d_mins,
+		    (void*)rs->d_min_off, (void*)rs->d_nf, (void*)rs->d_nr, (void*)rs->d_counters, (void*)rs->d_long_list,
+		    (void*)rs->d_long_scratch, (void*)rs->d_class})
+	icb_dfree(ctx, q);
     delete rs;
 }
 

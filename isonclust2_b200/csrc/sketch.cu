@@ -907,7 +907,7 @@ int icb_launch_sketch(icb_readset* rs, int k, int w, const uint8_t* d_skip)
 	int64_t lmaxL = (rs->max_len + 63) & ~int64_t(31);
 	int64_t stride = (int64_t(per_read_bytes<uint32_t>(lmaxL)) + 255) & ~int64_t(255);
 	if (!rs->d_long_scratch) {
-	    cudaError_t e = cudaMalloc((void**)&rs->d_long_scratch, size_t(stride) * nblk);
+	    cudaError_t e = icb_dmalloc(ctx, (void**)&rs->d_long_scratch, size_t(stride) * nblk);
 	    if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaMalloc long scratch", __FILE__, __LINE__);
 	}
 	a.long_scratch = rs->d_long_scratch;
@@ -933,7 +933,7 @@ int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const doub
     const int64_t n = rs->n_reads, nb = rs->n_bases;
     cudaError_t e;
 #define SK_ALLOC(ptr, bytes)                                              \
-    if (!(ptr) && (e = cudaMalloc((void**)&(ptr), (size_t)(bytes))) != cudaSuccess) \
+    if (!(ptr) && (e = icb_dmalloc(ctx, (void**)&(ptr), (size_t)(bytes))) != cudaSuccess) \
 	return ctx->fail_cuda(e, "cudaMalloc " #ptr, __FILE__, __LINE__);
     SK_ALLOC(rs->d_status, sizeof(int32_t) * (n + 1));
     SK_ALLOC(rs->d_hpc_len, sizeof(int32_t) * (n + 1));
@@ -955,10 +955,10 @@ int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const doub
     if (want > 2 * nb + 1024) want = 2 * nb + 1024;
     for (int attempt = 0; attempt < 2; attempt++) {
 	if (rs->mins_capacity < want) {
-	    cudaFree(rs->d_mins);
+	    icb_dfree(ctx, rs->d_mins);
 	    rs->d_mins = nullptr;
 	    rs->mins_capacity = 0;
-	    if ((e = cudaMalloc((void**)&rs->d_mins, sizeof(icb_minimizer) * size_t(want))) != cudaSuccess)
+	    if ((e = icb_dmalloc(ctx, (void**)&rs->d_mins, sizeof(icb_minimizer) * size_t(want))) != cudaSuccess)
 		return ctx->fail_cuda(e, "cudaMalloc minimizer arena", __FILE__, __LINE__);
 	    rs->mins_capacity = want;
 	}
