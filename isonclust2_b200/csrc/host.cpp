@@ -5,9 +5,26 @@
 #include <cmath>
 #include <cstdint>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "isonclust2_b200.h"
+
+namespace {
+// fn(a, b) over [0, n) in pieces of at least `grain`, on up to 16 host threads
+template <class F>
+void parallel_ranges(int64_t n, int64_t grain, F fn)
+{
+    const int T = int(std::min<int64_t>(std::min<int64_t>(16, std::max(1u, std::thread::hardware_concurrency())), (n + grain - 1) / grain));
+    if (T <= 1) {
+	fn(0, n);
+	return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back([=] { fn(n * t / T, n * (t + 1) / T); });
+    for (auto& x : th) x.join();
+}
+}  // namespace
 
 extern "C" {
 
@@ -26,16 +43,47 @@ void icb_init_qual_tab(double tab[129], int nomin)
 int icb_quality_filter(const double* err, int64_t n, double min_qual, uint8_t* filtered)
 {
     if (n < 0 || (n > 0 && (!err || !filtered))) return ICB_ERR_ARG;
-    for (int64_t i = 0; i < n; i++) filtered[i] = ((-10 * std::log10(err[i])) <= min_qual) ? 1 : 0;
+    parallel_ranges(n, 1 << 16, [&](int64_t a, int64_t b) {
+	for (int64_t i = a; i < b; i++) filtered[i] = ((-10 * std::log10(err[i])) <= min_qual) ? 1 : 0;
+    });
     return ICB_OK;
 }
 
-// SortByQualScores (qualscore.cpp:138-145): std::stable_sort, a before b iff score(a) > score(b)
+// SortByQualScores (qualscore.cpp:138-145): std::stable_sort, a before b iff score(a) > score(b).  The stable order by a
+// strict weak ordering is unique — (score descending, index ascending) — so sorted runs merged stably give the same
+// permutation as one std::stable_sort; with a NaN among the scores the comparator is no strict weak ordering and the
+// single library call is kept.
 int icb_sort_by_score(const double* score, int64_t n, int32_t* order)
 {
     if (n < 0 || n > 0x7fffffff || (n > 0 && (!score || !order))) return ICB_ERR_ARG;
     std::iota(order, order + n, 0);
-    std::stable_sort(order, order + n, [score](int32_t a, int32_t b) { return score[a] > score[b]; });
+    auto cmp = [score](int32_t a, int32_t b) { return score[a] > score[b]; };
+    bool nan = false;
+    for (int64_t i = 0; i < n; i++) nan |= score[i] != score[i];
+    const int T = nan || n < (1 << 16) ? 1 : std::min<int>(16, std::max(1u, std::thread::hardware_concurrency()));
+    if (T <= 1) {
+	std::stable_sort(order, order + n, cmp);
+	return ICB_OK;
+    }
+    std::vector<int64_t> cut(T + 1);
+    for (int t = 0; t <= T; t++) cut[t] = n * t / T;
+    {
+	std::vector<std::thread> th;
+	for (int t = 0; t < T; t++) th.emplace_back([&, t] { std::stable_sort(order + cut[t], order + cut[t + 1], cmp); });
+	for (auto& x : th) x.join();
+    }
+    std::vector<int32_t> tmp(static_cast<size_t>(n));
+    int32_t *src = order, *dst = tmp.data();
+    for (int width = 1; width < T; width *= 2) {
+	std::vector<std::thread> th;
+	for (int t = 0; t < T; t += 2 * width) {
+	    const int64_t a = cut[t], m = cut[std::min(t + width, T)], b = cut[std::min(t + 2 * width, T)];
+	    th.emplace_back([=] { std::merge(src + a, src + m, src + m, src + b, dst + a, cmp); });  // ties: the left run first
+	}
+	for (auto& x : th) x.join();
+	std::swap(src, dst);
+    }
+    if (src != order) std::copy(src, src + n, order);
     return ICB_OK;
 }
 
