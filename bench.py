@@ -70,7 +70,38 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def sketch_traffic_ratio():
+    """DRAM bytes per algorithmic byte of the sketch kernel, from the committed `ncu --set full` capture (newest
+    profiles/*_sketch_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch over that launch's algorithmic
+    bytes).  bench.py never runs under a profiler itself; the ratio is applied to this run's algorithmic bytes."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_sketch_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        return float(json.load(open(files[-1]))["dram_bytes_per_algorithmic_byte"]), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
+def cpu_share():
+    """Host cores this rank may count on: the process's affinity mask split evenly over the ranks of this node."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    return max(2, cores // max(local_world, 1)), cores
+
+
 def run_ours(args):
+    share, cores = cpu_share()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # N ranks share the node's cores: size this rank's batch workers and helper pool for its share (library defaults
+        # assume the whole machine: 3 workers per core, one helper per core)
+        os.environ.setdefault("ICB_HELPERS", str(min(16, share)))
+        if args.workers == 0:
+            args.workers = min(48, max(8, 3 * share))
     import torch
     import torch.distributed as dist
 
@@ -168,6 +199,7 @@ def run_ours(args):
     k_ms = tot_ms / max(n_l, 1)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    t_ratio, t_src = sketch_traffic_ratio()
     st = res["stats"]
     dp_ms = kt["align_dp"][1] / steps
     gcups = st["cells_aligned"] / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else 0.0
@@ -180,15 +212,15 @@ def run_ours(args):
         "config": {**workload_config(n_reads, args.batch_max_seq),
                    "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "batches": len(res["batches"]),
                    "clusters": int(sum(res["n_clusters"])), "reads_clustered": clustered,
-                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"reads sharded x{world}, no collective"},
+                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"reads sharded x{world}, no collective", "host_cores": cores, "host_cores_per_rank": share},
         "e2e": {"value": world * n_reads / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": 2 * n_bases + 8 * (n_reads + 1) + n_reads, "d2h_bytes_per_step": 16 * n_reads + 24 * n_reads,
                 "phases_ms_last_step": {k: round(v, 1) for k, v in res_e2e["phases_ms"].items()}},
         "phases_ms_last_step": {k: round(v, 1) for k, v in res["phases_ms"].items()},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "icb_k_sketch (sketch_reads)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel_ms": k_ms},
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": int(t_ratio * alg_bytes) if t_ratio else None,
+                     "traffic_source": t_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms},
         "alignment": {"gcups": gcups, "cells_per_step": st["cells_aligned"], "pairs_per_step": st["pairs_aligned"],
                       "aln_invoked": st["aln_invoked"], "dp_ms_per_step": dp_ms},
         "cluster_stats": st,

@@ -176,6 +176,13 @@ int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_
  * (AddMinimizers, minimizer.cpp:31-42).  A merge is then icb_cluster_reads over the right batch's representatives in
  * the right batch's cluster order. */
 int icb_clusterer_seed(icb_clusterer* cl, const int32_t* rep_reads, int64_t n);
+/* UpdateMinDB (minimizer.cpp:124-160) together with the representative swap the reference does around it after a
+ * consensus update (cluster.cpp:279-291): cluster `cluster` is represented by read `rep_read` of the read set from now on.
+ * The cluster leaves the posting list of every forward minimizer value only the old representative had and joins the list of
+ * every value only the new one has; mapping and alignment tests of later icb_cluster_reads calls use the new representative's
+ * compressed length, error rate and sequence.  The host that keeps the spoa consensus appends the consensus sequence to the
+ * read set it uploads (it is sketched like any read) and names it here. */
+int icb_clusterer_update_representative(icb_clusterer* cl, int32_t cluster, int32_t rep_read);
 int64_t icb_clusterer_n_clusters(const icb_clusterer* cl);
 int icb_clusterer_founders(const icb_clusterer* cl, int32_t* founder_read);
 int icb_clusterer_stats(const icb_clusterer* cl, icb_cluster_stats* stats);

@@ -142,6 +142,11 @@ class Clusterer:
         rep = np.ascontiguousarray(rep_reads, dtype=np.int32)
         c.check(c.L.icb_clusterer_seed(self.h, rep.ctypes.data, len(rep)))
 
+    def update_representative(self, cluster, rep_read):
+        """UpdateMinDB (minimizer.cpp:124-160): read `rep_read` represents `cluster` from now on."""
+        c = self.rs.ctx
+        c.check(c.L.icb_clusterer_update_representative(self.h, int(cluster), int(rep_read)))
+
     def cluster(self, order):
         c = self.rs.ctx
         order = np.ascontiguousarray(order, dtype=np.int32)

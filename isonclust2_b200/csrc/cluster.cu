@@ -115,6 +115,7 @@ struct icb_clusterer {
     void free_buffers();
     int reset();
     int seed(const int32_t* rep_reads, int64_t n);
+    int update_representative(int32_t cluster, int32_t rep_read);
 
     int ensure_scratch(int64_t words);
     int ensure_cands(int64_t n);
@@ -326,6 +327,29 @@ int icb_clusterer::seed(const int32_t* rep_reads, int64_t n)
 	ICB_CUDA(ctx, ctx->wait());
     }
     main_idx.nodes_upper += tot;
+    return ICB_OK;
+}
+
+// UpdateMinDB (minimizer.cpp:124-160) + the representative swap around it (cluster.cpp:279-291): from now on cluster
+// `cluster` is represented by read `rep_read` — its forward sketch in the index, its compressed length / error class in
+// the mapping test, its sequence in the alignment test.
+int icb_clusterer::update_representative(int32_t cluster, int32_t rep_read)
+{
+    if (cluster < 0 || size_t(cluster) >= founder.size()) return ctx->fail(ICB_ERR_ARG, "update_representative: no such cluster");
+    if (rep_read < 0 || rep_read >= rs->n_reads || rs->h_status[rep_read] != 1)
+	return ctx->fail(ICB_ERR_ARG, "update_representative: representative is not a sketched read");
+    const int32_t old = founder[cluster];
+    if (old == rep_read) return ICB_OK;
+    int rc = main_idx.reserve(rs->h_nf[rep_read]);
+    if (rc) return rc;
+    rc = icb_index_update(ctx, main_idx, rs, old, rep_read, cluster, rs->h_nf[old], rs->h_nf[rep_read]);
+    if (rc) return rc;
+    main_idx.nodes_upper += rs->h_nf[rep_read];
+    founder[cluster] = rep_read;
+    int32_t* stage = h_i32 + 2 * chunk_cap;
+    stage[0] = rep_read;
+    ICB_CUDA(ctx, cudaMemcpyAsync(d_cls_founder + cluster, stage, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    ICB_CUDA(ctx, ctx->wait());
     return ICB_OK;
 }
 
@@ -957,6 +981,13 @@ int icb_clusterer_seed(icb_clusterer* cl, const int32_t* rep_reads, int64_t n)
     if (!cl || n < 0 || (n > 0 && !rep_reads)) return ICB_ERR_ARG;
     ICB_CUDA(cl->ctx, cudaSetDevice(cl->ctx->device));
     return cl->seed(rep_reads, n);
+}
+
+int icb_clusterer_update_representative(icb_clusterer* cl, int32_t cluster, int32_t rep_read)
+{
+    if (!cl) return ICB_ERR_ARG;
+    ICB_CUDA(cl->ctx, cudaSetDevice(cl->ctx->device));
+    return cl->update_representative(cluster, rep_read);
 }
 
 int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,

@@ -23,6 +23,7 @@ namespace {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t NIL = 0xFFFFFFFFu;
+constexpr uint32_t DEAD = 0xFFFFFFFFu;	// posting node whose cluster left the list (UpdateMinDB's erase)
 constexpr int Q_THREADS = 128;
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x)
@@ -66,7 +67,7 @@ __device__ __forceinline__ void for_each_posting(const IcbIndexView& ix, uint32_
     uint32_t n = ix.heads[s];
     while (n != NIL) {
 	uint2 nd = ix.nodes[n];
-	f(nd.x);
+	if (nd.x != DEAD) f(nd.x);
 	n = nd.y;
     }
 }
@@ -117,6 +118,55 @@ icb_k_index_insert(IcbIndexView ix, const icb_minimizer* __restrict__ arena, con
 	    ix.nodes[nid] = make_uint2(id, old);
 	}
 	__syncthreads();
+    }
+}
+
+// UpdateMinDB (reference minimizer.cpp:124-160) for one cluster whose representative changed from read `r_old` to
+// read `r_new` (the reference calls it after a consensus update, cluster.cpp:287-291): with oldSet / newSet the distinct
+// FORWARD minimizer values of the two sketches, `cls` leaves the posting list of every value in oldSet \ newSet and joins
+// the list of every value in newSet \ oldSet.  Posting order is irrelevant here: the query only counts per cluster, and
+// the reference keeps its lists sorted (std::set round trip / std::sort), i.e. order carries no information there either.
+// Emptied lists stay as keys, as in the reference (the erase is commented out, minimizer.cpp:150-152).
+// One CTA; both value lists are staged in shared memory (dynamic: nf[r_old] + nf[r_new] words).
+__global__ void __launch_bounds__(Q_THREADS)
+icb_k_index_update(IcbIndexView ix, const icb_minimizer* __restrict__ arena, const int64_t* __restrict__ min_off,
+		   const int32_t* __restrict__ nf, int r_old, int r_new, uint32_t cls)
+{
+    extern __shared__ uint32_t s_vals[];
+    const int Mo = nf[r_old], Mn = nf[r_new];
+    uint32_t* vo = s_vals;
+    uint32_t* vn = s_vals + Mo;
+    const icb_minimizer* mo = arena + min_off[r_old];
+    const icb_minimizer* mn = arena + min_off[r_new];
+    for (int i = threadIdx.x; i < Mo; i += Q_THREADS) vo[i] = mo[i].Min;
+    for (int i = threadIdx.x; i < Mn; i += Q_THREADS) vn[i] = mn[i].Min;
+    __syncthreads();
+    // toDel = oldSet \ newSet: first occurrence of each old value that the new sketch does not hold
+    for (int i = threadIdx.x; i < Mo; i += Q_THREADS) {
+	const uint32_t v = vo[i];
+	bool act = true;
+	for (int j = 0; j < i && act; j++) act = vo[j] != v;
+	for (int j = 0; j < Mn && act; j++) act = vn[j] != v;
+	if (!act) continue;
+	const uint32_t s = find_slot(ix, v);
+	if (s == NIL) continue;
+	for (uint32_t n = ix.heads[s]; n != NIL;) {
+	    const uint2 nd = ix.nodes[n];
+	    if (nd.x == cls) ix.nodes[n].x = DEAD;  // every copy: tmp.erase(best) on a set
+	    n = nd.y;
+	}
+    }
+    // toIns = newSet \ oldSet
+    for (int i = threadIdx.x; i < Mn; i += Q_THREADS) {
+	const uint32_t v = vn[i];
+	bool act = true;
+	for (int j = 0; j < i && act; j++) act = vn[j] != v;
+	for (int j = 0; j < Mo && act; j++) act = vo[j] != v;
+	if (!act) continue;
+	const uint32_t nid = atomicAdd(ix.node_count, 1u);
+	const uint32_t s = claim_slot(ix, v);
+	const uint32_t old = atomicExch(&ix.heads[s], nid);
+	ix.nodes[nid] = make_uint2(cls, old);
     }
 }
 
@@ -439,6 +489,21 @@ int icb_index_insert(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, const i
     if (n <= 0) return ICB_OK;
     ICB_LAUNCH(ctx, "index_insert",
 	       icb_k_index_insert<<<n, Q_THREADS, 0, ctx->stream>>>(idx.v, rs->d_mins, rs->d_min_off, rs->d_nf, d_reads, d_ids, n));
+    return ICB_OK;
+}
+
+int icb_index_update(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, int r_old, int r_new, int cls, int nf_old, int nf_new)
+{
+    const size_t smem = sizeof(uint32_t) * size_t(nf_old + nf_new);
+    if (smem > 48 * 1024) {
+	static std::once_flag once;
+	static cudaError_t once_err = cudaSuccess;
+	std::call_once(once, [] { once_err = cudaFuncSetAttribute(icb_k_index_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+	ICB_CUDA(ctx, once_err);
+	if (smem > 200 * 1024) return ctx->fail(ICB_ERR_NOMEM, "index update: sketches too large for one CTA");
+    }
+    ICB_LAUNCH(ctx, "index_update",
+	       icb_k_index_update<<<1, Q_THREADS, smem, ctx->stream>>>(idx.v, rs->d_mins, rs->d_min_off, rs->d_nf, r_old, r_new, uint32_t(cls)));
     return ICB_OK;
 }
 

@@ -7,7 +7,8 @@
 //   heads[slot] newest node of the chain (NIL = 0xFFFFFFFF)
 //   nodes[i]    {id, next}; id = cluster id (main index) or C0 + position in the chunk (chunk index)
 // Append-only, like the reference's MinimizerDB without consensus (AddMinimizers, minimizer.cpp:31-42):
-// one (value, cluster) pair per distinct minimizer value of the founder's FORWARD sketch.
+// one (value, cluster) pair per distinct minimizer value of the founder's FORWARD sketch.  UpdateMinDB
+// (minimizer.cpp:124-160) marks the nodes of a cluster that left a list dead (id = 0xFFFFFFFF) and appends new ones.
 struct IcbIndexView {
     uint32_t* keys;
     uint32_t* heads;
@@ -78,5 +79,6 @@ struct IcbQueryArgs {
 };
 
 int icb_index_insert(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, const int32_t* d_reads, const int32_t* d_ids, int n);
+int icb_index_update(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, int r_old, int r_new, int cls, int nf_old, int nf_new);
 int icb_query_launch(icb_ctx* ctx, const IcbQueryArgs& a, int n_blocks, size_t smem_bytes);
 int icb_classify_errors(icb_ctx* ctx, const double* d_err, const int32_t* d_status, int64_t n, uint8_t* d_class);

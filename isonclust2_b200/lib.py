@@ -74,6 +74,7 @@ def load():
     L.icb_clusterer_founders.argtypes = [_p, _p]
     L.icb_clusterer_stats.argtypes = [_p, _p]
     L.icb_clusterer_seed.argtypes = [_p, _p, _i64]
+    L.icb_clusterer_update_representative.argtypes = [_p, C.c_int32, C.c_int32]
     L.icb_cluster_batches.argtypes = [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]
     L.icb_init_qual_tab.argtypes = [_p, _i32]
     L.icb_init_qual_tab.restype = None

@@ -43,6 +43,18 @@ class Reads(C.Structure):
                 ("raw_offs", _p), ("hpc_len", _p), ("mins", _p), ("min_offs", _p), ("rev_mins", _p), ("rev_offs", _p)]
 
 
+def _mindb_after_updates(fn, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs):
+    """AddMinimizers for the clusters, then UpdateMinDB per update; returns (keys sorted, offs, cls)."""
+    cm = np.ascontiguousarray(cls_mins, MIN_DT); co = np.ascontiguousarray(cls_offs, np.int64)
+    uc = np.ascontiguousarray(upd_cls, np.int32); um = np.ascontiguousarray(upd_mins, MIN_DT)
+    uo = np.ascontiguousarray(upd_offs, np.int64)
+    cap = len(cm) + len(um) + 1
+    keys, offs, cls = np.zeros(cap, np.uint32), np.zeros(cap + 1, np.int64), np.zeros(cap, np.uint32)
+    n = fn(_ptr(cm), _ptr(co), len(co) - 1, _ptr(uc), _ptr(um), _ptr(uo), len(uc), _ptr(keys), _ptr(offs), _ptr(cls), cap, cap)
+    assert n >= 0, n
+    return keys[:n].copy(), offs[:n + 1].copy(), cls[:offs[n]].copy()
+
+
 class Port:
     """The C restatement."""
 
@@ -83,6 +95,8 @@ class Port:
         L.orc_aligned_windows.argtypes = [_p, _i64, _dbl, _i32]
         L.orc_cluster_reads.restype = _i64
         L.orc_cluster_reads.argtypes = [_p, _p, _p, _p, _p, _p]
+        L.orc_mindb_after_updates.restype = _i64
+        L.orc_mindb_after_updates.argtypes = [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _i64, _i64]
         self.tab = np.zeros(129)
         self.tab_nomin = np.zeros(129)
         L.orc_init_qualtab(_ptr(self.tab), 0)
@@ -194,6 +208,9 @@ class Port:
         return dict(aligned=al, score=score.value, end_query=eq.value, end_ref=er.value, comp_len=cl.value,
                     comp=comp[:cl.value].tobytes() if want_comp else None)
 
+    def mindb_after_updates(self, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs):
+        return _mindb_after_updates(self.L.orc_mindb_after_updates, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs)
+
     def cluster(self, seq, offs, sk, score, raw_err, order, k, w, mode, p_shared, min_shared=5, mapped_th=0.65,
                 aligned_th=0.2, min_frac=0.8, min_prob_no_hits=0.1, min_qual=7.0, status=None):
         """Greedy clustering of reads given in SORTED order `order` (indices into the flat read set).
@@ -283,6 +300,8 @@ class Ref:
         L.ref_load_batch.argtypes = [C.c_char_p]
         L.ref_sorted_hits.restype = _i32
         L.ref_sorted_hits.argtypes = [_p, _p, _i32, _p, _i32, _p, _i32, _p]
+        L.ref_mindb_after_updates.restype = _i64
+        L.ref_mindb_after_updates.argtypes = [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _i64, _i64]
 
     def qualtabs(self):
         a, b = np.zeros(129), np.zeros(129)
@@ -354,6 +373,9 @@ class Ref:
         offs = np.ascontiguousarray(offs, np.int64)
         return RefBatch(self, self.L.ref_sort_and_sketch(_ptr(seq), _ptr(qual), _ptr(offs), len(offs) - 1, k, w, min_qual,
                                                           1 if sketch else 0), len(offs) - 1)
+
+    def mindb_after_updates(self, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs):
+        return _mindb_after_updates(self.L.ref_mindb_after_updates, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs)
 
     def sorted_hits(self, cls_mins, cls_offs, mins, rev_mins):
         cm = np.ascontiguousarray(cls_mins); co = np.ascontiguousarray(cls_offs, np.int64)

@@ -91,6 +91,12 @@ typedef struct {
 int64_t orc_cluster_reads(const orc_cluster_params* P, const orc_reads* R, int32_t* out_cluster, int32_t* out_strand,
 			  int32_t* out_founder, int64_t* n_aligned);
 
+/* a12: UpdateMinDB (minimizer.cpp:124-160) applied to a MinDB built by AddMinimizers; export sorted by key.
+ * Returns the number of keys, or -1 - needed if a capacity is too small. */
+int64_t orc_mindb_after_updates(const orc_minimizer* cls_mins, const int64_t* cls_offs, int n_cls, const int32_t* upd_cls,
+				const orc_minimizer* upd_mins, const int64_t* upd_offs, int n_upd, uint32_t* keys, int64_t* offs,
+				uint32_t* cls, int64_t key_cap, int64_t cls_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <iterator>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -167,4 +168,66 @@ extern "C" int64_t orc_cluster_reads(const orc_cluster_params* P, const orc_read
     for (size_t c = 0; c < founder.size(); c++) out_founder[c] = founder[c];
     if (n_aligned) *n_aligned = aligned_calls;
     return int64_t(founder.size());
+}
+
+// a12 — UpdateMinDB (minimizer.cpp:124-160) restated on the flat MinDB above, driven like
+// ref_mindb_after_updates of oracle/ref_shim.cpp: AddMinimizers (minimizer.cpp:31-42) for nCls founders, then update u
+// replaces the minimizers of cluster upd_cls[u] (its current ones are the "old" set).  Export sorted by key, empty
+// posting lists included (the reference does not erase emptied keys, minimizer.cpp:150-152).
+extern "C" int64_t orc_mindb_after_updates(const orc_minimizer* cls_mins, const int64_t* cls_offs, int n_cls, const int32_t* upd_cls,
+					   const orc_minimizer* upd_mins, const int64_t* upd_offs, int n_upd, uint32_t* keys,
+					   int64_t* offs, uint32_t* cls, int64_t key_cap, int64_t cls_cap)
+{
+    MinDB db(1000000);
+    std::vector<std::vector<uint32_t>> cur(n_cls);  // current minimizer VALUES per cluster (only .Min matters to UpdateMinDB)
+    for (int c = 0; c < n_cls; c++) {
+	for (int64_t j = cls_offs[c]; j < cls_offs[c + 1]; j++) {
+	    const uint32_t m = cls_mins[j].Min;
+	    cur[c].push_back(m);
+	    auto v = db.find(m);
+	    if (v == db.end()) db[m] = std::vector<unsigned>{unsigned(c)};
+	    else if (v->second.empty() || unsigned(c) > v->second.back()) v->second.push_back(unsigned(c));
+	}
+    }
+    for (int u = 0; u < n_upd; u++) {
+	const unsigned best = unsigned(upd_cls[u]);
+	std::vector<uint32_t> nw;
+	for (int64_t j = upd_offs[u]; j < upd_offs[u + 1]; j++) nw.push_back(upd_mins[j].Min);
+	std::vector<uint32_t> o(cur[best]), n(nw);  // the two std::set<unsigned> of minimizer.cpp:127-137
+	std::sort(o.begin(), o.end());
+	o.erase(std::unique(o.begin(), o.end()), o.end());
+	std::sort(n.begin(), n.end());
+	n.erase(std::unique(n.begin(), n.end()), n.end());
+	std::vector<uint32_t> to_del, to_ins;
+	std::set_difference(o.begin(), o.end(), n.begin(), n.end(), std::back_inserter(to_del));  // :139-140
+	std::set_difference(n.begin(), n.end(), o.begin(), o.end(), std::back_inserter(to_ins));  // :141-142
+	for (uint32_t m : to_del) {  // :144-153: the list becomes the sorted set of its ids without `best`
+	    std::vector<unsigned>& pl = db[m];
+	    std::sort(pl.begin(), pl.end());
+	    pl.erase(std::unique(pl.begin(), pl.end()), pl.end());
+	    pl.erase(std::remove(pl.begin(), pl.end(), best), pl.end());
+	}
+	for (uint32_t m : to_ins) {  // :155-159
+	    std::vector<unsigned>& pl = db[m];
+	    pl.push_back(best);
+	    std::sort(pl.begin(), pl.end());
+	}
+	cur[best] = nw;
+    }
+    std::vector<uint32_t> ks;
+    int64_t tot = 0;
+    for (auto& kv : db) {
+	ks.push_back(kv.first);
+	tot += int64_t(kv.second.size());
+    }
+    if (int64_t(ks.size()) > key_cap || tot > cls_cap) return -1 - std::max<int64_t>(int64_t(ks.size()), tot);
+    std::sort(ks.begin(), ks.end());
+    int64_t p = 0;
+    for (size_t i = 0; i < ks.size(); i++) {
+	keys[i] = ks[i];
+	offs[i] = p;
+	for (unsigned c : db[ks[i]]) cls[p++] = c;
+    }
+    offs[ks.size()] = p;
+    return int64_t(ks.size());
 }

@@ -7,6 +7,7 @@
 // checker / the CPU baseline.  Nothing here is an algorithm: every function
 // marshals flat buffers into the reference's own types and calls the
 // reference's own function, cited beside each wrapper.
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -522,6 +523,51 @@ int ref_sorted_hits(const uint32_t* clsMins, const int64_t* clsOffs, int nCls,
 	i++;
     }
     return i;
+}
+
+// UpdateMinDB (minimizer.cpp:124-160) on a MinDB built by AddMinimizers (minimizer.cpp:31-42) from `nCls` founders'
+// forward minimizers: update u replaces the minimizers of cluster updCls[u] (its current ones are the "old" set) by
+// updMins[updOffs[u] .. updOffs[u+1]).  Exports the resulting map sorted by key (empty posting lists included):
+// keys[], offs[nKeys+1], cls[].  Returns nKeys, or -1 - needed if a capacity is too small.
+int64_t ref_mindb_after_updates(const uint32_t* clsMins, const int64_t* clsOffs,
+				int nCls, const int32_t* updCls,
+				const uint32_t* updMins, const int64_t* updOffs,
+				int nUpd, uint32_t* keys, int64_t* offs,
+				uint32_t* cls, int64_t keyCap, int64_t clsCap)
+{
+    MinimizerDB db(MIN_DB_RESERVE, uh);
+    std::vector<Minimizers> cur(nCls);
+    for (int c = 0; c < nCls; c++) {
+	for (int64_t j = clsOffs[c]; j < clsOffs[c + 1]; j++)
+	    cur[c].push_back(Minimizer{clsMins[3 * j], clsMins[3 * j + 1],
+				       clsMins[3 * j + 2]});
+	AddMinimizers(cur[c], unsigned(c), db);
+    }
+    for (int u = 0; u < nUpd; u++) {
+	Minimizers nm;
+	for (int64_t j = updOffs[u]; j < updOffs[u + 1]; j++)
+	    nm.push_back(Minimizer{updMins[3 * j], updMins[3 * j + 1],
+				   updMins[3 * j + 2]});
+	UpdateMinDB(updCls[u], cur[updCls[u]], nm, db);
+	cur[updCls[u]] = nm;
+    }
+    std::vector<uint32_t> ks;
+    int64_t tot = 0;
+    for (auto& kv : db) {
+	ks.push_back(kv.first);
+	tot += int64_t(kv.second.size());
+    }
+    if (int64_t(ks.size()) > keyCap || tot > clsCap)
+	return -1 - std::max<int64_t>(int64_t(ks.size()), tot);
+    std::sort(ks.begin(), ks.end());
+    int64_t o = 0;
+    for (size_t i = 0; i < ks.size(); i++) {
+	keys[i] = ks[i];
+	offs[i] = o;
+	for (auto c : db[ks[i]]) cls[o++] = c;
+    }
+    offs[ks.size()] = o;
+    return int64_t(ks.size());
 }
 
 }  // extern "C"

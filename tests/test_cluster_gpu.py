@@ -181,3 +181,55 @@ def test_cluster_batches_and_merge_vs_reference(ref, ctx, mode):
         assert gm == mem_m
     finally:
         rs.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_update_representative_equals_fresh_seed(ctx, mode):
+    """a12, UpdateMinDB (minimizer.cpp:124-160) on the device index: seeding clusters and then swapping representatives gives
+    the assignments of a clusterer seeded with the final representatives directly (the MinDB equality the CPU suite pins on
+    the reference, tests/test_oracle.py::test_update_mindb_port_vs_reference), including for clusters founded later."""
+    k, w = 11, 15
+    seq, qual, offs = synth.make_reads(400, seed=91 + mode, reads_per_gene=8, min_len=300, max_len=900)
+    rs = ctx.upload(seq, qual, offs)
+    try:
+        score, err = rs.score(k)
+        rs.sketch_async(k, w, skip=api.quality_filtered(err, 7.0))
+        order = api.sort_by_qual_scores(score)
+        ok = rs.sketch_download(hpc=False)["status"] == 1
+        good = [int(r) for r in order if ok[r]]
+        reps = good[0:40:2]                         # 20 clusters
+        upd = [(3, good[41]), (7, good[43]), (3, good[45]), (0, reps[0]), (11, good[47]), (11, reps[11]), (19, good[49])]
+        final = list(reps)
+        for c, r in upd:
+            final[c] = r
+        used = set(reps) | {r for _, r in upd}
+        queries = np.array([r for r in good if r not in used], np.int32)
+        out = {}
+        for name in ("updated", "fresh"):
+            cl = api.Clusterer(rs, k, w, mode=mode, chunk_size=32)
+            try:
+                if name == "updated":
+                    cl.seed(reps)
+                    for c, r in upd:
+                        cl.update_representative(c, r)
+                    assert cl.founders().tolist() == final
+                else:
+                    cl.seed(final)
+                c1, s1 = cl.cluster(queries)
+                out[name] = (c1, s1, cl.n_clusters, cl.founders())
+            finally:
+                cl.close()
+        a, b = out["updated"], out["fresh"]
+        assert a[2] == b[2] and (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[3] == b[3]).all()
+        assert (a[0] < len(reps)).any() and a[2] > len(reps)  # reads joined seeded clusters and founded new ones
+        # a swapped-in representative attracts its own gene: some query lands in an updated cluster
+        assert np.isin(a[0], [3, 7, 19]).any()
+        with pytest.raises(api.IcbError):
+            m = api.Clusterer(rs, k, w, mode=mode)
+            try:
+                m.seed(reps[:2])
+                m.update_representative(5, reps[0])
+            finally:
+                m.close()
+    finally:
+        rs.close()

@@ -239,3 +239,47 @@ def test_ref_differential_cluster(port, ref, mode):
     ra = _assign_from_ref(rc["sizes"], rc["ids"], rc["strands"])
     pa = {int(order[s]): (int(pc["cluster"][s]), int(pc["strand"][s])) for s in range(len(order)) if pc["cluster"][s] >= 0}
     assert pa == ra and pc["n_aligned"] == rc["n_aligned"] and pc["n_clusters"] == rc["n_clusters"]
+
+
+# ---------------------------------------------------------------- a12: UpdateMinDB (minimizer.cpp:124-160)
+def _update_case(port):
+    k, w = 11, 15
+    seq, qual, offs = synth.make_reads(60, seed=77, reads_per_gene=6, min_len=300, max_len=700)
+    sk = port.sketch_batch(seq, qual, offs, k, w)
+    fwd = lambda r: sk["mins"][sk["min_offs"][r]:sk["min_offs"][r + 1]]
+    reps = [0, 6, 12, 18, 24, 30, 36, 1, 42]            # clusters 0..8 (cluster 7 shares a gene with cluster 0)
+    upd = [(2, 13), (5, 50), (2, 14), (0, 1), (8, 42), (3, 55), (3, 18)]  # same gene, foreign gene, twice, no-op, there and back
+    cm = np.concatenate([fwd(r) for r in reps])
+    co = np.cumsum([0] + [len(fwd(r)) for r in reps]).astype(np.int64)
+    um = np.concatenate([fwd(r) for _, r in upd])
+    uo = np.cumsum([0] + [len(fwd(r)) for _, r in upd]).astype(np.int64)
+    final = list(reps)
+    for c, r in upd:
+        final[c] = r
+    fm = np.concatenate([fwd(r) for r in final])
+    fo = np.cumsum([0] + [len(fwd(r)) for r in final]).astype(np.int64)
+    return (cm, co, [c for c, _ in upd], um, uo), (fm, fo)
+
+
+def _drop_empty(db):
+    keys, offs, cls = db
+    return {int(k): cls[offs[i]:offs[i + 1]].tolist() for i, k in enumerate(keys) if offs[i + 1] > offs[i]}
+
+
+def test_update_mindb_port_equals_fresh_build(port):
+    """After UpdateMinDB the non-empty posting lists are those of a MinDB built from the final representatives —
+    the property the device index update (icb_clusterer_update_representative) is tested through."""
+    case, (fm, fo) = _update_case(port)
+    got = port.mindb_after_updates(*case)
+    fresh = port.mindb_after_updates(fm, fo, [], np.zeros(0, MIN_DT), np.zeros(1, np.int64))
+    assert _drop_empty(got) == _drop_empty(fresh)
+    assert len(got[0]) > len(fresh[0])  # emptied keys stay (minimizer.cpp:150-152)
+
+
+def test_update_mindb_port_vs_reference(port, ref):
+    case, (fm, fo) = _update_case(port)
+    r, p = ref.mindb_after_updates(*case), port.mindb_after_updates(*case)
+    for a, b in zip(r, p):
+        assert (a == b).all()
+    fresh = ref.mindb_after_updates(fm, fo, [], np.zeros(0, MIN_DT), np.zeros(1, np.int64))
+    assert _drop_empty(r) == _drop_empty(fresh)
