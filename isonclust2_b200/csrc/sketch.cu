@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(Sketch
     uint32_t* Rs = Fs + SW_NWORD;
     const int k = a.k;
     const uint32_t kmask = (1u << (2 * k)) - 1u;
+    const uint32_t krmul = 1u << (32 - 2 * k);
 
     for (;;) {
 	long long t0 = 0;
@@ -683,9 +684,10 @@ __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(Sketch
 			const uint32_t y = o == 0 ? fB : (o < 16 ? __funnelshift_l(fC, fB, 2 * o) : (o == 16 ? fC : __funnelshift_l(fD, fC, 2 * (o - 16))));
 			const uint32_t vf = y >> (32 - 2 * k);
 			const uint32_t z = o == 0 ? rB : (o < 16 ? __funnelshift_r(rB, rC, 2 * o) : (o == 16 ? rC : __funnelshift_r(rC, rD, 2 * (o - 16))));
-			const uint32_t vr = z & kmask;
 			kf[o] = vf * 32u + uint32_t(o + 1);	   // smallest key = smallest value, leftmost position
-			kr[o] = vr * 32u + uint32_t(31 - (o + 1)); // reverse strand: leftmost there = rightmost here
+			// reverse strand: leftmost there = rightmost here.  The multiplication drops the bits above the k-mer
+			// (mod 2^32): value in the top 2k bits, position in the low 5 of the 32 - 2k below — one IMAD, no mask
+			kr[o] = z * krmul + uint32_t(31 - (o + 1));
 		    }
 		    uint32_t mf[16], mr[16];
 #pragma unroll
@@ -749,17 +751,23 @@ __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(Sketch
 		    int rf = Mf + (inc & 0xffff) - cf, rr = Mr + (inc >> 16) - cr;
 		    Mf += tot & 0xffff;
 		    Mr += tot >> 16;
-		    if (Mf > SW_LIST || Mr > SW_LIST) {
+		    if (Mf > SW_LIST || Mr > SW_LIST) {  // (stores are predicated: nothing is written past a list)
 			overflow = true;
 			break;
 		    }
-		    // argmin positions (k-mer start, forward coordinates) of the flagged windows
+		    // argmin positions (k-mer start, forward coordinates) of the flagged windows; running pointers, not indices:
+		    // one predicated store + one predicated pointer bump per flag
+		    {
+			uint16_t* pF = posF + rf;
+			uint16_t* pR = posR + rr;
+			const uint32_t q0m1 = uint32_t(q0 - 1);
 #pragma unroll
-		    for (int t = 0; t < 16; t++) {
-			if (ff & (1u << t)) posF[rf++] = uint16_t(q0 - 1 + int(mf[t] & 31u));
-			if (fr & (1u << t)) {
+			for (int t = 0; t < 16; t++) {
 			    const uint32_t key = t == 0 ? pr : mr[t - 1];
-			    posR[rr++] = uint16_t(q0 - 1 + (31 - int(key & 31u)));
+			    const uint32_t vF = q0m1 + (mf[t] & 31u);
+			    const uint32_t vR = q0m1 + (~key & 31u);  // 31 - (key & 31)
+			    if (ff & (1u << t)) *pF++ = uint16_t(vF);
+			    if (fr & (1u << t)) *pR++ = uint16_t(vR);
 			}
 		    }
 		}
@@ -781,26 +789,26 @@ __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(Sketch
 	    }
 	    base = __shfl_sync(0xffffffffu, base, 0);
 	    if (base + Mf + Mr <= a.mins_capacity) {
-		icb_minimizer* of = a.mins + base;
-		icb_minimizer* orv = of + Mf;
-		for (int j = lane; j < Mf; j += 32) {
-		    const int p = posF[j];
-		    const uint32_t y = __funnelshift_l(Fs[(p >> 4) + 1], Fs[p >> 4], 2 * (p & 15));
-		    icb_minimizer m;
-		    m.Min = y >> (32 - 2 * k);
-		    m.Pos = uint32_t(p);
-		    m.Index = uint32_t(j);
-		    of[j] = m;
+		// running word pointers (32 records = 96 words per step) instead of 64-bit index arithmetic per record
+		uint32_t* of = reinterpret_cast<uint32_t*>(a.mins + base + lane);
+		const uint16_t* pp = posF + lane;
+		for (int j = lane; j < Mf; j += 32, of += 96, pp += 32) {
+		    const uint32_t p = *pp;
+		    const uint32_t* fw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(Fs) + ((p >> 2) & ~3u));
+		    const uint32_t y = __funnelshift_l(fw[1], fw[0], 2 * (p & 15));
+		    of[0] = y >> (32 - 2 * k);	// Min
+		    of[1] = p;			// Pos
+		    of[2] = uint32_t(j);	// Index
 		}
-		for (int j = lane; j < Mr; j += 32) {
-		    const int p = posR[j];
-		    const uint32_t z = __funnelshift_r(Rs[p >> 4], Rs[(p >> 4) + 1], 2 * (p & 15));
-		    const int idx = Mr - 1 - j;
-		    icb_minimizer m;
-		    m.Min = z & kmask;
-		    m.Pos = uint32_t(nk - p);  // position in reverse-complement coordinates
-		    m.Index = uint32_t(idx);
-		    orv[idx] = m;
+		uint32_t* orv = reinterpret_cast<uint32_t*>(a.mins + base + Mf + (Mr - 1 - lane));
+		pp = posR + lane;
+		for (int j = lane; j < Mr; j += 32, orv -= 96, pp += 32) {
+		    const uint32_t p = *pp;
+		    const uint32_t* rw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(Rs) + ((p >> 2) & ~3u));
+		    const uint32_t z = __funnelshift_r(rw[0], rw[1], 2 * (p & 15));
+		    orv[0] = z & kmask;		       // Min
+		    orv[1] = uint32_t(nk) - p;	       // Pos in reverse-complement coordinates
+		    orv[2] = uint32_t(Mr - 1 - j);     // Index
 		}
 	    }
 	}
