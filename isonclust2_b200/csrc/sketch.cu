@@ -507,16 +507,18 @@ __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(Sketch
 		const int c = c0 + lane;
 		const int pfirst = 16 * c - shiftA;  // raw position of byte 0 of this lane's chunk
 		uint4 s4 = make_uint4(0, 0, 0, 0), q4 = make_uint4(0, 0, 0, 0);
+		uint32_t nbcur = 0;
 		if (c < nchunks) {
 		    s4 = *reinterpret_cast<const uint4*>(gseq + 16 * c);
 		    q4 = *reinterpret_cast<const uint4*>(gqual + 16 * c);
+		    if (lane == 31) nbcur = gseq[16 * c + 16];
 		}
 		// valid bytes of the chunk: raw positions 0 .. L-1
 		const int lo = max(0, -pfirst), hi = min(16, L - pfirst);
 		uint32_t vmask = hi > lo ? ((0xffffu >> (16 - hi)) & (0xffffu << lo)) : 0u;
 		// the byte after the chunk: first byte of the next lane's chunk; lane 31 reads it (it exists: slack after the buffers)
 		uint32_t nb = __shfl_down_sync(0xffffffffu, s4.x, 1);
-		if (lane == 31) nb = (c < nchunks) ? uint32_t(gseq[16 * c + 16]) : 0u;
+		if (lane == 31) nb = nbcur;
 		// run ends: byte i differs from byte i+1
 		uint32_t e = sw_nonzero_bytes(s4.x ^ __funnelshift_r(s4.x, s4.y, 8)) |
 			     (sw_nonzero_bytes(s4.y ^ __funnelshift_r(s4.y, s4.z, 8)) << 4) |
