@@ -25,6 +25,7 @@ constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t NIL = 0xFFFFFFFFu;
 constexpr uint32_t DEAD = 0xFFFFFFFFu;	// posting node whose cluster left the list (UpdateMinDB's erase)
 constexpr int Q_THREADS = 128;
+constexpr int INS_SET = 2048;  // shared-memory value set of icb_k_index_insert (sketches of up to 1024 minimizers)
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x)
 {
@@ -81,6 +82,7 @@ icb_k_index_insert(IcbIndexView ix, const icb_minimizer* __restrict__ arena, con
 {
     __shared__ int s_w[Q_THREADS / 32];
     __shared__ uint32_t s_base;
+    __shared__ uint32_t s_set[INS_SET];	 // values of this founder seen so far (open addressing), for sketches that fit
     int b = blockIdx.x;
     if (b >= n) return;
     const int r = reads[b];
@@ -88,6 +90,11 @@ icb_k_index_insert(IcbIndexView ix, const icb_minimizer* __restrict__ arena, con
     const int M = nf[r];
     const icb_minimizer* m = arena + min_off[r];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool use_set = 2 * M <= INS_SET;  // load factor <= 1/2; which duplicate keeps the node does not matter
+    if (use_set) {
+	for (int i = threadIdx.x; i < INS_SET; i += Q_THREADS) s_set[i] = EMPTY;
+	__syncthreads();
+    }
     for (int i0 = 0; i0 < M; i0 += Q_THREADS) {
 	const int i = i0 + threadIdx.x;
 	uint32_t v = 0;
@@ -95,11 +102,25 @@ icb_k_index_insert(IcbIndexView ix, const icb_minimizer* __restrict__ arena, con
 	if (i < M) {
 	    v = m[i].Min;
 	    fresh = true;
-	    for (int j = 0; j < i; j++)
-		if (m[j].Min == v) {
-		    fresh = false;
-		    break;
+	    if (use_set && v != EMPTY) {
+		uint32_t s = hash32(v) & (INS_SET - 1);
+		for (;;) {
+		    const uint32_t prev = atomicCAS(&s_set[s], EMPTY, v);
+		    if (prev == EMPTY) break;
+		    if (prev == v) {
+			fresh = false;
+			break;
+		    }
+		    s = (s + 1) & (INS_SET - 1);
 		}
+	    }
+	    else {
+		for (int j = 0; j < i; j++)
+		    if (m[j].Min == v) {
+			fresh = false;
+			break;
+		    }
+	    }
 	}
 	const uint32_t bal = __ballot_sync(0xffffffffu, fresh);
 	if (lane == 0) s_w[warp] = __popc(bal);
