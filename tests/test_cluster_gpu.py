@@ -233,3 +233,46 @@ def test_update_representative_equals_fresh_seed(ctx, mode):
                 m.close()
     finally:
         rs.close()
+
+
+def test_cluster_full_size_properties(ctx):
+    """BASELINE-shape property check (no oracle): 120k reads of the configs[1] generator in 4 batches of 30 000, `sahlin`.
+    The assignment is a pure function of the sorted order — independent of the chunk size and of how many batches are in
+    flight — and carries the greedy loop's invariants."""
+    k, w = 11, 15
+    n, B = 120_000, 30_000
+    seq, qual, offs = synth.make_reads(n, seed=100, err_set=(0.08,))
+    rs = ctx.upload(seq, qual, offs)
+    try:
+        score, err = rs.score(k)
+        filt = api.quality_filtered(err, 7.0)
+        rs.sketch_async(k, w, skip=filt)
+        order = api.sort_by_qual_scores(score)
+        assert (np.diff(score[order]) <= 0).all()  # SortByQualScores: descending, stable
+        bounds = np.arange(0, n + 1, B, dtype=np.int64)
+        a = api.cluster_batches(rs, order, bounds, k, w, n_workers=4, mode=0, chunk_size=256)
+        b = api.cluster_batches(rs, order, bounds, k, w, n_workers=2, mode=0, chunk_size=96)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+        assert a[3]["aln_invoked"] == b[3]["aln_invoked"]
+        cl, st, ncl, stats = a
+        status = rs.sketch_download(hpc=False)["status"]
+        for bi in range(len(bounds) - 1):
+            c, s = cl[bounds[bi]:bounds[bi + 1]], st[bounds[bi]:bounds[bi + 1]]
+            o = order[bounds[bi]:bounds[bi + 1]]
+            live = c >= 0
+            assert (live == (status[o] == 1)).all() and ((s == 0) == ~live).all()  # skipped <=> not sketched
+            ids = c[live]
+            assert ids.max() + 1 == ncl[bi]
+            # cluster ids are handed out in order of first appearance, and the first member founds the cluster on strand +1
+            first = np.full(int(ncl[bi]), -1, np.int64)
+            pos = np.flatnonzero(live)
+            firstpos = np.unique(ids, return_index=True)[1]
+            first[:] = pos[firstpos]
+            assert (np.diff(first) > 0).all()
+            assert (s[first] == 1).all()
+            assert set(np.unique(s[live]).tolist()) <= {-1, 1}
+        # the generator draws ~1 read in 20 per gene family and reverse-complements half: both strands are hit, most reads join
+        assert (st == -1).sum() > n // 10 and int(ncl.sum()) < n // 4
+        assert stats["aln_invoked"] > 0 and stats["cells_aligned"] > 0
+    finally:
+        rs.close()
