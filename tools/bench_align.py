@@ -8,6 +8,7 @@ from isonclust2_b200 import api, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 per = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+prof = len(sys.argv) > 4 and sys.argv[4] == "prof"  # bracket the saturated call with cudaProfilerStart/Stop (ncu --profile-from-start off)
 k, w = 11, 15
 seq, qual, offs = synth.make_reads(n, seed=100, err_set=(0.08,))
 ctx = api.Context(0)
@@ -31,6 +32,12 @@ for per_call in (per, len(pairs)):
     sub = pairs[:per_call]
     cells = float((lens[sub["read"]] * lens[sub["rep"]]).sum())
     rs.align_pairs(sub, k)
+    if prof and per_call == len(pairs):
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaProfilerStart()
+        rs.align_pairs(sub, k)
+        rt.cudaProfilerStop()
     ctx.timing(True); ctx.timing_reset()
     t0 = time.perf_counter()
     for _ in range(reps):

@@ -32,13 +32,14 @@ if has ncu_sketch; then
     echo "ncu sketch exit $?"
 fi
 if has ncu_align; then
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:icb_k_align16_dp -s 2 -c 1 -f -o $O/${tag}_align16 \
-        python tools/bench_align.py 3000 128 1 > $O/${tag}_ncu_align.log 2>&1
+    # the saturated launch (all pairs of 3000 reads in one call), bracketed by cudaProfilerStart/Stop inside the tool
+    timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:icb_k_align16_dp -c 1 -f -o $O/${tag}_align16 \
+        python tools/bench_align.py 3000 128 1 prof > $O/${tag}_ncu_align.log 2>&1
     ncu -i $O/${tag}_align16.ncu-rep --page raw --csv > $O/${tag}_align16_raw.csv 2>/dev/null
     echo "ncu align exit $?"
 fi
 if has ncu_query; then
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:icb_k_query -s 40 -c 1 -f -o $O/${tag}_query \
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:icb_k_query -s 60 -c 4 -f -o $O/${tag}_query \
         python bench.py --reads 20000 --steps 1 --warmup 3 --no-cpu-baseline > $O/${tag}_ncu_query.log 2>&1
     ncu -i $O/${tag}_query.ncu-rep --page raw --csv > $O/${tag}_query_raw.csv 2>/dev/null
     echo "ncu query exit $?"
