@@ -96,6 +96,9 @@ def cpu_share():
 
 def run_ours(args):
     share, cores = cpu_share()
+    # torchrun exports OMP_NUM_THREADS=1; the synthetic read generator (OpenMP, outside every timed region) may use this
+    # rank's share of the cores
+    os.environ["OMP_NUM_THREADS"] = str(share)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         # N ranks share the node's cores: size this rank's batch workers and helper pool for its share (library defaults
         # assume the whole machine: 3 workers per core, one helper per core)
