@@ -203,12 +203,6 @@ __global__ void icb_k_index_rehash(IcbIndexView oldv, IcbIndexView newv)
     newv.heads[t] = h;
 }
 
-__global__ void icb_k_fill_u32(uint32_t* p, uint32_t v, int64_t n)
-{
-    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
 // error class of p_emp_prob.cpp:66-94: round(e, 2) (util.cpp:6-10) clamped to [0.01, 0.15] -> 0..14
 __global__ void icb_k_classify(const double* __restrict__ err, const int32_t* __restrict__ status, int64_t n, uint8_t* __restrict__ cls)
 {
