@@ -29,6 +29,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before torch initi
 K, W_, MIN_QUAL, MODE = 11, 15, 7.0, "sahlin"
 BATCH_KB, BATCH_MAX_SEQ = 50000, 30000  # CmdArgs defaults (args.h:14-15)
 METRIC = "reads/sec clustered (sahlin)"
+INT_PIPE_PEAK_GCUPS = 148 * 4 * 16 * 1.965 / 7.5  # SMs x sub-partitions x ALU lanes/clk x GHz / ALU instructions per cell = 2482
 KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_full", "index_insert", "align_dp",
            "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "sketch_reads_cta", "gather_minimizers")
 
@@ -225,7 +226,13 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "icb_k_sketch (sketch_reads)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": int(t_ratio * alg_bytes) if t_ratio else None,
                      "traffic_source": t_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms},
-        "alignment": {"gcups": gcups, "cells_per_step": st["cells_aligned"], "pairs_per_step": st["pairs_aligned"],
+        # integer-ALU class (no "hbm"/"tensor" bound fits): cells per second of the whole step against the ALU-pipe ceiling of
+        # the DP update (15 ALU-pipe instructions per 2 cells, 16 lanes/clk per SM sub-partition).
+        # `gcups` divides by the SUMMED durations of launches that overlap on 35 streams; `effective_gcups` by the step time.
+        "alignment": {"gcups": gcups, "effective_gcups": st["cells_aligned"] / (ms * 1e-3) / 1e9,
+                      "int_pipe_peak_gcups": INT_PIPE_PEAK_GCUPS,
+                      "effective_frac": st["cells_aligned"] / (ms * 1e-3) / 1e9 / INT_PIPE_PEAK_GCUPS,
+                      "cells_per_step": st["cells_aligned"], "pairs_per_step": st["pairs_aligned"],
                       "aln_invoked": st["aln_invoked"], "dp_ms_per_step": dp_ms},
         "cluster_stats": st,
         "kernels_ms_per_step": {n: v[1] / steps for n, v in kt.items() if v[0]},
