@@ -11,8 +11,8 @@
 //   rows need the low rows' result of the same column, so they trail by one step).  A step is therefore four
 //   dependent packed cell updates = 8 cells, each update VIADDMNMX.S16x2 x2 (E, F), PRMT (score look-up),
 //   VIMNMX3.S16x2 (H) plus the four trace bits.  Thread g trails thread g-1 by two columns; inside a warp the
-//   hand-over is one shuffle per value, between warps a shared-memory ring read 8 steps after it is written (warps are staggered
-//   by 72 steps and meet at a barrier every 8 steps).
+//   hand-over is one shuffle per value, between warps a shared-memory ring read 16 steps after it is written (warps are staggered
+//   by 80 steps and meet at a barrier every 16 steps).
 //   Scores are stored biased, H~ = H + 2j + 64: the diagonal increment becomes {0,+4} (one byte-permute from a
 //   one-hot word per reference base), every packed value stays positive (plain 32-bit adds never carry between the
 //   halves) and E~ never decreases along a row.  Comparisons are between quantities of the same cell, so the trace
@@ -31,7 +31,9 @@ namespace {
 
 constexpr int A16_THREADS = 256;
 constexpr int A16_WARPS = A16_THREADS / 32;
-constexpr int A16_LAG = 72;			   // warp-to-warp stagger in steps (>= 63 + 8, multiple of 8)
+constexpr int A16_DELAY = 16;			   // steps between a warp publishing its bottom row and the next warp reading it:
+						   // one CTA barrier per A16_DELAY steps (two 8-step tiles)
+constexpr int A16_LAG = 64 + A16_DELAY;		   // warp-to-warp stagger in steps: thread 31 holds column s - 64 after local step s - 1
 constexpr int A16_PASS_ROWS = A16_THREADS * 8;	   // 2048 query rows per pass
 constexpr int A16_BIAS = 64;
 constexpr int A16_RING = 64;			   // ring slots per warp (steps)
@@ -83,7 +85,7 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl, const
     // Wp = W + sl0 - 2*lane, rd / wr = this block's 8 ring slots to read / write (all offsets below are compile-time)
     const int lane = P.lane;
     const int jl = sl - 2 * lane;
-    // thread 31 publishes the values it holds after the PREVIOUS step; the next warp reads them 8 steps later
+    // thread 31 publishes the values it holds after the PREVIOUS step; the next warp reads them A16_DELAY steps later
     if (lane == 31) wr[Q] = make_uint2(S.hb, S.fb);
     uint32_t x = __shfl_up_sync(FULL, S.hb, 1);
     uint32_t y = __shfl_up_sync(FULL, S.fb, 1);
@@ -204,7 +206,7 @@ __device__ __forceinline__ void quad16(Lane16& S, const Pass16& P, int sl0, uint
     const int sg0 = sl0 + A16_LAG * P.warp;  // global step of the quad start
     const uint32_t* Wp = P.W + (sl0 - 2 * P.lane);
     const uint2* rd = P.ring + (P.warp > 0 ? (P.warp - 1) * A16_RING : 0) + (sg0 & (A16_RING - 1));
-    uint2* wr = P.ring + P.warp * A16_RING + ((sg0 + 8) & (A16_RING - 1));
+    uint2* wr = P.ring + P.warp * A16_RING + ((sg0 + A16_DELAY) & (A16_RING - 1));
     if (EDGE) {
 #pragma unroll
 	for (int r = 0; r < 4; r++) S.T[r] = 0;
@@ -311,8 +313,10 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 		    for (int hq = 0; hq < 2; hq++) quad16<false>(S, P, sl0 + 4 * hq, dst + hq, store);
 		}
 	    }
-	    __syncthreads();
+	    // a slot written in tile b is read in tile b + A16_DELAY / 8: one barrier per A16_DELAY / 8 tiles keeps them apart
+	    if ((blk + 1) % (A16_DELAY / 8) == 0) __syncthreads();
 	}
+	if (nblk % (A16_DELAY / 8)) __syncthreads();
     }
     // ---- end cell (sg_trace_scan_avx2_256_16.c:355-395): first maximum of the last row, then the last column:
     // strictly larger wins, the smallest row among equals; a tie with the row maximum only moves the end if
