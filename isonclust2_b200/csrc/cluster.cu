@@ -493,10 +493,15 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	// the order is a function of the real candidates (which provisional ones count, and under which id)
 	OrderSlot& slot = order_cache[2 * size_t(pos) + bank];
 	if (slot.n_real == int(T.ro_real.size()) && slot.target == target && slot.set_hash == h) return slot.order;
+	// the other bank may hold it: a prediction that came true leaves the committed founders with exactly the set (and
+	// ids) the read was decided under one round earlier.  The passes over the two banks never overlap in time.
+	const OrderSlot& other = order_cache[2 * size_t(pos) + (bank ^ 1)];
+	if (other.n_real == int(T.ro_real.size()) && other.target == target && other.set_hash == h) return other.order;
 	const int r = chunk[pos];
 	Stopwatch t;
-	icb_reference_order_group(T.ro_real.data(), int(T.ro_real.size()), 20 * (size_t(nf[r]) + size_t(nr[r])), uint32_t(target), T.ro,
-				  T.ro_out);
+	// full[pos] is kept in the reference's insertion order (see where it is filled), and so is every subset of it
+	icb_reference_order_group<true>(T.ro_real.data(), int(T.ro_real.size()), 20 * (size_t(nf[r]) + size_t(nr[r])), uint32_t(target),
+					T.ro, T.ro_out);
 	T.ms_order += t.lap();
 	T.order_calls++;
 	slot.n_real = int(T.ro_real.size());
@@ -784,7 +789,16 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	    if (rc) return rc;
 	    for (size_t t = 0; t < needFull.size(); t++) {
 		const int pos = needFull[t];
-		full[pos].assign(h_cands + h_off[t], h_cands + h_off[t] + h_hdr[t].n_cand);
+		// the device writes the list ascending by id; it is kept in the reference's insertion order (strand, first hit,
+		// id: GetMinimizerHits, minimizer.cpp:44-76), which every later evaluation of the candidate order starts from
+		{
+		    const IcbCand* src = h_cands + h_off[t];
+		    const int nc = h_hdr[t].n_cand;
+		    DecideScratch& Ts = *scratch[0];
+		    icb_insertion_order(src, nc, Ts.ro, Ts.ro.ins);
+		    full[pos].resize(size_t(nc));
+		    for (int q = 0; q < nc; q++) full[pos][q] = src[Ts.ro.ins[q]];
+		}
 		have_full[pos] = 1;
 		// the candidate ORDER depends on every real candidate of the full list, however few hits it has
 		for (auto& c : full[pos])

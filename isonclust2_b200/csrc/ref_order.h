@@ -177,22 +177,37 @@ inline void loop(Key* first, Key* last, long depth, uint32_t target)
 }
 }  // namespace icb_introsort
 
-// The members of the group Size == target, in the order the reference's sorted `order` vector lists them.
+// Insertion order of GetMinimizerHits for an id-sorted candidate list: stable counting sort by (strand: +1 first, first
+// hit).  perm[rank] = index into cands.
 template <class Cand>
-void icb_reference_order_group(const Cand* cands, int n, size_t bucket_hint, uint32_t target, IcbRefOrderScratch& S,
-			       std::vector<IcbSortedCand>& out)
+void icb_insertion_order(const Cand* cands, int n, IcbRefOrderScratch& S, std::vector<int32_t>& perm)
 {
-    out.clear();
+    perm.resize(size_t(n > 0 ? n : 0));
     if (n <= 0) return;
-    // ---- insertion order: stable counting sort by (strand, first hit) of the id-sorted input
     uint32_t maxFirst = 0;
     for (int i = 0; i < n; i++) maxFirst = std::max(maxFirst, uint32_t(cands[i].tmapped));
     const uint32_t M1 = maxFirst + 1;
     S.count.assign(size_t(2) * M1 + 1, 0u);
     for (int i = 0; i < n; i++) S.count[(cands[i].strand < 0 ? M1 : 0u) + uint32_t(cands[i].tmapped) + 1]++;
     for (size_t b = 1; b < S.count.size(); b++) S.count[b] += S.count[b - 1];
-    S.ins.resize(n);
-    for (int i = 0; i < n; i++) S.ins[S.count[(cands[i].strand < 0 ? M1 : 0u) + uint32_t(cands[i].tmapped)]++] = i;
+    for (int i = 0; i < n; i++) perm[S.count[(cands[i].strand < 0 ? M1 : 0u) + uint32_t(cands[i].tmapped)]++] = i;
+}
+
+// The members of the group Size == target, in the order the reference's sorted `order` vector lists them.
+// PRESORTED: cands is in insertion order already (icb_insertion_order applied by the caller; dropping elements from such a
+// list keeps it in insertion order) instead of ascending by id.
+template <bool PRESORTED = false, class Cand>
+void icb_reference_order_group(const Cand* cands, int n, size_t bucket_hint, uint32_t target, IcbRefOrderScratch& S,
+			       std::vector<IcbSortedCand>& out)
+{
+    out.clear();
+    if (n <= 0) return;
+    if (PRESORTED) {
+	S.ins.resize(n);
+	for (int i = 0; i < n; i++) S.ins[i] = i;
+    }
+    else
+	icb_insertion_order(cands, n, S, S.ins);
     // ---- iteration order of the unordered_map -> S.keys[position] = Size << 32 | candidate index
     const size_t bkt = std::__detail::_Prime_rehash_policy()._M_next_bkt(bucket_hint);
     S.keys.clear();

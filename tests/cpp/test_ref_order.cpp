@@ -54,6 +54,29 @@ int main()
 		    q++;
 		}
 	    ok = ok && q == grp.size();
+	    // the same from a list the caller keeps in insertion order (what csrc/cluster.cu does), also after dropping elements
+	    {
+		std::vector<int32_t> perm;
+		icb_insertion_order(v.data(), int(v.size()), S, perm);
+		std::vector<Cand> pv;
+		for (int32_t i : perm) pv.push_back(v[i]);
+		std::vector<IcbSortedCand> grp2;
+		icb_reference_order_group<true>(pv.data(), int(pv.size()), hint, target, S, grp2);
+		ok = ok && grp2.size() == grp.size();
+		for (size_t i = 0; ok && i < grp.size(); i++) ok = grp2[i].Cls == grp[i].Cls && grp2[i].Strand == grp[i].Strand && grp2[i].Size == grp[i].Size;
+		if (it % 5 == 0) {
+		    std::vector<Cand> sub_id, sub_ins;
+		    for (auto& c : v)
+			if (c.id % 3) sub_id.push_back(c);
+		    for (auto& c : pv)
+			if (c.id % 3) sub_ins.push_back(c);
+		    std::vector<IcbSortedCand> a, b;
+		    icb_reference_order_group(sub_id.data(), int(sub_id.size()), hint, target, S, a);
+		    icb_reference_order_group<true>(sub_ins.data(), int(sub_ins.size()), hint, target, S, b);
+		    ok = ok && a.size() == b.size();
+		    for (size_t i = 0; ok && i < a.size(); i++) ok = a[i].Cls == b[i].Cls && a[i].Strand == b[i].Strand;
+		}
+	    }
 	    if (!ok) {
 		bad_group++;
 		if (bad_group < 5) fprintf(stderr, "case %d group %u differs (n=%zu hint=%zu)\n", it, target, v.size(), hint);
