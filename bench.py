@@ -104,9 +104,7 @@ def run_ours(args):
         # N ranks share the node's cores: size this rank's batch workers and helper pool for its share (library defaults
         # assume the whole machine: 3 workers per core, one helper per core).  Measured on 8 cores, 1 M reads, N=1
         # (taskset): 24 workers 279 k reads/s, the default 48 (35 batches in flight) 233 k reads/s.
-        os.environ.setdefault("ICB_HELPERS", str(min(16, share)))
-        if args.workers == 0:
-            args.workers = min(48, max(8, 3 * share))
+        os.environ.setdefault("ICB_HOST_CORES", str(share))
     import torch
     import torch.distributed as dist
 

@@ -189,7 +189,7 @@ int icb_clusterer_stats(const icb_clusterer* cl, icb_cluster_stats* stats);
 
 /* Initial clustering of n_batches independent sorted batches of one read set — what the reference's pipeline runs as
  * one `isONclust2 cluster` process per batch file (README.md:105-117).  Batch b is order[bounds[b] .. bounds[b+1]);
- * cluster ids are batch-local.  n_workers host threads (0 = three per host core, at most 48; a worker sleeps while its stream is busy) each drive one CUDA stream, so
+ * cluster ids are batch-local.  n_workers host threads (0 = three per host core of the process's affinity mask or of ICB_HOST_CORES, at most 48; a worker sleeps while its stream is busy) each drive one CUDA stream, so
  * the device always has several batches' kernels in flight; results do not depend on n_workers.
  * n_clusters[n_batches] and stats (summed over the batches) may be NULL. */
 int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,

@@ -1021,7 +1021,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
     if (rc) return rc;
     ICB_CUDA(ctx, ctx->wait());  // scores / sketches are complete before other streams read them
     // a worker mostly sleeps on its stream (icb_ctx::wait), so several batches per host core are kept in flight
-    int nw = n_workers > 0 ? n_workers : int(std::min<unsigned>(std::max(8u, 3u * std::thread::hardware_concurrency()), 48u));
+    int nw = n_workers > 0 ? n_workers : std::min(std::max(8, 3 * icb_host_cores()), 48);
     nw = std::min(nw, int(n_batches));
     std::atomic<int> next(0), first_err(0);
     std::vector<icb_cluster_stats> wstats(nw);

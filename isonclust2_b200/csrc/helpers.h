@@ -17,6 +17,26 @@
 #include <thread>
 #include <vector>
 
+#include <sched.h>
+
+// Host cores this process may run on: the affinity mask (taskset, cgroup cpusets, container limits), not the machine's
+// core count; ICB_HOST_CORES overrides it (a launcher that runs one process per GPU passes each rank its share).
+inline int icb_host_cores()
+{
+    if (const char* e = getenv("ICB_HOST_CORES")) {
+	const int v = atoi(e);
+	if (v > 0) return v;
+    }
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0) {
+	const int c = CPU_COUNT(&set);
+	if (c > 0) return c;
+    }
+    const unsigned h = std::thread::hardware_concurrency();
+    return h ? int(h) : 1;
+}
+
 class IcbHelperPool {
 public:
     static IcbHelperPool& get()
@@ -66,7 +86,7 @@ private:
     };
     IcbHelperPool()
     {
-	int want = int(std::thread::hardware_concurrency());
+	int want = icb_host_cores();
 	if (want > 16) want = 16;
 	if (const char* e = getenv("ICB_HELPERS")) want = atoi(e);
 	for (int t = 0; t < want; t++) threads_.emplace_back([this] { run(); });

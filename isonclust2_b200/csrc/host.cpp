@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 
+#include "helpers.h"
 #include "isonclust2_b200.h"
 
 namespace {
@@ -15,7 +16,7 @@ namespace {
 template <class F>
 void parallel_ranges(int64_t n, int64_t grain, F fn)
 {
-    const int T = int(std::min<int64_t>(std::min<int64_t>(16, std::max(1u, std::thread::hardware_concurrency())), (n + grain - 1) / grain));
+    const int T = int(std::min<int64_t>(std::min<int64_t>(16, icb_host_cores()), (n + grain - 1) / grain));
     if (T <= 1) {
 	fn(0, n);
 	return;
@@ -60,7 +61,7 @@ int icb_sort_by_score(const double* score, int64_t n, int32_t* order)
     auto cmp = [score](int32_t a, int32_t b) { return score[a] > score[b]; };
     bool nan = false;
     for (int64_t i = 0; i < n; i++) nan |= score[i] != score[i];
-    const int T = nan || n < (1 << 16) ? 1 : std::min<int>(16, std::max(1u, std::thread::hardware_concurrency()));
+    const int T = nan || n < (1 << 16) ? 1 : std::min<int>(16, icb_host_cores());
     if (T <= 1) {
 	std::stable_sort(order, order + n, cmp);
 	return ICB_OK;

@@ -70,6 +70,14 @@ def run_tree(n_batches, batch_dir, workdir, mode="sahlin", rank=0, world=1, barr
     env = dict(os.environ)
     if device is not None:
         env["ICB_DEVICE"] = str(device)
+    if world > 1 and "ICB_HOST_CORES" not in env:
+        # the ranks of one node share its cores: each job's helper threads are sized for this rank's share
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        env["ICB_HOST_CORES"] = str(max(1, cores // max(local_world, 1)))
 
     def default_runner(cmd, env):
         r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
