@@ -283,3 +283,12 @@ def test_update_mindb_port_vs_reference(port, ref):
         assert (a == b).all()
     fresh = ref.mindb_after_updates(fm, fo, [], np.zeros(0, MIN_DT), np.zeros(1, np.int64))
     assert _drop_empty(r) == _drop_empty(fresh)
+
+
+def test_update_mindb_golden(port):
+    """The port against the fixture written by the reference's own UpdateMinDB (tests/golden/make_golden_update_mindb.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_update_mindb.npz"))
+    keys, offs, cls = port.mindb_after_updates(g["cls_mins"], g["cls_offs"], g["upd_cls"], g["upd_mins"], g["upd_offs"])
+    assert (keys == g["keys"]).all() and (offs == g["offs"]).all() and (cls == g["cls"]).all()
+    assert (offs[1:] == offs[:-1]).any()  # emptied keys are kept
