@@ -26,12 +26,35 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before torch initialises CUDA: one hardware queue per worker stream
 
-K, W_, MIN_QUAL, MODE = 11, 15, 7.0, "sahlin"
+K, W_, MIN_QUAL = 11, 15, 7.0
 BATCH_KB, BATCH_MAX_SEQ = 50000, 30000  # CmdArgs defaults (args.h:14-15)
-METRIC = "reads/sec clustered (sahlin)"
+MODE_IDS = {"sahlin": 0, "fast": 1, "furious": 2}
+DIGEST_FILE = os.path.join(ROOT, ".bench_reference_digest.json")  # written by --impl reference, read by the GPU arm
+
+
+def metric_name(mode):
+    return f"reads/sec clustered ({mode})"
+
+
+def result_digest(n_clusters, cluster, strand, aln_invoked):
+    """sha256 over what a clustering run decides: clusters per batch, (cluster, strand) per sorted slot, ALN_INVOKED."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(n_clusters, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(cluster, dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(strand, dtype=np.int32).tobytes())
+    h.update(np.int64(aln_invoked).tobytes())
+    return h.hexdigest()
+
+
+def digest_key(reads, seed, mode, batch_max_seq, n_genes):
+    return f"reads={reads} seed={seed} genes={n_genes} k={K} w={W_} mode={mode} B={BATCH_KB} M={batch_max_seq} minq={MIN_QUAL}"
+
+
 INT_PIPE_PEAK_GCUPS = 148 * 4 * 16 * 1.965 / 7.5  # SMs x sub-partitions x ALU lanes/clk x GHz / ALU instructions per cell = 2482
 KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_full", "index_insert", "align_dp",
-           "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "sketch_reads_cta", "gather_minimizers")
+           "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "sketch_reads_cta", "gather_minimizers",
+           "dl_init", "dl_decide", "dl_commit", "dl_gather", "dl_finalize")
 
 
 def clocks_sampler(stop, out, device):
@@ -95,15 +118,39 @@ def cpu_share():
     return max(2, cores // max(local_world, 1)), cores
 
 
+def accepted_pairs(res, err, limit):
+    """(read, representative, strand, gap_open, window limit) of the reads that JOINED a cluster in `res`, batch by batch — real
+    read / representative pairs with the step's length distribution, replayed through icb_align_pairs for the DP roofline."""
+    from isonclust2_b200 import api
+    order, cl, st = res["order"], res["cluster"], res["strand"]
+    out = []
+    for (lo, hi) in res["batches"]:
+        c = cl[lo:hi]
+        live = np.flatnonzero(c >= 0)
+        if not len(live):
+            continue
+        ids, first = np.unique(c[live], return_index=True)
+        founder_slot = np.full(int(ids.max()) + 1, -1, np.int64)
+        founder_slot[ids] = live[first]
+        joined = live[founder_slot[c[live]] != live]
+        reads = order[lo + joined]
+        reps = order[lo + founder_slot[c[joined]]]
+        strands = st[lo:hi][joined]
+        for r, p, sd in zip(reads.tolist(), reps.tolist(), strands.tolist()):
+            e = err[r] + err[p]
+            out.append((r, p, sd, api.set_gap_open(e), api.aln_limit(e, K)))
+            if len(out) >= limit:
+                return np.array(out, dtype=api.PAIR_DT)
+    return np.array(out, dtype=api.PAIR_DT)
+
+
 def run_ours(args):
     share, cores = cpu_share()
     # torchrun exports OMP_NUM_THREADS=1; the synthetic read generator (OpenMP, outside every timed region) may use this
     # rank's share of the cores
     os.environ["OMP_NUM_THREADS"] = str(share)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        # N ranks share the node's cores: size this rank's batch workers and helper pool for its share (library defaults
-        # assume the whole machine: 3 workers per core, one helper per core).  Measured on 8 cores, 1 M reads, N=1
-        # (taskset): 24 workers 279 k reads/s, the default 48 (35 batches in flight) 233 k reads/s.
+        # N ranks share the node's cores: size this rank's batch workers and helper pool for its share
         os.environ.setdefault("ICB_HOST_CORES", str(share))
     import torch
     import torch.distributed as dist
@@ -117,6 +164,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    mode = args.mode
     n_reads = args.reads  # per GPU (weak scaling)
     pin = lambda n: torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
     seq, qual, offs = synth.make_reads(n_reads, seed=100 + rank, err_set=(0.08,), seq_out=pin, qual_out=pin)
@@ -131,7 +179,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    pipe = dict(k=K, w=W_, mode=MODE, min_qual=MIN_QUAL, batch_kb=BATCH_KB, batch_max_seq=args.batch_max_seq, chunk_size=args.chunk,
+    pipe = dict(k=K, w=W_, mode=mode, min_qual=MIN_QUAL, batch_kb=BATCH_KB, batch_max_seq=args.batch_max_seq, chunk_size=args.chunk,
                 n_workers=args.workers)
 
     # ---------------- device-resident steps: reads already in HBM
@@ -159,25 +207,61 @@ def run_ours(args):
         barrier()
         times.append(e0.elapsed_time(e1))
     launches = ctx.launch_count() - launches0
-    # one more pass with an event pair around every kernel launch (the library's per-kernel timers): kernel-level
-    # durations for the roofline; not part of the timed steps above
-    ctx.timing(True)
-    ctx.timing_reset()
-    l2_flush.add_(1)
-    barrier()
-    res = api.run_pipeline(ctx, None, None, None, rs=rs, **pipe)
-    ctx.sync()
-    kt = {n: ctx.kernel_time(n) for n in KERNELS}
-    ctx.timing(False)
+    digest = result_digest(res["n_clusters"], res["cluster"], res["strand"], res["stats"]["aln_invoked"])
+
+    # ---------------- kernel-level passes (not part of the timed steps): event pairs around every launch, ONE stream, so the
+    # per-kernel durations do not overlap
     nf, nr = rs.sketch_sizes()
     sk = rs.sketch_download(hpc=False)
     hpc_total = int(sk["hpc_len"].sum())
+    ctx.timing(True)
+    # (1) scores + sketches of the whole read set
+    ctx.timing_reset()
+    l2_flush.add_(1)
+    barrier()
+    rs.score_async(K)
+    rs.sketch_async(K, W_, skip=api.quality_filtered(res["err"], MIN_QUAL))
+    ctx.sync()
+    kt = {n: ctx.kernel_time(n) for n in KERNELS}
+    # (2) the first batches on a single worker stream: index build / probe kernels, alignment launches as the loop issues them
+    ser_batches = res["batches"][:max(1, min(args.serial_batches, len(res["batches"])))]
+    ser_bounds = np.array([a for a, _ in ser_batches] + [ser_batches[-1][1]], dtype=np.int64)
+    ctx.timing_reset()
+    barrier()
+    t0 = time.perf_counter()
+    _, _, _, ser_stats = api.cluster_batches(rs, res["order"], ser_bounds, K, W_, n_workers=1, mode=mode, min_qual=MIN_QUAL,
+                                             chunk_size=args.chunk)
+    ctx.sync()
+    ser_wall = time.perf_counter() - t0
+    ks = {n: ctx.kernel_time(n) for n in KERNELS}
+    ser_reads = int(ser_bounds[-1] - ser_bounds[0])
+    ser_sel = res["order"][ser_bounds[0]:ser_bounds[-1]]
+    ser_mins = int((sk["min_offs"][1:] - sk["min_offs"][:-1])[ser_sel].sum() + (sk["rev_offs"][1:] - sk["rev_offs"][:-1])[ser_sel].sum())
+    # (3) alignment kernels saturated: the step's accepted (read, representative) pairs replayed in full launches
+    dp_sat = None
+    if mode != "fast":
+        pairs = accepted_pairs(res, res["err"], args.replay_pairs)
+        if len(pairs):
+            lens = np.diff(rs.offs)
+            cells = int((lens[pairs["read"]].astype(np.int64) * lens[pairs["rep"]].astype(np.int64)).sum())
+            rs.align_pairs(pairs[:256], K)  # workspace growth outside the timed launches
+            ctx.timing_reset()
+            l2_flush.add_(1)
+            barrier()
+            rs.align_pairs(pairs, K)
+            ctx.sync()
+            n_dp, ms_dp = ctx.kernel_time("align_dp")
+            n_tr, ms_tr = ctx.kernel_time("align_trace")
+            dp_sat = {"pairs": int(len(pairs)), "cells": cells, "dp_launches": n_dp, "dp_ms": ms_dp, "trace_ms": ms_tr,
+                      "gcups": cells / (ms_dp * 1e-3) / 1e9 if ms_dp > 0 else 0.0}
+    ctx.timing(False)
     rs.close()
 
     # ---------------- e2e through the C ABI with host buffers
     for _ in range(1):
         api.run_pipeline(ctx, seq, qual, offs, **pipe)
     e2e_times = []
+    res_e2e = None
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
@@ -187,6 +271,7 @@ def run_ours(args):
         e2e_times.append((time.perf_counter() - t0) * 1e3)
     stop.set()
     th.join(timeout=2)
+    digest_e2e = result_digest(res_e2e["n_clusters"], res_e2e["cluster"], res_e2e["strand"], res_e2e["stats"]["aln_invoked"])
 
     ms = float(np.mean(times))
     ms_e2e = float(np.mean(e2e_times))
@@ -195,50 +280,94 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
-    # roofline of the dominant data-moving kernel (sketch_reads): algorithmic bytes per launch / measured launch time
-    steps = 1  # the kernel timers cover the single profiling pass
+    peak, peak_src = measured_peak()
+    # sketch kernel: algorithmic bytes per launch / measured launch time (HBM class)
     alg_bytes = 2 * n_bases + 2 * hpc_total + 12 * (nf + nr) + 24 * n_reads
     n_l, tot_ms = kt["sketch_reads"]
     k_ms = tot_ms / max(n_l, 1)
-    peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     t_ratio, t_src = sketch_traffic_ratio()
+    roofline_hbm = {"bound": "hbm", "kernel": "icb_k_sketch_warp (sketch_reads)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": int(t_ratio * alg_bytes) if t_ratio else None,
+                    "traffic_source": t_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms}
+    # index probe kernel (SURVEY 8d bytes: minimizers in 12 B + bucket heads 8 B per probe, 8 B per posting node walked —
+    # twice: counts, then the bitmaps of the relevant candidates —, 16 B per candidate record out)
+    q_n, q_ms = ks["index_query"]
+    probe_bytes = 20 * ser_mins + 2 * 8 * ser_stats["hits"] + 16 * ser_stats["cands"]
+    index_probe = {"bound": "hbm", "kernel": "icb_k_query (index_query)", "launches": q_n, "kernel_ms": q_ms,
+                   "reads": ser_reads, "hits": ser_stats["hits"], "candidates": ser_stats["cands"],
+                   "algorithmic_bytes": probe_bytes, "achieved": probe_bytes / (q_ms * 1e-3) / 1e9 if q_ms > 0 else 0.0, "peak": peak,
+                   "unit": "GB/s", "frac": (probe_bytes / (q_ms * 1e-3) / 1e9 / peak) if q_ms > 0 else 0.0,
+                   "hits_per_s": ser_stats["hits"] / (q_ms * 1e-3) if q_ms > 0 else 0.0,
+                   "note": "latency-bound posting-chain gathers; single worker stream, first batches of the step"}
     st = res["stats"]
-    dp_ms = kt["align_dp"][1] / steps
-    gcups = st["cells_aligned"] / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else 0.0
     clustered = int((res["cluster"] >= 0).sum())
+    eff_gcups = st["cells_aligned"] / (ms * 1e-3) / 1e9
+    if mode == "fast":
+        roofline = dict(index_probe)
+    else:
+        # the dominant kernel: icb_k_align16_dp, integer-ALU class.  achieved = cells of the saturated replay / summed DP launch
+        # time on one stream; ceiling = ALU-pipe issue: 15 ALU-pipe instructions per packed update of 2 cells
+        roofline = {"bound": "int-alu", "kernel": "icb_k_align16_dp (align_dp)", "achieved": dp_sat["gcups"] if dp_sat else 0.0,
+                    "peak": INT_PIPE_PEAK_GCUPS, "peak_source": "148 SM x 4 x 16 lanes x 1.965 GHz / 7.5 ALU instr per cell",
+                    "unit": "GCUPS", "frac": (dp_sat["gcups"] / INT_PIPE_PEAK_GCUPS) if dp_sat else 0.0, "traffic": None,
+                    "saturated_replay": dp_sat,
+                    "in_step": {"cells_per_step": st["cells_aligned"], "pairs_per_step": st["pairs_aligned"],
+                                "effective_gcups": eff_gcups, "effective_frac": eff_gcups / INT_PIPE_PEAK_GCUPS,
+                                "aln_invoked": st["aln_invoked"], "aln_calls_ref": st["aln_calls_ref"]}}
+
+    parity, parity_src = None, None
+    if rank == 0:
+        try:
+            ref = json.load(open(DIGEST_FILE))
+            key = digest_key(n_reads, 100, mode, args.batch_max_seq, max(1, n_reads // 25))
+            if key in ref:
+                parity = bool(ref[key]["digest"] == digest and digest_e2e == digest)
+                parity_src = f"{os.path.basename(DIGEST_FILE)} written by `bench.py --impl reference` ({ref[key].get('when', '?')})"
+        except Exception:
+            pass
 
     line = {
-        "metric": METRIC, "value": world * n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(mode), "value": world * n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/u32/i32 (+f64 quality chains)", "data": "synthetic",
-        "config": {**workload_config(n_reads, args.batch_max_seq),
+        "config": {**workload_config(n_reads, args.batch_max_seq, mode),
                    "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "batches": len(res["batches"]),
                    "clusters": int(sum(res["n_clusters"])), "reads_clustered": clustered,
-                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"reads sharded x{world}, no collective", "host_cores": cores, "host_cores_per_rank": share},
+                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"reads sharded x{world}, no collective",
+                   "host_cores": cores, "host_cores_per_rank": share},
         "e2e": {"value": world * n_reads / (ms_e2e * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": 2 * n_bases + 8 * (n_reads + 1) + n_reads, "d2h_bytes_per_step": 16 * n_reads + 24 * n_reads,
                 "phases_ms_last_step": {k: round(v, 1) for k, v in res_e2e["phases_ms"].items()}},
         "phases_ms_last_step": {k: round(v, 1) for k, v in res["phases_ms"].items()},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "icb_k_sketch (sketch_reads)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": int(t_ratio * alg_bytes) if t_ratio else None,
-                     "traffic_source": t_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms},
-        # integer-ALU class (no "hbm"/"tensor" bound fits): cells per second of the whole step against the ALU-pipe ceiling of
-        # the DP update (15 ALU-pipe instructions per 2 cells, 16 lanes/clk per SM sub-partition).
-        # `gcups` divides by the SUMMED durations of launches that overlap on 35 streams; `effective_gcups` by the step time.
-        "alignment": {"gcups": gcups, "effective_gcups": st["cells_aligned"] / (ms * 1e-3) / 1e9,
-                      "int_pipe_peak_gcups": INT_PIPE_PEAK_GCUPS,
-                      "effective_frac": st["cells_aligned"] / (ms * 1e-3) / 1e9 / INT_PIPE_PEAK_GCUPS,
-                      "cells_per_step": st["cells_aligned"], "pairs_per_step": st["pairs_aligned"],
-                      "aln_invoked": st["aln_invoked"], "dp_ms_per_step": dp_ms},
+        "result_digest": digest, "result_digest_e2e": digest_e2e,
+        "parity_vs_reference": parity, "parity_source": parity_src,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "index_probe": index_probe,
         "cluster_stats": st,
-        "kernels_ms_per_step": {n: v[1] / steps for n, v in kt.items() if v[0]},
-        "kernel_launches_per_step": {n: v[0] / steps for n, v in kt.items() if v[0]},
+        "kernels_serialized": {"what": f"one worker stream: scores + sketches of all reads; cluster of the first {len(ser_batches)} batch(es) "
+                                       f"({ser_reads} reads, {ser_wall * 1e3:.0f} ms wall)",
+                               "ms": {n: round(v[1], 3) for n, v in {**kt, **{k2: v2 for k2, v2 in ks.items() if v2[0]}}.items() if v[0]},
+                               "launches": {n: v[0] for n, v in {**kt, **{k2: v2 for k2, v2 in ks.items() if v2[0]}}.items() if v[0]}},
         "clocks": summarize_clocks(samples),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_subprocess(args)
+        cb = cpu_baseline_subprocess(args)
+        # the same bounded sample through the GPU path: the two must decide identically
+        if cb.get("digest"):
+            try:
+                n_s, m_s = cb["sample_reads"], cb["sample_batch_max_seq"]
+                sseq, squal, soffs = synth.make_reads(n_s, seed=100, err_set=(0.08,), n_genes=max(1, n_reads // 25))
+                sres = api.run_pipeline(ctx, sseq, squal, soffs, **{**pipe, "batch_max_seq": m_s})
+                cb["gpu_digest"] = result_digest(sres["n_clusters"], sres["cluster"], sres["strand"], sres["stats"]["aln_invoked"])
+                cb["parity"] = bool(cb["gpu_digest"] == cb["digest"])
+            except Exception as ex:  # noqa: BLE001
+                cb["parity"] = None
+                cb["parity_error"] = repr(ex)[:200]
+        line["cpu_baseline"] = cb
+        if line["parity_vs_reference"] is None and cb.get("parity") is not None:
+            line["parity_vs_reference"] = cb["parity"]
+            line["parity_source"] = "cpu_baseline sample (same reads and batch bounds through both implementations)"
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -247,54 +376,77 @@ def run_ours(args):
 
 
 def _ref_cluster_worker(args):
-    """One `isONclust2 cluster -x sahlin` job: runs in a forked child on the parent's sorted batch (copy-on-write)."""
-    lo, hi, nr = args
+    """One `isONclust2 cluster -x <mode>` job: runs in a forked child on the parent's sorted batch (copy-on-write)."""
+    lo, hi, nr, mode_id = args
     t0 = time.perf_counter()
-    rc = _REF_STATE["batch"].slice(lo, hi, nr).cluster(0)
-    return rc["n_clusters"], time.perf_counter() - t0
+    rc = _REF_STATE["batch"].slice(lo, hi, nr).cluster(mode_id)
+    return rc["n_clusters"], rc["sizes"], rc["ids"], rc["strands"], rc["n_aligned"], time.perf_counter() - t0
 
 
 _REF_STATE = {}
 
 
-def reference_step(seq, qual, offs, batch_reads, cores):
+def reference_step(seq, qual, offs, batch_max_seq, cores, mode):
     """The reference's own CPU implementation of one step over the given reads: `sort` (FillQualScores + SortByQualScores +
-    PrepareSortedBatch, TBB on all host cores) then one single-threaded `cluster -x sahlin` job per batch, `cores` jobs at a
-    time — how the reference's pipeline runs it (README.md:105-117).  Returns (seconds, clusters, kind)."""
+    PrepareSortedBatch, TBB on all host cores), batches by the main.cpp:149-199 rule, then one single-threaded
+    `cluster -x <mode>` job per batch, `cores` jobs at a time — how the reference's pipeline runs it (README.md:105-117).
+    Returns (seconds, clusters, kind, digest, n_batches)."""
     import multiprocessing as mp
 
     import oracle
-    from isonclust2_b200 import pemp
+    from isonclust2_b200 import api, pemp
 
     n = len(offs) - 1
-    bounds = list(range(0, n, batch_reads)) + [n]
     t0 = time.perf_counter()
     if oracle.have_ref():
         R = oracle.ref()
         batch = R.sort_and_sketch(seq, qual, offs, K, W_, MIN_QUAL)
+        _, _, order = batch.scores()
+        batches = api.split_batches(order, np.diff(offs), BATCH_KB, batch_max_seq)
         _REF_STATE["batch"] = batch
-        jobs = [(bounds[i], bounds[i + 1] - 1, i) for i in range(len(bounds) - 1)]
+        jobs = [(lo, hi - 1, i, MODE_IDS[mode]) for i, (lo, hi) in enumerate(batches)]
         if len(jobs) == 1:
             out = [_ref_cluster_worker(jobs[0])]
         else:
             with mp.get_context("fork").Pool(min(cores, len(jobs))) as pool:
                 out = pool.map(_ref_cluster_worker, jobs, chunksize=1)
         _REF_STATE.clear()
-        return time.perf_counter() - t0, int(sum(o[0] for o in out)), "reference"
+        dt = time.perf_counter() - t0
+        # per sorted slot (cluster, strand) from the member lists (element 0 of a cluster is the representative's copy)
+        slot_of = np.empty(n, np.int64)
+        slot_of[order] = np.arange(n)
+        cl, st = np.full(n, -1, np.int32), np.zeros(n, np.int32)
+        for (_, sizes, ids, strands, _, _) in out:
+            pos = 0
+            for ci, sz in enumerate(sizes):
+                m = ids[pos + 1:pos + sz]
+                cl[slot_of[m]] = ci
+                st[slot_of[m]] = strands[pos + 1:pos + sz]
+                pos += sz
+        ncl = [o[0] for o in out]
+        dg = result_digest(ncl, cl, st, sum(int(o[4]) for o in out))
+        return dt, int(sum(ncl)), "reference", dg, len(batches)
     # no compiled reference on this box: the C restatement, one thread
     P = oracle.port()
     s, e = P.fill_scores(qual, offs, K)
     o = P.sort_order(s)
     sk = P.sketch_batch(seq, qual, offs, K, W_)
-    ncl = 0
-    for i in range(len(bounds) - 1):
-        ncl += P.cluster(seq, offs, sk, s, e, o[bounds[i]:bounds[i + 1]], K, W_, 0, pemp.load_p_shared(K, W_))["n_clusters"]
-    return time.perf_counter() - t0, int(ncl), "port"
+    status = sk["status"].copy()
+    status[api.quality_filtered(e, MIN_QUAL).astype(bool)] = 0
+    batches = api.split_batches(o, np.diff(offs), BATCH_KB, batch_max_seq)
+    cl, st, ncl, nal = np.full(n, -1, np.int32), np.zeros(n, np.int32), [], 0
+    for (lo, hi) in batches:
+        pc = P.cluster(seq, offs, sk, s, e, o[lo:hi], K, W_, MODE_IDS[mode], pemp.load_p_shared(K, W_), status=status)
+        cl[lo:hi], st[lo:hi] = pc["cluster"], pc["strand"]
+        ncl.append(pc["n_clusters"])
+        nal += pc["n_aligned"]
+    return time.perf_counter() - t0, int(sum(ncl)), "port", result_digest(ncl, cl, st, nal), len(batches)
 
 
 def run_reference(args, quiet=False):
-    """--impl reference: the reference's CPU path on the host cores, on a bounded sample of the same workload
-    (same generator and seed, same k / w / mode / batch size; `cores` batches so every core has one cluster job)."""
+    """--impl reference: the reference's CPU path on the host cores, on the SAME reads and batch bounds as the GPU arm
+    (same generator, seed, k / w / mode, split rule).  --sample-reads bounds it to the first reads of that read set (the
+    cpu_baseline leg).  Prints the result digest and leaves it in DIGEST_FILE for the GPU arm's parity_vs_reference."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
@@ -302,44 +454,61 @@ def run_reference(args, quiet=False):
     from isonclust2_b200 import synth
 
     cores = os.cpu_count() or 1
-    batch_reads = min(args.batch_max_seq, args.ref_batch_reads)
-    n_batches = max(1, min(cores, args.reads // batch_reads)) if oracle.have_ref() else 1
-    n_reads = n_batches * batch_reads
-    seq, qual, offs = synth.make_reads(args.reads, seed=100, err_set=(0.08,))
-    seq, qual, offs = seq[:offs[n_reads]], qual[:offs[n_reads]], offs[:n_reads + 1]
+    mode = args.mode
+    n_genes = max(1, args.reads // 25)
+    n_reads = min(args.reads, args.sample_reads) if args.sample_reads > 0 else args.reads
+    if not oracle.have_ref():
+        n_reads = min(n_reads, 3000)  # the scalar port is ~20x slower than the compiled reference
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    seq, qual, offs = synth.make_reads(n_reads, seed=100, err_set=(0.08,), n_genes=n_genes)
     for _ in range(args.warmup):  # a CPU run has nothing to warm but the page cache: one small batch per warm-up step
         m = min(n_reads, 500)
-        reference_step(seq[:offs[m]], qual[:offs[m]], offs[:m + 1], m, 1)
-    secs, kind, ncl = [], "port", 0
-    # one step is about a minute of CPU work on every core: at most 3 are timed, so that any --steps K ends within minutes
-    n_steps = min(max(args.steps, 1), 3)
-    for _ in range(n_steps):
-        dt, ncl, kind = reference_step(seq, qual, offs, batch_reads, cores)
+        reference_step(seq[:offs[m]], qual[:offs[m]], offs[:m + 1], m, 1, mode)
+    secs, kind, ncl, dg, nb = [], "port", 0, None, 0
+    # one step of the full configuration is minutes of CPU work on every core: steps stop once a minute has been spent
+    n_want = min(max(args.steps, 1), 3)
+    while len(secs) < n_want:
+        dt, ncl, kind, dg, nb = reference_step(seq, qual, offs, args.batch_max_seq, cores, mode)
         secs.append(dt)
+        if sum(secs) > 60.0:
+            break
+    n_steps = len(secs)
     dt = float(np.mean(secs))
     v = n_reads / dt
-    used = min(cores, n_batches) if kind == "reference" else 1
+    used = min(cores, nb) if kind == "reference" else 1
+    full = n_reads == args.reads
     cb = {"value": v, "unit": "reads/s", "cores": cores if kind == "reference" else 1, "kind": kind,
-          "sample": f"{n_reads} reads of the same workload = {n_batches} batches of {batch_reads}: sort + sketch on {cores} TBB threads, "
-                    f"then {used} single-threaded `cluster -x sahlin` jobs in parallel; {dt:.1f} s per step, {ncl} clusters; "
-                    f"{n_steps} step(s) timed" + (f" of the {args.steps} requested" if n_steps != args.steps else "")}
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+          "sample": (f"the whole workload ({n_reads} reads" if full else f"the first {n_reads} of the workload's {args.reads} reads (") +
+                    f"{'' if full else 'same gene set, '}{nb} batches by the main.cpp:149-199 rule, M={args.batch_max_seq}): sort + sketch on "
+                    f"{cores} TBB threads, then {used} single-threaded `cluster -x {mode}` jobs in parallel; {dt:.1f} s per step, "
+                    f"{ncl} clusters; {n_steps} step(s) timed" + (f" of the {args.steps} requested" if n_steps != args.steps else ""),
+          "digest": dg, "sample_reads": n_reads, "sample_batch_max_seq": args.batch_max_seq}
+    line = {"impl": "reference", "metric": metric_name(mode), "value": v, "unit": "reads/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": n_steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u32/i32 (+f64 quality chains)", "data": "synthetic",
-            "config": workload_config(args.reads, args.batch_max_seq),
+            "config": workload_config(args.reads, args.batch_max_seq, mode), "result_digest": dg,
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if full and dg:
+        try:
+            ref = json.load(open(DIGEST_FILE)) if os.path.exists(DIGEST_FILE) else {}
+            ref[digest_key(n_reads, 100, mode, args.batch_max_seq, n_genes)] = {"digest": dg, "clusters": ncl, "kind": kind,
+                                                                                "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}
+            json.dump(ref, open(DIGEST_FILE, "w"))
+        except Exception:
+            pass
     if not quiet:
         print(json.dumps(line), flush=True)
     return line
 
 
 def cpu_baseline_subprocess(args):
-    """cpu_baseline of the main line: the reference arm on a smaller bounded sample, in a fresh process (no CUDA state
-    is forked)."""
+    """cpu_baseline of the main line: the reference arm on a bounded sample (the first reads of the same read set, smaller
+    batches so that every core has one), in a fresh process (no CUDA state is forked)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--reads", str(args.reads),
-           "--batch-max-seq", str(args.batch_max_seq), "--ref-batch-reads", str(args.cpu_baseline_batch_reads)]
+           "--mode", args.mode, "--sample-reads", str(min(args.reads, args.cpu_baseline_reads)),
+           "--batch-max-seq", str(args.cpu_baseline_batch_reads)]
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith("{"):
                 return json.loads(ln)["cpu_baseline"]
@@ -348,9 +517,9 @@ def cpu_baseline_subprocess(args):
         return {"value": None, "unit": "reads/s", "cores": 0, "kind": "failed", "sample": repr(ex)[:300]}
 
 
-def workload_config(reads, batch_max_seq):
+def workload_config(reads, batch_max_seq, mode):
     return {"workload": f"configs[1] read set: {reads} synthetic ONT cDNA reads per GPU (~1.3 kb mean, 8% error), k={K} w={W_}, "
-                        f"sort + cluster -x {MODE} of every batch (B={BATCH_KB} kb, M={batch_max_seq})"}
+                        f"sort + cluster -x {mode} of every batch (B={BATCH_KB} kb, M={batch_max_seq})"}
 
 
 def main():
@@ -359,10 +528,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU (configs[1]: 1M)")
+    ap.add_argument("--mode", default="sahlin", choices=["sahlin", "fast", "furious"], help="cluster -x (configs[2] = fast, configs[3] = sahlin)")
     ap.add_argument("--workers", type=int, default=0, help="batches in flight per GPU (0 = library default)")
-    ap.add_argument("--ref-batch-reads", type=int, default=BATCH_MAX_SEQ, help="--impl reference: reads per batch of its sample")
+    ap.add_argument("--sample-reads", type=int, default=0, help="--impl reference: only the first reads of the read set (0 = all)")
+    ap.add_argument("--cpu-baseline-reads", type=int, default=80000, help="cpu_baseline leg: reads of its sample")
     ap.add_argument("--cpu-baseline-batch-reads", type=int, default=5000, help="cpu_baseline leg: reads per batch of its sample")
     ap.add_argument("--batch-max-seq", type=int, default=BATCH_MAX_SEQ)
+    ap.add_argument("--serial-batches", type=int, default=2, help="batches of the single-stream kernel timing pass")
+    ap.add_argument("--replay-pairs", type=int, default=60000, help="pairs of the saturated alignment replay")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

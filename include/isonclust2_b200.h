@@ -160,6 +160,10 @@ typedef struct {
     double ms_batch_max;   /* icb_cluster_batches: wall clock of the slowest batch */
     double ms_wall;	   /* icb_cluster_batches: wall clock of the whole call */
     int64_t hyp_decisions; /* decisions re-taken under predicted founders, only to request device work one round trip earlier */
+    int64_t hits;	   /* posting entries matched by the queried reads' minimizers (H of the index-probe byte count) */
+    int64_t cands;	   /* candidate records written by the chunk queries (C of the index-probe byte count) */
+    int64_t dl_chunks;	   /* chunks decided entirely on the device (device-resident loop) */
+    int64_t dl_fallback_chunks; /* chunks the device loop handed back to the host loop */
 } icb_cluster_stats;
 
 typedef struct icb_clusterer icb_clusterer;

@@ -57,9 +57,6 @@ def quality_filtered(err, min_qual):
     return out
 
 
-quality_filtered_fast = quality_filtered
-
-
 def sort_by_qual_scores(score):
     """SortByQualScores (qualscore.cpp:138-145): std::stable_sort, descending."""
     score = np.ascontiguousarray(score, dtype=np.float64)
@@ -81,7 +78,8 @@ class ClusterStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("chunks", "rounds", "reads_queried", "aln_invoked", "pairs_aligned", "cells_aligned",
                                          "tie_fallbacks", "decisions")] + \
                [(n, C.c_double) for n in ("ms_query", "ms_full", "ms_align", "ms_insert", "ms_host", "ms_cpu", "ms_order")] + \
-               [("order_calls", C.c_int64), ("aln_calls_ref", C.c_int64), ("ms_batch_max", C.c_double), ("ms_wall", C.c_double), ("hyp_decisions", C.c_int64)]
+               [("order_calls", C.c_int64), ("aln_calls_ref", C.c_int64), ("ms_batch_max", C.c_double), ("ms_wall", C.c_double), ("hyp_decisions", C.c_int64),
+                ("hits", C.c_int64), ("cands", C.c_int64), ("dl_chunks", C.c_int64), ("dl_fallback_chunks", C.c_int64)]
 
 
 MODES = {"sahlin": 0, "fast": 1, "furious": 2}

@@ -119,9 +119,11 @@ __device__ icb_align_result traceback_warp(const uint8_t* __restrict__ seq, cons
 
 __global__ void __launch_bounds__(AL_THREADS)
 icb_k_align32_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, int n_pairs, uint4* __restrict__ trace,
-	       int* __restrict__ lines, int k, icb_align_result* __restrict__ out, unsigned long long* __restrict__ ticket)
+	       int* __restrict__ lines, int k, icb_align_result* __restrict__ out, unsigned long long* __restrict__ ticket,
+	       const int32_t* __restrict__ n_pairs_dev, int32_t* __restrict__ aln_out)
 {
     const int lane = threadIdx.x & 31;
+    if (n_pairs_dev) n_pairs = *n_pairs_dev;  // device-built pair queue (dloop.cu)
     for (;;) {
 	int p = 0;
 	if (lane == 0) p = int(atomicAdd(ticket, 1ull));
@@ -308,7 +310,10 @@ icb_k_align32_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	// ---- traceback by the same warp while the trace tiles are still in L2 (all lanes walk in lockstep; the
 	// tiles of a 4x4-tile window and the 32 query / reference characters it spans are held across the lanes)
 	icb_align_result res = traceback_warp(seq, d, tr, ncg, k, score, ei, ej);
-	if (lane == 0) out[d.out] = res;
+	if (lane == 0) {
+	    if (aln_out) aln_out[d.out] = res.aligned;
+	    else out[d.out] = res;
+	}
     }
 }
 
@@ -392,7 +397,23 @@ int icb_align32_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, c
     unsigned grid = unsigned((warps + AL_WARPS - 1) / AL_WARPS);
     ICB_LAUNCH(ctx, "align_dp32",
 	       icb_k_align32_dp<<<grid, AL_THREADS, 0, st>>>(d_seq, ws.d_descs, int(cnt), reinterpret_cast<uint4*>(ws.d_trace), ws.d_lines,
-							       k, ws.d_out, ws.d_ticket));
+							       k, ws.d_out, ws.d_ticket, nullptr, nullptr));
+    return ICB_OK;
+}
+
+// the same over a pair queue built on the device: *d_count descriptors (at most max_pairs), results (window counts) to
+// aln_out[desc.out]; the caller guarantees the workspace sizes (IcbDLoopState::tiles_cap / words_cap)
+int icb_align32_run_dev(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, const IcbPairDesc* d_descs, const int32_t* d_count,
+			int max_pairs, int k, int32_t* aln_out)
+{
+    if (max_pairs <= 0) return ICB_OK;
+    cudaStream_t st = ctx->stream;
+    ICB_CUDA(ctx, cudaMemsetAsync(ws.d_ticket, 0, 8, st));
+    int64_t warps = std::min<int64_t>(max_pairs, int64_t(ctx->sm_count) * 16);
+    unsigned grid = unsigned((warps + AL_WARPS - 1) / AL_WARPS);
+    ICB_LAUNCH(ctx, "align_dp32",
+	       icb_k_align32_dp<<<grid, AL_THREADS, 0, st>>>(d_seq, d_descs, 0, reinterpret_cast<uint4*>(ws.d_trace), ws.d_lines, k, nullptr,
+							       ws.d_ticket, d_count, aln_out));
     return ICB_OK;
 }
 

@@ -93,6 +93,11 @@ int icb_align16_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, c
 		    int64_t tiles, int64_t line_words, int max_m, int k);
 int icb_align32_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, const IcbPairDesc* descs, int64_t cnt,
 		    int64_t tiles, int64_t line_words, int k);
+// device-built pair queues (dloop.cu): *d_count descriptors in device memory, window counts to aln_out[desc.out]
+int icb_align16_run_dev(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, const IcbPairDesc* d_descs, const int32_t* d_count,
+			int max_pairs, int max_m, int k, int32_t* aln_out);
+int icb_align32_run_dev(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, const IcbPairDesc* d_descs, const int32_t* d_count,
+			int max_pairs, int k, int32_t* aln_out);
 // the dispatcher behind icb_align_pairs, on an explicit context (stream)
 int icb_align_pairs_on(icb_ctx* ctx, icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size,
 		       icb_align_result* results);

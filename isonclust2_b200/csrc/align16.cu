@@ -220,8 +220,9 @@ __device__ __forceinline__ void quad16(Lane16& S, const Pass16& P, int sl0, uint
 
 __global__ void __launch_bounds__(A16_THREADS, 4)
 icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, uint4* __restrict__ trace,
-		 uint32_t* __restrict__ lines, IcbAlignEnd* __restrict__ ends)
+		 uint32_t* __restrict__ lines, IcbAlignEnd* __restrict__ ends, const int32_t* __restrict__ n_pairs_dev)
 {
+    if (n_pairs_dev && int(blockIdx.x) >= *n_pairs_dev) return;  // device-built pair queue (dloop.cu): the grid is its capacity
     extern __shared__ uint32_t smW[];  // m + 1 words
     __shared__ uint2 s_ring[A16_WARPS * A16_RING];
     __shared__ int s_red[A16_WARPS * 2];
@@ -245,7 +246,7 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	    e.score = 0;
 	    e.ei = e.ej = 0;
 	    e.status = 1;
-	    ends[d.out] = e;
+	    ends[blockIdx.x] = e;
 	}
 	return;
     }
@@ -360,7 +361,7 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 		e.ej = m - 1;
 	    }
 	    e.status = 0;
-	    ends[d.out] = e;
+	    ends[blockIdx.x] = e;
 	}
     }
 }
@@ -373,14 +374,19 @@ constexpr int TB_WARPS = 4;
 __global__ void __launch_bounds__(TB_WARPS * 32)
 icb_k_align16_trace(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, int n_pairs,
 		    const uint4* __restrict__ trace, const IcbAlignEnd* __restrict__ ends, int k,
-		    icb_align_result* __restrict__ out)
+		    icb_align_result* __restrict__ out, const int32_t* __restrict__ n_pairs_dev, int32_t* __restrict__ aln_out)
 {
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * TB_WARPS + (threadIdx.x >> 5);
+    if (n_pairs_dev) n_pairs = *n_pairs_dev;
     if (p >= n_pairs) return;
     const IcbPairDesc d = descs[p];
-    const IcbAlignEnd en = ends[d.out];
+    const IcbAlignEnd en = ends[p];
     if (en.status != 0) {
+	if (aln_out) {
+	    if (lane == 0) aln_out[d.out] = -3;  // DL_ALN_REDO32: a character outside ACGT, the 32-bit kernel takes the pair
+	    return;
+	}
 	if (lane == 0) {
 	    icb_align_result r;
 	    r.aligned = r.score = r.end_query = r.end_ref = 0;
@@ -469,6 +475,10 @@ icb_k_align16_trace(const uint8_t* __restrict__ seq, const IcbPairDesc* __restri
 	}
     }
     if (pend) st.push(pa == pb ? 1u : 0u);
+    if (aln_out) {
+	if (lane == 0) aln_out[d.out] = st.pushed >= k ? st.aligned : 0;
+	return;
+    }
     if (lane == 0) {
 	icb_align_result r;
 	r.aligned = st.pushed >= k ? st.aligned : 0;
@@ -493,9 +503,26 @@ int icb_align16_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, c
     const size_t smem = size_t(max_m + 1) * 4;
     ICB_LAUNCH(ctx, "align_dp",
 	       icb_k_align16_dp<<<unsigned(cnt), A16_THREADS, smem, st>>>(d_seq, ws.d_descs, reinterpret_cast<uint4*>(ws.d_trace),
-									   reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends));
+									   reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends, nullptr));
     ICB_LAUNCH(ctx, "align_trace",
 	       icb_k_align16_trace<<<unsigned((cnt + TB_WARPS - 1) / TB_WARPS), TB_WARPS * 32, 0, st>>>(
-		   d_seq, ws.d_descs, int(cnt), reinterpret_cast<const uint4*>(ws.d_trace), ws.d_ends, k, ws.d_out));
+		   d_seq, ws.d_descs, int(cnt), reinterpret_cast<const uint4*>(ws.d_trace), ws.d_ends, k, ws.d_out, nullptr, nullptr));
+    return ICB_OK;
+}
+
+// the same over a pair queue built on the device: *d_count descriptors (at most max_pairs = the grid), window counts to
+// aln_out[desc.out] (-3 where the packed kernel refused the pair); the caller guarantees the workspace sizes
+int icb_align16_run_dev(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, const IcbPairDesc* d_descs, const int32_t* d_count,
+			int max_pairs, int max_m, int k, int32_t* aln_out)
+{
+    if (max_pairs <= 0) return ICB_OK;
+    cudaStream_t st = ctx->stream;
+    const size_t smem = size_t(max_m + 1) * 4;
+    ICB_LAUNCH(ctx, "align_dp",
+	       icb_k_align16_dp<<<unsigned(max_pairs), A16_THREADS, smem, st>>>(d_seq, d_descs, reinterpret_cast<uint4*>(ws.d_trace),
+										 reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends, d_count));
+    ICB_LAUNCH(ctx, "align_trace",
+	       icb_k_align16_trace<<<unsigned((max_pairs + TB_WARPS - 1) / TB_WARPS), TB_WARPS * 32, 0, st>>>(
+		   d_seq, d_descs, 0, reinterpret_cast<const uint4*>(ws.d_trace), ws.d_ends, k, nullptr, d_count, aln_out));
     return ICB_OK;
 }

@@ -25,6 +25,7 @@
 #include <thread>
 
 #include "align.cuh"
+#include "dloop.cuh"
 #include "index.cuh"
 #include "helpers.h"
 #include "ref_order.h"
@@ -111,18 +112,48 @@ struct icb_clusterer {
     int64_t h_cands_cap = 0;
     int64_t* h_off = nullptr;	 // chunk_cap + 1
 
+    // device-resident loop (dloop.cu): the chunk's records, pools and work queues
+    bool use_dloop = true;
+    IcbDLoopView V{};
+    IcbQueryHeader* d_hdr_full = nullptr;
+    int32_t* d_n_ins = nullptr;
+    uint32_t cand_cap = 0;
+    unsigned long long full_cap = 0;
+    IcbDLoopState* h_state = nullptr;  // pinned
+    int32_t* h_out = nullptr;	       // pinned: 3 * chunk_cap (cluster, strand, founder positions)
+    double rounds_avg = 3.0;
+
     int init_buffers();
     void free_buffers();
+    int init_dloop();
+    void free_dloop();
+    int grow_cand_pool(uint32_t want);
+    int grow_full_pool(unsigned long long want);
+    int ensure_founder_cap(int64_t n);
+    int plan_query(int Ctot, int cap, int mode, IcbQueryArgs& a, int n_items_max, int& n_blocks, size_t& smem_bytes);
+    int process_chunk_device(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of, int32_t* strand_of,
+			     bool& handled);
     int reset();
     int seed(const int32_t* rep_reads, int64_t n);
     int update_representative(int32_t cluster, int32_t rep_read);
 
     int ensure_scratch(int64_t words);
     int ensure_cands(int64_t n);
+    int ensure_cands_host(int64_t n);
     int query(const std::vector<int32_t>& chunk, int C0, const std::vector<int32_t>* list, int mode, int cap,
 	      const std::vector<int32_t>* live);
     int upload_founders(int64_t from);
     int process_chunk(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of, int32_t* strand_of);
+    // the device-resident loop; the host loop takes the chunks it hands back
+    int run_chunk(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of, int32_t* strand_of)
+    {
+	bool handled = false;
+	if (use_dloop) {
+	    int rc = process_chunk_device(chunk, slots, cluster_of, strand_of, handled);
+	    if (rc) return rc;
+	}
+	return handled ? ICB_OK : process_chunk(chunk, slots, cluster_of, strand_of);
+    }
 };
 
 int icb_clusterer::ensure_scratch(int64_t words)
@@ -135,6 +166,21 @@ int icb_clusterer::ensure_scratch(int64_t words)
     const int64_t want = words + words / 2;  // geometric: the index grows with every chunk
     ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_scratch, size_t(want) * 4));
     scratch_words = want;
+    return ICB_OK;
+}
+
+// pinned mirror only (pool-mode results are copied from the candidate pool)
+int icb_clusterer::ensure_cands_host(int64_t n)
+{
+    if (n > h_cands_cap) {
+	ICB_CUDA(ctx, ctx->wait());
+	cudaFreeHost(h_cands);
+	h_cands = nullptr;
+	h_cands_cap = 0;
+	const int64_t want = std::max<int64_t>(n + n / 2, 1 << 16);
+	ICB_CUDA(ctx, cudaMallocHost((void**)&h_cands, size_t(want) * sizeof(IcbCand)));
+	h_cands_cap = want;
+    }
     return ICB_OK;
 }
 
@@ -179,12 +225,104 @@ int icb_clusterer::init_buffers()
     if (rc) return rc;
     rc = chunk_idx.create(ctx, 1u << 18, 1 << 17);
     if (rc) return rc;
+    rc = init_dloop();
+    if (rc) return rc;
     ICB_CUDA(ctx, ctx->wait());
+    return ICB_OK;
+}
+
+// buffers of the device-resident loop; also used by the host loop for reads with more relevant candidates than its
+// fixed per-read capacity (pool-mode query)
+int icb_clusterer::init_dloop()
+{
+    const int cs = chunk_cap;
+    const int mw = (cs + 31) / 32;
+    static const bool off = getenv("ICB_HOST_LOOP") != nullptr;
+    use_dloop = !off && mw <= DL_MAXW;
+    V = IcbDLoopView{};
+    V.mw = mw;
+    auto dm = [&](void** p, size_t bytes) { return icb_dmalloc(ctx, p, bytes); };
+    ICB_CUDA(ctx, dm((void**)&V.st, sizeof(IcbDLoopState)));
+    ICB_CUDA(ctx, dm((void**)&V.hdr, sizeof(IcbQueryHeader) * cs));
+    ICB_CUDA(ctx, dm((void**)&d_hdr_full, sizeof(IcbQueryHeader) * cs));
+    ICB_CUDA(ctx, dm((void**)&V.founder_cls, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.outcome, cs));
+    ICB_CUDA(ctx, dm((void**)&V.flags, cs));
+    ICB_CUDA(ctx, dm((void**)&V.dec_cls, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.dec_strand, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.aln_calls, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.plan_n, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.plan_i, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.need_slot, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.full_off, 8 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.full_n, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.depmask, size_t(4) * cs * mw));
+    ICB_CUDA(ctx, dm((void**)&V.seenmask, size_t(4) * cs * mw));
+    ICB_CUDA(ctx, dm((void**)&V.out_cls, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.out_strand, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.founder_pos, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.descs16, sizeof(IcbPairDesc) * cs));
+    ICB_CUDA(ctx, dm((void**)&V.descs32, sizeof(IcbPairDesc) * cs));
+    ICB_CUDA(ctx, dm((void**)&V.full_list, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.full_list_off, 8 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.ins_reads, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.ins_ids, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&d_n_ins, 16));
+    ICB_CUDA(ctx, cudaMallocHost((void**)&h_state, sizeof(IcbDLoopState)));
+    ICB_CUDA(ctx, cudaMallocHost((void**)&h_out, sizeof(int32_t) * 3 * cs));
+    cand_cap = 0;
+    full_cap = 0;
+    int rc = grow_cand_pool(uint32_t(cs) * 256u);
+    if (rc) return rc;
+    if (use_dloop) rc = grow_full_pool((unsigned long long)cs * 4096ull);
+    return rc;
+}
+
+void icb_clusterer::free_dloop()
+{
+    void* ps[] = {V.st, V.hdr, d_hdr_full, V.founder_cls, V.outcome, V.flags, V.dec_cls, V.dec_strand, V.aln_calls, V.plan_n, V.plan_i,
+		  V.need_slot, V.full_off, V.full_n, V.depmask, V.seenmask, V.out_cls, V.out_strand, V.founder_pos, V.descs16, V.descs32,
+		  V.full_list, V.full_list_off, V.ins_reads, V.ins_ids, d_n_ins, V.cands, V.aln, V.plan, V.full};
+    for (void* p : ps) icb_dfree(ctx, p);
+    cudaFreeHost(h_state);
+    cudaFreeHost(h_out);
+    V = IcbDLoopView{};
+    h_state = nullptr;
+    h_out = nullptr;
+}
+
+int icb_clusterer::grow_cand_pool(uint32_t want)
+{
+    if (want <= cand_cap) return ICB_OK;
+    ICB_CUDA(ctx, ctx->wait());
+    icb_dfree(ctx, V.cands);
+    icb_dfree(ctx, V.aln);
+    icb_dfree(ctx, V.plan);
+    V.cands = nullptr;
+    V.aln = V.plan = nullptr;
+    cand_cap = 0;
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&V.cands, sizeof(IcbCand) * size_t(want)));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&V.aln, 4 * size_t(want)));
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&V.plan, 4 * size_t(want)));
+    cand_cap = want;
+    return ICB_OK;
+}
+
+int icb_clusterer::grow_full_pool(unsigned long long want)
+{
+    if (want <= full_cap) return ICB_OK;
+    ICB_CUDA(ctx, ctx->wait());
+    icb_dfree(ctx, V.full);
+    V.full = nullptr;
+    full_cap = 0;
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&V.full, sizeof(IcbCand) * size_t(want)));
+    full_cap = want;
     return ICB_OK;
 }
 
 void icb_clusterer::free_buffers()
 {
+    free_dloop();
     main_idx.destroy();
     chunk_idx.destroy();
     icb_dfree(ctx, d_nmax);
@@ -210,9 +348,64 @@ int icb_clusterer::reset()
     return main_idx.clear();
 }
 
-// one query launch over (a subset of) the chunk; results land in the pinned mirrors h_hdr / h_cands.
+// common part of every query launch: read set, indices, parameters
+static void query_base(icb_clusterer* cl, IcbQueryArgs& a, int n_chunk, int C0)
+{
+    icb_readset* rs = cl->rs;
+    a = IcbQueryArgs{};
+    a.arena = rs->d_mins;
+    a.min_off = rs->d_min_off;
+    a.nf = rs->d_nf;
+    a.nr = rs->d_nr;
+    a.hpc_len = rs->d_hpc_len;
+    a.read_class = rs->d_class;
+    a.chunk_reads = cl->d_chunk_reads;
+    a.n_chunk = n_chunk;
+    a.main_idx = cl->main_idx.v;
+    a.chunk_idx = cl->chunk_idx.v;
+    a.C0 = C0;
+    a.cls_founder = cl->d_cls_founder;
+    a.nmax = cl->d_nmax;
+    a.min_shared = cl->P.min_shared;
+    a.min_frac = cl->P.min_fraction;
+}
+
+// shared-memory / global-scratch plan of one query launch: dense counters (Ctot words) + candidate list (2*cap, mode 0
+// only) + bitmaps in shared memory when they fit, the counters (and mode 1's first-hit table) in per-CTA global scratch
+// otherwise
+int icb_clusterer::plan_query(int Ctot, int cap, int mode, IcbQueryArgs& a, int n_items_max, int& n_blocks, size_t& smem_bytes)
+{
+    const int bw = (rs->max_m + 31) / 32;
+    const int bmWords = std::max(bw, 1024);
+    int64_t words_smem = int64_t(Ctot) + 2 * int64_t(cap) + bmWords;
+    const int64_t smem_limit_words = (200 * 1024) / 4;
+    n_blocks = std::min(n_items_max, ctx->sm_count * 8);
+    a.smem_cnt = words_smem <= smem_limit_words;
+    int64_t stride = 0;
+    if (!a.smem_cnt) {
+	words_smem = 2 * int64_t(cap) + bmWords;
+	stride += Ctot;
+    }
+    if (mode == 1) stride += 2 * int64_t(Ctot);
+    if (words_smem > smem_limit_words) return ctx->fail(ICB_ERR_ARG, "a read has too many minimizers for the candidate query");
+    a.cap = cap;
+    a.mode = mode;
+    a.smem_words = int32_t(words_smem);
+    a.g_stride = stride;
+    a.g_scratch = nullptr;
+    if (stride > 0) {
+	int rc = ensure_scratch(stride * n_blocks);
+	if (rc) return rc;
+	a.g_scratch = d_scratch;
+    }
+    smem_bytes = size_t(words_smem) * 4;
+    return ICB_OK;
+}
+
+// one query launch of the HOST loop over (a subset of) the chunk; results land in the pinned mirrors h_hdr / h_cands.
 // mode 0: `cap` records per item at item*cap.  mode 1: item t at h_off[t], sized by `live` (the n_total a mode-0
-// query reported for that read).
+// query reported for that read).  mode 2: the relevant candidates of the listed reads without a per-read capacity
+// (pool-mode query): item t at h_hdr[t].cand_off, h_hdr[t].n_cand records; `live` = the n_rel_all a mode-0 query reported.
 int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::vector<int32_t>* list, int mode, int cap,
 			 const std::vector<int32_t>* live)
 {
@@ -221,17 +414,8 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
     const int n_items = list ? int(list->size()) : n_chunk;
     if (n_items == 0) return ICB_OK;
     const int Ctot = C0 + n_chunk;
-    IcbQueryArgs a{};
-    a.arena = rs->d_mins;
-    a.min_off = rs->d_min_off;
-    a.nf = rs->d_nf;
-    a.nr = rs->d_nr;
-    a.hpc_len = rs->d_hpc_len;
-    a.read_class = rs->d_class;
-    a.chunk_reads = d_chunk_reads;
-    a.n_chunk = n_chunk;
-    a.list = nullptr;
-    a.n_list = 0;
+    IcbQueryArgs a;
+    query_base(this, a, n_chunk, C0);
     if (list) {
 	int32_t* h_list = h_i32 + 2 * chunk_cap;
 	memcpy(h_list, list->data(), sizeof(int32_t) * n_items);
@@ -239,17 +423,7 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
 	a.list = d_list;
 	a.n_list = n_items;
     }
-    a.main_idx = main_idx.v;
-    a.chunk_idx = chunk_idx.v;
-    a.C0 = C0;
-    a.cls_founder = d_cls_founder;
-    a.nmax = d_nmax;
-    a.min_shared = P.min_shared;
-    a.min_frac = P.min_fraction;
-    a.cap = cap;
-    a.mode = mode;
     a.hdr = d_hdr;
-    a.full_off = nullptr;
     int64_t n_records;
     if (mode == 1) {
 	h_off[0] = 0;
@@ -258,38 +432,38 @@ int icb_clusterer::query(const std::vector<int32_t>& chunk, int C0, const std::v
 	ICB_CUDA(ctx, cudaMemcpyAsync(d_full_off, h_off, sizeof(int64_t) * n_items, cudaMemcpyHostToDevice, st));
 	a.full_off = d_full_off;
     }
+    else if (mode == 2) {
+	n_records = 0;
+	for (int i = 0; i < n_items; i++) {
+	    if ((*live)[i] > 32767) return ctx->fail(ICB_ERR_ARG, "a read has more than 32767 candidate clusters within minFraction of its best");
+	    n_records += (*live)[i];
+	}
+	int rc = grow_cand_pool(uint32_t(std::min<int64_t>(n_records + n_records / 2 + 1024, 0xfffffff0ll)));
+	if (rc) return rc;
+	if (n_records > int64_t(cand_cap)) return ctx->fail(ICB_ERR_NOMEM, "candidate pool too large");
+	rc = icb_dl_init(ctx, V, n_chunk, C0, cand_cap, full_cap, 0, 0);
+	if (rc) return rc;
+	a.dl_state = V.st;
+	a.dl_pool = V.cands;
+	a.dl_pool_aln = V.aln;
+	a.dl_depmask = V.depmask;
+	a.dl_mw = V.mw;
+	cap = 0;
+    }
     else
 	n_records = int64_t(n_items) * cap;
-    int rc = ensure_cands(std::max<int64_t>(n_records, 1));
+    int rc = mode == 2 ? ensure_cands_host(std::max<int64_t>(n_records, 1)) : ensure_cands(std::max<int64_t>(n_records, 1));
     if (rc) return rc;
     a.cands = d_cands;
-    // shared memory plan: dense counters (Ctot words) + candidate list (2*cap) + bitmaps
-    const int bw = (rs->max_m + 31) / 32;
-    const int bmWords = std::max(bw, 1024);
-    int64_t words_smem = int64_t(Ctot) + 2 * cap + bmWords;
-    const int64_t smem_limit_words = (200 * 1024) / 4;
-    int n_blocks = std::min(n_items, ctx->sm_count * 8);
-    a.smem_cnt = words_smem <= smem_limit_words;
-    int64_t stride = 0;
-    if (!a.smem_cnt) {
-	words_smem = 2 * cap + bmWords;
-	stride += Ctot;
-    }
-    if (mode == 1) stride += 2 * int64_t(Ctot);
-    if (words_smem > smem_limit_words) return ctx->fail(ICB_ERR_ARG, "a read has too many minimizers for the candidate query");
-    a.smem_words = int32_t(words_smem);
-    a.g_stride = stride;
-    a.g_scratch = nullptr;
-    if (stride > 0) {
-	rc = ensure_scratch(stride * n_blocks);
-	if (rc) return rc;
-	a.g_scratch = d_scratch;
-    }
-    rc = icb_query_launch(ctx, a, n_blocks, size_t(words_smem) * 4);
+    int n_blocks;
+    size_t smem_bytes;
+    rc = plan_query(Ctot, cap, mode, a, n_items, n_blocks, smem_bytes);
+    if (rc) return rc;
+    rc = icb_query_launch(ctx, a, n_blocks, smem_bytes);
     if (rc) return rc;
     ICB_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, sizeof(IcbQueryHeader) * n_items, cudaMemcpyDeviceToHost, st));
     if (n_records > 0)
-	ICB_CUDA(ctx, cudaMemcpyAsync(h_cands, d_cands, sizeof(IcbCand) * n_records, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(h_cands, mode == 2 ? V.cands : d_cands, sizeof(IcbCand) * n_records, cudaMemcpyDeviceToHost, st));
     ICB_CUDA(ctx, ctx->wait());
     return ICB_OK;
 }
@@ -353,22 +527,31 @@ int icb_clusterer::update_representative(int32_t cluster, int32_t rep_read)
     return ICB_OK;
 }
 
+// room for n entries in the device table cluster -> representative read (the first founder.size() entries are kept)
+int icb_clusterer::ensure_founder_cap(int64_t n)
+{
+    if (n <= cls_founder_cap) return ICB_OK;
+    cudaStream_t st = ctx->stream;
+    const int64_t keep = std::min<int64_t>(int64_t(founder.size()), cls_founder_cap);
+    const int64_t ncap = std::max<int64_t>(cls_founder_cap * 2, n + 4096);
+    int32_t* nd = nullptr;
+    ICB_CUDA(ctx, ctx->wait());
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&nd, sizeof(int32_t) * ncap));
+    if (keep > 0) ICB_CUDA(ctx, cudaMemcpyAsync(nd, d_cls_founder, sizeof(int32_t) * keep, cudaMemcpyDeviceToDevice, st));
+    ICB_CUDA(ctx, ctx->wait());
+    icb_dfree(ctx, d_cls_founder);
+    d_cls_founder = nd;
+    cls_founder_cap = ncap;
+    return ICB_OK;
+}
+
 // device copy of founder[from..]
 int icb_clusterer::upload_founders(int64_t from)
 {
     cudaStream_t st = ctx->stream;
     const int64_t n = int64_t(founder.size());
-    if (n > cls_founder_cap) {
-	const int64_t ncap = std::max<int64_t>(cls_founder_cap * 2, n + 4096);
-	int32_t* nd = nullptr;
-	ICB_CUDA(ctx, ctx->wait());
-	ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&nd, sizeof(int32_t) * ncap));
-	if (from > 0) ICB_CUDA(ctx, cudaMemcpyAsync(nd, d_cls_founder, sizeof(int32_t) * from, cudaMemcpyDeviceToDevice, st));
-	ICB_CUDA(ctx, ctx->wait());
-	icb_dfree(ctx, d_cls_founder);
-	d_cls_founder = nd;
-	cls_founder_cap = ncap;
-    }
+    int rc = ensure_founder_cap(n);
+    if (rc) return rc;
     int32_t* stage = h_i32 + 2 * chunk_cap;
     for (int64_t done = from; done < n; done += chunk_cap) {
 	const int64_t cnt = std::min<int64_t>(chunk_cap, n - done);
@@ -423,11 +606,16 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 	else cl[i].assign(h_cands + int64_t(i) * CAP, h_cands + int64_t(i) * CAP + hdr[i].n_cand);
     }
     if (!over.empty()) {
-	const int cap2 = 2 * (C0 + N);
-	rc = query(chunk, C0, &over, 0, cap2, nullptr);
+	// more relevant candidates than the fixed per-read capacity: asked again through the pool-mode query, which sizes
+	// every read's list by what the first pass counted
+	std::vector<int32_t> want(over.size());
+	for (size_t t = 0; t < over.size(); t++) want[t] = hdr[over[t]].n_rel_all;
+	rc = query(chunk, C0, &over, 2, 0, &want);
 	if (rc) return rc;
-	for (size_t t = 0; t < over.size(); t++)
-	    cl[over[t]].assign(h_cands + int64_t(t) * cap2, h_cands + int64_t(t) * cap2 + h_hdr[t].n_cand);
+	for (size_t t = 0; t < over.size(); t++) {
+	    if (h_hdr[t].overflow) return ctx->fail(ICB_ERR_STATE, "candidate pool overflow");
+	    cl[over[t]].assign(h_cands + h_hdr[t].cand_off, h_cands + h_hdr[t].cand_off + h_hdr[t].n_cand);
+	}
     }
 
     stats.ms_query += sw.lap();
@@ -864,6 +1052,186 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
     return ICB_OK;
 }
 
+// One chunk through the device-resident loop (dloop.cu).  The host enqueues the chunk's kernels — chunk index, pool-mode
+// query, then rounds of commit / decide / gather / full lists / alignments — and reads one state block back per batch of
+// rounds; nothing of the chunk is decided on the host.  handled = false: the device loop met a case it leaves to the host
+// loop (a read with more candidates than its shared-memory plan, a hit map that would rehash, a pool that was too small
+// and has been enlarged for the next chunks) and nothing of the chunk has been applied.
+int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of,
+					int32_t* strand_of, bool& handled)
+{
+    handled = false;
+    cudaStream_t st = ctx->stream;
+    const int N = int(chunk.size());
+    const int C0 = int(founder.size());
+    const int Ctot = C0 + N;
+    const int k = P.kmer_size;
+    Stopwatch sw;
+    // ---- capacities that may reallocate (and synchronise) before anything of the chunk is queued
+    int rc = ensure_founder_cap(Ctot);
+    if (rc) return rc;
+    int64_t tot = 0;
+    for (int i = 0; i < N; i++) tot += rs->h_nf[chunk[i]];
+    rc = main_idx.reserve(tot);
+    if (rc) return rc;
+    if (!ctx->align_ws) ctx->align_ws = new IcbAlignWorkspace;
+    IcbAlignWorkspace& ws = *ctx->align_ws;
+    {
+	// trace arena of this stream: room for the largest pair of the read set at least, a few hundred average pairs by default
+	static const size_t trace_mb = getenv("ICB_DLOOP_TRACE_MB") ? size_t(atol(getenv("ICB_DLOOP_TRACE_MB"))) : 256;
+	const size_t L = size_t(std::max<int64_t>(rs->max_len, 64));
+	const size_t one = ((L + 7) / 8) * ((L + 71) / 8 + 1) * 32 + 4096;
+	const size_t lines_one = (4 * L + 64) * 4;
+	rc = ws.ensure(ctx, std::max(trace_mb << 20, one), std::max(lines_one * size_t(N), size_t(4) << 20), 2 * int64_t(N) + 16);
+	if (rc) return rc;
+    }
+    const unsigned long long tiles_cap = ws.trace_bytes / 32 - 4, words_cap = ws.lines_bytes / 4 - 32;
+    IcbQueryArgs qa, qf;
+    int nb_a, nb_f;
+    size_t smem_a, smem_f;
+    query_base(this, qa, N, C0);
+    rc = plan_query(Ctot, 0, 2, qa, N, nb_a, smem_a);
+    if (rc) return rc;
+    qa.hdr = V.hdr;
+    qa.dl_state = V.st;
+    qa.dl_pool = V.cands;
+    qa.dl_pool_aln = V.aln;
+    qa.dl_depmask = V.depmask;
+    qa.dl_mw = V.mw;
+    query_base(this, qf, N, C0);
+    rc = plan_query(Ctot, 0, 1, qf, N, nb_f, smem_f);  // same scratch block as the pool-mode plan: the two never overlap in time
+    if (rc) return rc;
+    if (qa.g_stride > 0) qa.g_scratch = d_scratch;  // the second plan may have enlarged (moved) the scratch block
+    qf.g_scratch = d_scratch;
+    qf.hdr = d_hdr_full;
+    qf.list = V.full_list;
+    qf.dl_n_list = &V.st->n_full;
+    qf.full_off = V.full_list_off;
+    qf.cands = V.full;
+    qf.dl_depmask = V.depmask;
+    qf.dl_mw = V.mw;
+    qf.dl_full_off = V.full_off;
+    qf.dl_full_n = V.full_n;
+    // the view's per-run pointers
+    V.chunk_reads = d_chunk_reads;
+    V.offs = rs->d_offs;
+    V.raw_err = rs->d_err;
+    V.hpc_len = rs->d_hpc_len;
+    V.nf = rs->d_nf;
+    V.nr = rs->d_nr;
+    V.bkt = rs->d_bkt;
+    V.cls_founder = d_cls_founder;
+    V.mode = P.mode;
+    V.min_shared = P.min_shared;
+    V.k = k;
+    V.min_frac = P.min_fraction;
+    V.mapped_th = P.mapped_threshold;
+    V.aligned_th = P.aligned_threshold;
+    static const int force = getenv("ICB_DLOOP_FORCE_FALLBACK") ? atoi(getenv("ICB_DLOOP_FORCE_FALLBACK")) : 0;
+    V.force_fallback = force;
+    // ---- chunk index: every read of the chunk as a provisional founder (id = C0 + position)
+    for (int i = 0; i < N; i++) {
+	h_i32[i] = chunk[i];
+	h_i32[chunk_cap + i] = C0 + i;
+    }
+    ICB_CUDA(ctx, cudaMemcpyAsync(d_chunk_reads, h_i32, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    ICB_CUDA(ctx, cudaMemcpyAsync(d_ids, h_i32 + chunk_cap, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+    rc = chunk_idx.clear();
+    if (rc) return rc;
+    rc = chunk_idx.reserve(tot);
+    if (rc) return rc;
+    qa.chunk_idx = qf.chunk_idx = chunk_idx.v;
+    qa.main_idx = qf.main_idx = main_idx.v;
+    rc = icb_index_insert(ctx, chunk_idx, rs, d_chunk_reads, d_ids, N);
+    if (rc) return rc;
+    chunk_idx.nodes_upper = tot;
+    // ---- candidates of every read, first decisions
+    rc = icb_dl_init(ctx, V, N, C0, cand_cap, full_cap, tiles_cap, words_cap);
+    if (rc) return rc;
+    rc = icb_query_launch(ctx, qa, nb_a, smem_a);
+    if (rc) return rc;
+    rc = icb_dl_decide(ctx, V, N);
+    if (rc) return rc;
+    const int max_m = int(std::min<int64_t>(rs->max_len, 8000));
+    int enqueued = 0;
+    for (;;) {
+	const int R = std::max(2, std::min(16, int(rounds_avg + 1.5) - enqueued));
+	for (int q = 0; q < R; q++) {
+	    rc = icb_dl_commit(ctx, V);
+	    if (rc) return rc;
+	    rc = icb_dl_decide(ctx, V, N);
+	    if (rc) return rc;
+	    rc = icb_dl_gather(ctx, V, N);
+	    if (rc) return rc;
+	    rc = icb_query_launch(ctx, qf, nb_f, smem_f);
+	    if (rc) return rc;
+	    if (P.mode != 1) {
+		rc = icb_align16_run_dev(ctx, ws, rs->d_seq, V.descs16, &V.st->n_pairs16, N, max_m, k, V.aln);
+		if (rc) return rc;
+		// pairs the packed kernel cannot take (longer than 8000, or refused for a character outside ACGT)
+		rc = icb_align32_run_dev(ctx, ws, rs->d_seq, V.descs32, &V.st->n_pairs32, N, k, V.aln);
+		if (rc) return rc;
+	    }
+	}
+	enqueued += R;
+	rc = icb_dl_commit(ctx, V);  // a last walk, so that a chunk whose work is complete ends in this batch of rounds
+	if (rc) return rc;
+	rc = icb_dl_finalize(ctx, V, d_n_ins);
+	if (rc) return rc;
+	rc = icb_index_insert_dev(ctx, main_idx, rs, V.ins_reads, V.ins_ids, d_n_ins, N);
+	if (rc) return rc;
+	ICB_CUDA(ctx, cudaMemcpyAsync(h_state, V.st, sizeof(IcbDLoopState), cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(h_out, V.out_cls, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(h_out + chunk_cap, V.out_strand, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(h_out + 2 * chunk_cap, V.founder_pos, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, ctx->wait());
+	if (h_state->fallback || h_state->done == 2) break;
+	if (enqueued > 64 * N + 1024) return ctx->fail(ICB_ERR_STATE, "device loop made no progress");
+    }
+    stats.ms_align += sw.lap();
+    if (h_state->fallback) {
+	stats.dl_fallback_chunks++;
+	if (h_state->fallback == DL_FB_POOL) {
+	    rc = grow_cand_pool(uint32_t(std::min<uint64_t>(uint64_t(cand_cap) * 4, 0xfffffff0ull)));
+	    if (rc) return rc;
+	}
+	if (h_state->fallback == DL_FB_FULLPOOL) {
+	    rc = grow_full_pool(full_cap * 4);
+	    if (rc) return rc;
+	}
+	return ICB_OK;	// handled stays false: nothing was applied (the founders' insert is skipped unless the chunk finished)
+    }
+    // ---- apply
+    const IcbDLoopState& S = *h_state;
+    rounds_avg = 0.75 * rounds_avg + 0.25 * double(S.rounds);
+    for (int i = 0; i < N; i++) {
+	cluster_of[slots[i]] = h_out[i];
+	strand_of[slots[i]] = h_out[chunk_cap + i];
+    }
+    int64_t ftot = 0;
+    for (int i = 0; i < S.n_founders; i++) {
+	const int32_t r = chunk[h_out[2 * chunk_cap + i]];
+	founder.push_back(r);
+	ftot += rs->h_nf[r];
+    }
+    main_idx.nodes_upper += ftot;
+    stats.chunks++;
+    stats.dl_chunks++;
+    stats.rounds += S.rounds;
+    stats.reads_queried += N;
+    stats.aln_invoked += S.aln_invoked;
+    stats.aln_calls_ref += S.aln_calls_ref;
+    stats.pairs_aligned += S.pairs_aligned;
+    stats.cells_aligned += S.cells_aligned;
+    stats.tie_fallbacks += S.tie_fallbacks;
+    stats.decisions += S.decisions;
+    stats.order_calls += S.order_calls;
+    stats.hits += S.hits;
+    stats.cands += S.cands;
+    handled = true;
+    return ICB_OK;
+}
+
 // per-read scalars the greedy loop reads on the host + the device error classes: once per read set
 int icb_readset_prepare_host(icb_readset* rs)
 {
@@ -886,11 +1254,29 @@ int icb_readset_prepare_host(icb_readset* rs)
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_err.data(), rs->d_err, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     }
     if (!rs->d_class) ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&rs->d_class, n + 16));
+    if (!rs->d_bkt) ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&rs->d_bkt, sizeof(uint32_t) * (n + 16)));
     int rc0 = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, rs->d_class);
     if (rc0) return rc0;
     ICB_CUDA(ctx, ctx->wait());
     rs->max_m = 0;
     for (int64_t i = 0; i < n; i++) rs->max_m = std::max(rs->max_m, std::max(rs->h_nf[i], rs->h_nr[i]));
+    // bucket count of the reference's hit map per read: unordered_map(20 * (|mins| + |revMins|)) (minimizer.cpp:48) asks the
+    // HOST libstdc++ for the next prime; the device loop's candidate-order emulation reads it from this table
+    {
+	rs->h_bkt.resize(size_t(n));
+	std::__detail::_Prime_rehash_policy pol;
+	size_t last_hint = ~size_t(0), last_bkt = 0;
+	for (int64_t i = 0; i < n; i++) {
+	    const size_t hint = 20 * (size_t(rs->h_nf[i]) + size_t(rs->h_nr[i]));
+	    if (hint != last_hint) {
+		last_hint = hint;
+		last_bkt = pol._M_next_bkt(hint);
+	    }
+	    rs->h_bkt[size_t(i)] = uint32_t(std::min<size_t>(last_bkt, 0xffffffffu));
+	}
+	if (n) ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_bkt, rs->h_bkt.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, ctx->wait());
+    }
     rs->host_ready = true;
     return ICB_OK;
 }
@@ -955,6 +1341,17 @@ static int clusterer_rebind(icb_clusterer* cl, icb_readset* rs, const icb_cluste
     memcpy(cl->h_i32 + 3 * cl->chunk_cap, cl->nmax, sizeof(int32_t) * 225);
     ICB_CUDA(ctx, cudaMemcpyAsync(cl->d_nmax, cl->h_i32 + 3 * cl->chunk_cap, sizeof(int32_t) * 225, cudaMemcpyHostToDevice, ctx->stream));
     return cl->reset();
+}
+
+// sums of the additive counters and timers (ms_batch_max / ms_wall are set by the caller)
+static void add_stats(icb_cluster_stats& t, const icb_cluster_stats& s)
+{
+    t.chunks += s.chunks; t.rounds += s.rounds; t.reads_queried += s.reads_queried; t.aln_invoked += s.aln_invoked;
+    t.pairs_aligned += s.pairs_aligned; t.cells_aligned += s.cells_aligned; t.tie_fallbacks += s.tie_fallbacks;
+    t.decisions += s.decisions; t.ms_query += s.ms_query; t.ms_full += s.ms_full; t.ms_align += s.ms_align;
+    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host; t.ms_cpu += s.ms_cpu; t.ms_order += s.ms_order; t.order_calls += s.order_calls;
+    t.aln_calls_ref += s.aln_calls_ref; t.hyp_decisions += s.hyp_decisions; t.hits += s.hits; t.cands += s.cands;
+    t.dl_chunks += s.dl_chunks; t.dl_fallback_chunks += s.dl_fallback_chunks;
 }
 
 void icb_worker_pool_release(icb_ctx* ctx)
@@ -1071,13 +1468,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 			(long long)q.decisions, (long long)q.order_calls, cl->founder.size());
 	    }
 	    if (n_clusters) n_clusters[b] = int64_t(cl->founder.size());
-	    const icb_cluster_stats& s = cl->stats;
-	    icb_cluster_stats& t = wstats[w];
-	    t.chunks += s.chunks; t.rounds += s.rounds; t.reads_queried += s.reads_queried; t.aln_invoked += s.aln_invoked;
-	    t.pairs_aligned += s.pairs_aligned; t.cells_aligned += s.cells_aligned; t.tie_fallbacks += s.tie_fallbacks;
-	    t.decisions += s.decisions; t.ms_query += s.ms_query; t.ms_full += s.ms_full; t.ms_align += s.ms_align;
-	    t.ms_insert += s.ms_insert; t.ms_host += s.ms_host; t.ms_cpu += s.ms_cpu; t.ms_order += s.ms_order; t.order_calls += s.order_calls;
-		t.aln_calls_ref += s.aln_calls_ref; t.hyp_decisions += s.hyp_decisions;
+	    add_stats(wstats[w], cl->stats);
 	}
 	if (rc) {
 	    int z = 0;
@@ -1094,13 +1485,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
     for (int w = 0; w < nw; w++) {
 	if (stats) {
 	    const icb_cluster_stats& s = wstats[w];
-	    stats->chunks += s.chunks; stats->rounds += s.rounds; stats->reads_queried += s.reads_queried;
-	    stats->aln_invoked += s.aln_invoked; stats->pairs_aligned += s.pairs_aligned; stats->cells_aligned += s.cells_aligned;
-	    stats->tie_fallbacks += s.tie_fallbacks; stats->decisions += s.decisions; stats->ms_query += s.ms_query;
-	    stats->ms_full += s.ms_full; stats->ms_align += s.ms_align; stats->ms_insert += s.ms_insert; stats->ms_host += s.ms_host;
-	    stats->ms_cpu += s.ms_cpu; stats->ms_order += s.ms_order; stats->order_calls += s.order_calls;
-	    stats->aln_calls_ref += s.aln_calls_ref;
-	    stats->hyp_decisions += s.hyp_decisions;
+	    add_stats(*stats, s);
 	    stats->ms_batch_max = std::max(stats->ms_batch_max, s.ms_batch_max);
 	}
 	icb_ctx_fold_child(ctx, ctx->pool_ctx[w]);  // the worker's kernel timers and launch count -> parent
@@ -1143,14 +1528,14 @@ int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_
 	chunk.push_back(r);
 	slots.push_back(s);
 	if (int(chunk.size()) == cl->chunk_cap) {
-	    int rc = cl->process_chunk(chunk, slots, cluster_of, strand_of);
+	    int rc = cl->run_chunk(chunk, slots, cluster_of, strand_of);
 	    if (rc) return rc;
 	    chunk.clear();
 	    slots.clear();
 	}
     }
     if (!chunk.empty()) {
-	int rc = cl->process_chunk(chunk, slots, cluster_of, strand_of);
+	int rc = cl->run_chunk(chunk, slots, cluster_of, strand_of);
 	if (rc) return rc;
     }
     return ICB_OK;

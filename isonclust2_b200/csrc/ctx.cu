@@ -5,6 +5,10 @@
 #include <initializer_list>
 #include <mutex>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include "align.cuh"
 
 int icb_ctx::fail_cuda(cudaError_t e, const char* what, const char* file, int line)
@@ -143,10 +147,26 @@ int icb_device_count(void)
     return n;
 }
 
+// ICB_SEGV_TRACE=1: print the native backtrace of a crashing thread (addresses resolve with addr2line on the shipped .so)
+static void icb_segv_handler(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    static const char msg[] = "[icb] fatal signal, native backtrace:\n";
+    if (write(2, msg, sizeof msg - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+
 int icb_ctx_create(int device, icb_ctx** out)
 {
     if (!out) return ICB_ERR_ARG;
     *out = nullptr;
+    if (getenv("ICB_SEGV_TRACE")) {
+	signal(SIGSEGV, icb_segv_handler);
+	signal(SIGABRT, icb_segv_handler);
+    }
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return ICB_ERR_CUDA;  // no CPU fallback: fail loudly
     if (device < 0 || device >= n) return ICB_ERR_ARG;
@@ -317,7 +337,7 @@ void icb_readset_destroy(icb_readset* rs)
     for (void* q : {(void*)rs->d_seq, (void*)rs->d_qual, (void*)rs->d_offs, (void*)rs->d_score, (void*)rs->d_err, (void*)rs->d_status,
 		    (void*)rs->d_hpc_len, (void*)rs->d_hpc_err, (void*)rs->d_hpc_seq, (void*)rs->d_hpc_qual, (void*)rs->d_mins,
 		    (void*)rs->d_min_off, (void*)rs->d_nf, (void*)rs->d_nr, (void*)rs->d_counters, (void*)rs->d_long_list,
-		    (void*)rs->d_long_scratch, (void*)rs->d_class})
+		    (void*)rs->d_long_scratch, (void*)rs->d_class, (void*)rs->d_bkt})
 	icb_dfree(ctx, q);
     delete rs;
 }

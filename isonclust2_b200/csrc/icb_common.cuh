@@ -108,6 +108,8 @@ struct icb_readset {
     std::vector<double> h_score, h_err;
     int max_m = 0;
     uint8_t* d_class = nullptr;
+    std::vector<uint32_t> h_bkt;  // per read: bucket count of the reference's hit map (libstdc++ _M_next_bkt(20 * (nf + nr)))
+    uint32_t* d_bkt = nullptr;
 };
 
 // a worker's context: same device, own stream and timers; destroy folds timers / launch count into the parent

@@ -17,6 +17,7 @@
 // chains), reported as hits/s; bytes per read = 12(M_f+M_r) + 8(M_f+M_r) + 8H + 16C.
 #include <mutex>
 
+#include "dloop.cuh"
 #include "index.cuh"
 
 namespace {
@@ -78,12 +79,14 @@ __device__ __forceinline__ void for_each_posting(const IcbIndexView& ix, uint32_
 // not per node: a single global counter would serialise in L2).
 __global__ void __launch_bounds__(Q_THREADS)
 icb_k_index_insert(IcbIndexView ix, const icb_minimizer* __restrict__ arena, const int64_t* __restrict__ min_off,
-		   const int32_t* __restrict__ nf, const int32_t* __restrict__ reads, const int32_t* __restrict__ ids, int n)
+		   const int32_t* __restrict__ nf, const int32_t* __restrict__ reads, const int32_t* __restrict__ ids, int n,
+		   const int32_t* __restrict__ n_dev)
 {
     __shared__ int s_w[Q_THREADS / 32];
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_set[INS_SET];	 // values of this founder seen so far (open addressing), for sketches that fit
     int b = blockIdx.x;
+    if (n_dev) n = *n_dev;
     if (b >= n) return;
     const int r = reads[b];
     const uint32_t id = uint32_t(ids[b]);
@@ -223,7 +226,10 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
     extern __shared__ uint32_t sm[];
     __shared__ int s_red[Q_THREADS / 32];
     __shared__ int s_red2[Q_THREADS / 32];
+    __shared__ int s_red3[Q_THREADS / 32];
     __shared__ int s_n;
+    __shared__ uint32_t s_off;
+    __shared__ int s_ok;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Ctot = a.C0 + a.n_chunk;
     uint32_t* cnt = SMEM_CNT ? sm : a.g_scratch + int64_t(blockIdx.x) * a.g_stride;
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
     const int bmWords = a.smem_words - (SMEM_CNT ? Ctot : 0) - 2 * a.cap;
     uint32_t* first = a.g_scratch + int64_t(blockIdx.x) * a.g_stride + (SMEM_CNT ? 0 : Ctot);  // mode 1 only
 
-    const int n_items = a.list ? a.n_list : a.n_chunk;
+    const int n_items = a.dl_n_list ? *a.dl_n_list : (a.list ? a.n_list : a.n_chunk);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
 	const int pos = a.list ? a.list[item] : item;
 	const int r = a.chunk_reads[pos];
@@ -262,28 +268,33 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
 	}
 	__syncthreads();
 	// ---- top count among snapshot clusters, number of live keys
-	int top = 0, live = 0;
+	int top = 0, live = 0, hits = 0;
 	for (int i = tid; i < Ctot; i += Q_THREADS) {
 	    uint32_t v = cnt[i];
 	    int lo = v & 0xffff, hi = v >> 16;
 	    live += (lo > 0) + (hi > 0);
+	    hits += lo + hi;
 	    if (i < a.C0) top = max(top, max(lo, hi));
 	}
 #pragma unroll
 	for (int d = 16; d; d >>= 1) {
 	    top = max(top, __shfl_xor_sync(0xffffffffu, top, d));
 	    live += __shfl_xor_sync(0xffffffffu, live, d);
+	    hits += __shfl_xor_sync(0xffffffffu, hits, d);
 	}
 	if (lane == 0) {
 	    s_red[warp] = top;
 	    s_red2[warp] = live;
+	    s_red3[warp] = hits;
 	}
 	__syncthreads();
 	top = 0;
 	live = 0;
+	hits = 0;
 	for (int i = 0; i < Q_THREADS / 32; i++) {
 	    top = max(top, s_red[i]);
 	    live += s_red2[i];
+	    hits += s_red3[i];
 	}
 	IcbQueryHeader* hdr = a.hdr + item;
 	if (a.mode == 1) {
@@ -319,6 +330,9 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
 			cd.count = c;
 			cd.tmapped = int(first[2 * i + half]);
 			out[slot++] = cd;
+			// the candidate ORDER of a read depends on every real candidate of its full list
+			if (a.dl_depmask && i >= a.C0)
+			    atomicOr(&a.dl_depmask[int64_t(pos) * a.dl_mw + ((i - a.C0) >> 5)], 1u << ((i - a.C0) & 31));
 		    }
 		}
 	    }
@@ -329,9 +343,144 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
 		hdr->n_cand = s_n;
 		hdr->overflow = 0;
 		hdr->n_total = live;
+		hdr->n_rel_all = 0;
+		hdr->hits = hits;
+		hdr->cand_off = 0;
+		if (a.dl_full_off) {
+		    a.dl_full_n[pos] = s_n;
+		    a.dl_full_off[pos] = a.full_off[item];
+		}
 	    }
 	    continue;
 	}
+	if (a.mode == 2) {
+	    // ---- pool mode (device-resident loop): the relevant candidates of mode 0, written as records into the chunk's
+	    // candidate pool at a range reserved with one atomic per read
+	    const int tbase2 = max(top, a.min_shared);
+	    int thr2 = __double2int_rz(__dmul_rn(double(tbase2), a.min_frac));
+	    if (thr2 < 1) thr2 = 1;
+	    int mine = 0;
+	    for (int i = tid; i < Ctot; i += Q_THREADS) {
+		const uint32_t v = cnt[i];
+		mine += (int(v & 0xffff) >= thr2) + (int(v >> 16) >= thr2);
+	    }
+#pragma unroll
+	    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+	    __syncthreads();  // s_red was read above
+	    if (lane == 0) s_red[warp] = mine;
+	    __syncthreads();
+	    if (tid == 0) {
+		int nAll = 0;
+		for (int i = 0; i < Q_THREADS / 32; i++) nAll += s_red[i];
+		const uint32_t off = atomicAdd(&a.dl_state->cand_cursor, uint32_t(nAll));
+		const bool ok = nAll <= 32767 && uint64_t(off) + uint64_t(nAll) <= uint64_t(a.dl_state->cand_cap);
+		if (!ok) atomicMax(&a.dl_state->fallback, nAll > 32767 ? DL_FB_TOO_MANY : DL_FB_POOL);
+		s_off = off;
+		s_ok = ok;
+		s_red2[0] = nAll;
+	    }
+	    __syncthreads();
+	    const uint32_t off = s_off;
+	    const int nAll = s_red2[0];
+	    if (!s_ok) {
+		if (tid == 0) {
+		    hdr->top_snap = top;
+		    hdr->n_cand = 0;
+		    hdr->overflow = 1;
+		    hdr->n_total = live;
+		    hdr->n_rel_all = nAll;
+		    hdr->hits = hits;
+		    hdr->cand_off = 0;
+		}
+		continue;
+	    }
+	    for (int i = tid; i < Ctot; i += Q_THREADS) {
+		const uint32_t v = cnt[i];
+		uint32_t nv = v;
+		for (int half = 0; half < 2; half++) {
+		    const int c = half ? int(v >> 16) : int(v & 0xffff);
+		    if (c >= thr2) {
+			const int slot = atomicAdd(&s_n, 1);
+			IcbCand cd;
+			cd.id = i;
+			cd.strand = half ? -1 : 1;
+			cd.count = c;
+			cd.tmapped = 0;
+			a.dl_pool[off + slot] = cd;
+			a.dl_pool_aln[off + slot] = DL_ALN_UNKNOWN;
+			const uint32_t tag = 0x8000u | uint32_t(slot);
+			nv = half ? ((nv & 0x0000ffffu) | (tag << 16)) : ((nv & 0xffff0000u) | tag);
+			if (i >= a.C0) atomicOr(&a.dl_depmask[int64_t(pos) * a.dl_mw + ((i - a.C0) >> 5)], 1u << ((i - a.C0) & 31));
+		    }
+		}
+		if (nv != v) cnt[i] = nv;
+	    }
+	    __syncthreads();
+	    const int nRel2 = s_n;
+	    const int bw2 = (max(nf, nr) + 31) >> 5;
+	    const int perRound2 = max(1, bmWords / max(bw2, 1));
+	    const int myClass2 = a.read_class[r];
+	    const int Lh2 = a.hpc_len[r];
+	    for (int base = 0; base < nRel2; base += perRound2) {
+		const int cntRound = min(perRound2, nRel2 - base);
+		for (int i = tid; i < cntRound * bw2; i += Q_THREADS) bm[i] = 0;
+		__syncthreads();
+		for (int t = tid; t < nf + nr; t += Q_THREADS) {
+		    const icb_minimizer m = mins[t];
+		    const int half = t >= nf;
+		    auto mark = [&](uint32_t id) {
+			const uint32_t v = cnt[id];
+			const uint32_t h = half ? (v >> 16) : (v & 0xffffu);
+			if (h & 0x8000u) {
+			    const int slot = int(h & 0x7fffu) - base;
+			    if (slot >= 0 && slot < cntRound) atomicOr(&bm[slot * bw2 + (m.Index >> 5)], 1u << (m.Index & 31));
+			}
+		    };
+		    for_each_posting(a.main_idx, m.Min, mark);
+		    for_each_posting(a.chunk_idx, m.Min, [&](uint32_t id) {
+			if (int(id) - a.C0 < pos) mark(id);
+		    });
+		}
+		__syncthreads();
+		for (int q = tid; q < cntRound; q += Q_THREADS) {
+		    IcbCand* cd = a.dl_pool + off + base + q;
+		    const int id = cd->id, half = cd->strand < 0;
+		    const int M = half ? nr : nf;
+		    const icb_minimizer* mm = mins + (half ? nf : 0);
+		    const int repRead = id < a.C0 ? a.cls_founder[id] : a.chunk_reads[id - a.C0];
+		    const int nm = a.nmax[int(a.read_class[repRead]) * 15 + myClass2];
+		    const uint32_t* b = bm + q * bw2;
+		    long long T = 0;
+		    int prev = -1;
+		    for (int wd = 0; wd < bw2; wd++) {
+			uint32_t x = b[wd];
+			while (x) {
+			    const int bit = __ffs(x) - 1;
+			    x &= x - 1;
+			    const int idx = wd * 32 + bit;
+			    if (prev < 0) {
+				if (idx <= nm) T += mm[idx].Pos;
+			    }
+			    else if (idx - prev - 1 <= nm) T += (long long)mm[idx].Pos - mm[prev].Pos;
+			    prev = idx;
+			}
+		    }
+		    if (prev >= 0 && M - prev - 1 <= nm) T += (long long)Lh2 - mm[prev].Pos;
+		    cd->tmapped = int(T);
+		}
+		__syncthreads();
+	    }
+	    if (tid == 0) {
+		hdr->top_snap = top;
+		hdr->n_cand = nRel2;
+		hdr->overflow = 0;
+		hdr->n_total = live;
+		hdr->n_rel_all = nAll;
+		hdr->hits = hits;
+		hdr->cand_off = off;
+	    }
+	    continue;
+    }
 	// ---- mode 0: candidates the mapping / alignment tests can reach.  The real top count may still be raised
 	// by a provisional founder, never lowered, so int(max(top, minShared) * minFraction) is a safe lower bound
 	// of the cut getBestClusterMapping applies (cluster.cpp:387).
@@ -425,6 +574,9 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
 	    hdr->n_cand = nRel;
 	    hdr->overflow = nRelAll > a.cap;
 	    hdr->n_total = live;
+	    hdr->n_rel_all = nRelAll;
+	    hdr->hits = hits;
+	    hdr->cand_off = 0;
 	}
     }
 }
@@ -503,7 +655,16 @@ int icb_index_insert(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, const i
 {
     if (n <= 0) return ICB_OK;
     ICB_LAUNCH(ctx, "index_insert",
-	       icb_k_index_insert<<<n, Q_THREADS, 0, ctx->stream>>>(idx.v, rs->d_mins, rs->d_min_off, rs->d_nf, d_reads, d_ids, n));
+	       icb_k_index_insert<<<n, Q_THREADS, 0, ctx->stream>>>(idx.v, rs->d_mins, rs->d_min_off, rs->d_nf, d_reads, d_ids, n, nullptr));
+    return ICB_OK;
+}
+
+int icb_index_insert_dev(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, const int32_t* d_reads, const int32_t* d_ids, const int32_t* d_n,
+			 int n_max)
+{
+    if (n_max <= 0) return ICB_OK;
+    ICB_LAUNCH(ctx, "index_insert",
+	       icb_k_index_insert<<<n_max, Q_THREADS, 0, ctx->stream>>>(idx.v, rs->d_mins, rs->d_min_off, rs->d_nf, d_reads, d_ids, 0, d_n));
     return ICB_OK;
 }
 

@@ -9,6 +9,8 @@
 // Append-only, like the reference's MinimizerDB without consensus (AddMinimizers, minimizer.cpp:31-42):
 // one (value, cluster) pair per distinct minimizer value of the founder's FORWARD sketch.  UpdateMinDB
 // (minimizer.cpp:124-160) marks the nodes of a cluster that left a list dead (id = 0xFFFFFFFF) and appends new ones.
+struct IcbDLoopState;
+
 struct IcbIndexView {
     uint32_t* keys;
     uint32_t* heads;
@@ -38,10 +40,14 @@ struct IcbCand {
 };
 
 struct IcbQueryHeader {
-    int32_t top_snap;  // largest count among snapshot clusters
-    int32_t n_cand;    // records written
-    int32_t overflow;  // 1: more relevant candidates than the per-read capacity (host asks for the full list)
-    int32_t n_total;   // number of (cluster,strand) keys with at least one hit (snapshot + provisional)
+    int32_t top_snap;	 // largest count among snapshot clusters
+    int32_t n_cand;	 // records written
+    int32_t overflow;	 // 1: more relevant candidates than the per-read capacity (the host asks again with room for n_rel_all)
+    int32_t n_total;	 // number of (cluster,strand) keys with at least one hit (snapshot + provisional)
+    int32_t n_rel_all;	 // relevant candidates of this read (>= n_cand)
+    int32_t hits;	 // posting entries matched by the read's minimizers (H of SURVEY 8d)
+    uint32_t cand_off;	 // pool mode: first record of this read in the candidate pool
+    int32_t pad;
 };
 
 struct IcbQueryArgs {
@@ -76,9 +82,21 @@ struct IcbQueryArgs {
     int64_t g_stride;		// in uint32 words
     int32_t smem_words;		// words of dynamic shared memory available for counters + bitmaps
     int32_t smem_cnt;		// 1: dense counters live in shared memory, 0: in g_scratch
+    // device-resident loop (dloop.cuh): work lists and pools live on the device
+    struct IcbDLoopState* dl_state;	// pool cursors, fallback flag; NULL on the host-loop path
+    const int32_t* dl_n_list;		// number of entries of `list`, written by the gather kernel
+    IcbCand* dl_pool;			// mode 2: candidate pool (records) ...
+    int32_t* dl_pool_aln;		// ... and its alignment results, reset to "unknown"
+    uint32_t* dl_depmask;		// [pos][dl_mw] provisional founders among the read's candidates
+    int32_t dl_mw;
+    int64_t* dl_full_off;		// mode 1: per chunk position, where the read's full list starts / its length
+    int32_t* dl_full_n;
 };
 
 int icb_index_insert(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, const int32_t* d_reads, const int32_t* d_ids, int n);
+// the same with the number of founders in device memory (*d_n <= n_max, the grid)
+int icb_index_insert_dev(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, const int32_t* d_reads, const int32_t* d_ids, const int32_t* d_n,
+			 int n_max);
 int icb_index_update(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, int r_old, int r_new, int cls, int nf_old, int nf_new);
 int icb_query_launch(icb_ctx* ctx, const IcbQueryArgs& a, int n_blocks, size_t smem_bytes);
 int icb_classify_errors(icb_ctx* ctx, const double* d_err, const int32_t* d_status, int64_t n, uint8_t* d_class);

@@ -111,12 +111,12 @@ static int64_t gen_read(const genes_t *g, uint64_t seed, int64_t i, const double
     return n;
 }
 
-/* offs[n_reads+1] filled; returns total bases */
-int64_t synth_sizes(uint64_t seed, int64_t n_reads, int reads_per_gene, int min_len, int max_len,
-		    const double *err_set, int n_err, int64_t *offs)
+/* offs[n_reads+1] filled; returns total bases.  n_genes is explicit so that a prefix of a large read set (the first
+ * reads of configs[1]'s 1 M reads over 40 000 genes) can be produced without generating the rest. */
+int64_t synth_sizes_g(uint64_t seed, int64_t n_reads, int n_genes, int min_len, int max_len, const double *err_set, int n_err,
+		      int64_t *offs)
 {
-    int ng = (int)(n_reads / reads_per_gene);
-    if (ng < 1) ng = 1;
+    int ng = n_genes < 1 ? 1 : n_genes;
     genes_t g = make_genes(seed, ng, min_len, max_len);
 #pragma omp parallel for schedule(static, 1024)
     for (int64_t i = 0; i < n_reads; i++) offs[i + 1] = gen_read(&g, seed, i, err_set, n_err, NULL, NULL);
@@ -132,14 +132,25 @@ int64_t synth_sizes(uint64_t seed, int64_t n_reads, int reads_per_gene, int min_
     return tot;
 }
 
-void synth_fill(uint64_t seed, int64_t n_reads, int reads_per_gene, int min_len, int max_len,
-		const double *err_set, int n_err, const int64_t *offs, char *seq, char *qual)
+void synth_fill_g(uint64_t seed, int64_t n_reads, int n_genes, int min_len, int max_len, const double *err_set, int n_err,
+		  const int64_t *offs, char *seq, char *qual)
 {
-    int ng = (int)(n_reads / reads_per_gene);
-    if (ng < 1) ng = 1;
+    int ng = n_genes < 1 ? 1 : n_genes;
     genes_t g = make_genes(seed, ng, min_len, max_len);
 #pragma omp parallel for schedule(static, 1024)
     for (int64_t i = 0; i < n_reads; i++) gen_read(&g, seed, i, err_set, n_err, seq + offs[i], qual + offs[i]);
     free(g.goffs);
     free(g.gseq);
+}
+
+int64_t synth_sizes(uint64_t seed, int64_t n_reads, int reads_per_gene, int min_len, int max_len, const double *err_set, int n_err,
+		    int64_t *offs)
+{
+    return synth_sizes_g(seed, n_reads, (int)(n_reads / reads_per_gene), min_len, max_len, err_set, n_err, offs);
+}
+
+void synth_fill(uint64_t seed, int64_t n_reads, int reads_per_gene, int min_len, int max_len, const double *err_set, int n_err,
+		const int64_t *offs, char *seq, char *qual)
+{
+    synth_fill_g(seed, n_reads, (int)(n_reads / reads_per_gene), min_len, max_len, err_set, n_err, offs, seq, qual);
 }

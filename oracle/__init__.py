@@ -97,6 +97,8 @@ class Port:
         L.orc_cluster_reads.argtypes = [_p, _p, _p, _p, _p, _p]
         L.orc_mindb_after_updates.restype = _i64
         L.orc_mindb_after_updates.argtypes = [_p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _i64, _i64]
+        L.orc_cluster_seeded.restype = _i64
+        L.orc_cluster_seeded.argtypes = [_p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _p, _p]
         self.tab = np.zeros(129)
         self.tab_nomin = np.zeros(129)
         L.orc_init_qualtab(_ptr(self.tab), 0)
@@ -211,19 +213,18 @@ class Port:
     def mindb_after_updates(self, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs):
         return _mindb_after_updates(self.L.orc_mindb_after_updates, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs)
 
-    def cluster(self, seq, offs, sk, score, raw_err, order, k, w, mode, p_shared, min_shared=5, mapped_th=0.65,
-                aligned_th=0.2, min_frac=0.8, min_prob_no_hits=0.1, min_qual=7.0, status=None):
-        """Greedy clustering of reads given in SORTED order `order` (indices into the flat read set).
-
-        sk: dict from sketch_batch over the ORIGINAL read order.  Returns dict with per-sorted-slot results."""
-        n = len(order)
+    def _params(self, k, w, mode, p_shared, min_shared, mapped_th, aligned_th, min_frac, min_prob_no_hits, min_qual):
         P = ClusterParams(k=k, w=w, mode=mode, min_shared=min_shared, mapped_th=mapped_th, aligned_th=aligned_th,
                           min_frac=min_frac, min_prob_no_hits=min_prob_no_hits, min_qual=min_qual)
         ps = np.ascontiguousarray(p_shared, np.float64).reshape(225)
         for i in range(225):
             P.p_shared[i] = ps[i]
+        return P
+
+    def _reads(self, seq, offs, sk, score, raw_err, order, status):
+        """orc_reads over the reads `order` (indices into the flat read set), in that order; returns (struct, keepalive)."""
+        n = len(order)
         order = np.asarray(order)
-        # gather into sorted order
         lens = (offs[1:] - offs[:-1])[order]
         raw_offs = np.zeros(n + 1, np.int64); raw_offs[1:] = np.cumsum(lens)
         raw = np.concatenate([seq[offs[i]:offs[i + 1]] for i in order]) if n else np.zeros(0, np.uint8)
@@ -243,9 +244,37 @@ class Port:
         R = Reads(n_reads=n, status=_ptr(st), score=_ptr(sc), raw_err=_ptr(re_), hpc_err=_ptr(he), raw_seq=_ptr(raw),
                   raw_offs=_ptr(raw_offs), hpc_len=_ptr(hl), mins=_ptr(mins), min_offs=_ptr(moffs), rev_mins=_ptr(rmins),
                   rev_offs=_ptr(roffs))
+        return R, (st, sc, re_, he, raw, raw_offs, hl, mins, moffs, rmins, roffs)
+
+    def cluster(self, seq, offs, sk, score, raw_err, order, k, w, mode, p_shared, min_shared=5, mapped_th=0.65,
+                aligned_th=0.2, min_frac=0.8, min_prob_no_hits=0.1, min_qual=7.0, status=None):
+        """Greedy clustering of reads given in SORTED order `order` (indices into the flat read set).
+
+        sk: dict from sketch_batch over the ORIGINAL read order.  Returns dict with per-sorted-slot results."""
+        n = len(order)
+        P = self._params(k, w, mode, p_shared, min_shared, mapped_th, aligned_th, min_frac, min_prob_no_hits, min_qual)
+        R, _keep = self._reads(seq, offs, sk, score, raw_err, order, status)
         oc, os_, of = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
         na = _i64()
         nc = self.L.orc_cluster_reads(C.byref(P), C.byref(R), _ptr(oc), _ptr(os_), _ptr(of), C.byref(na))
+        return dict(n_clusters=nc, cluster=oc, strand=os_, founder=of[:nc].copy(), n_aligned=na.value)
+
+    def cluster_seeded(self, seq, offs, sk, score, raw_err, seeds, updates, queries, k, w, mode, p_shared, min_shared=5,
+                       mapped_th=0.65, aligned_th=0.2, min_frac=0.8, min_prob_no_hits=0.1, min_qual=7.0, status=None):
+        """Clusters seeded from the reads `seeds`, representatives replaced by `updates` [(cluster, read)] (UpdateMinDB), then the
+        reads `queries` clustered in that order.  All read ids index the flat read set.  Returns per-query results."""
+        P = self._params(k, w, mode, p_shared, min_shared, mapped_th, aligned_th, min_frac, min_prob_no_hits, min_qual)
+        R, _keep = self._reads(seq, offs, sk, score, raw_err, np.arange(len(offs) - 1), status)
+        seeds = np.ascontiguousarray(seeds, np.int32)
+        uc = np.ascontiguousarray([c for c, _ in updates], np.int32)
+        ur = np.ascontiguousarray([r for _, r in updates], np.int32)
+        q = np.ascontiguousarray(queries, np.int32)
+        oc, os_ = np.zeros(len(q), np.int32), np.zeros(len(q), np.int32)
+        of = np.zeros(len(seeds) + len(q), np.int32)
+        na = _i64()
+        nc = self.L.orc_cluster_seeded(C.byref(P), C.byref(R), _ptr(seeds), len(seeds), _ptr(uc), _ptr(ur), len(uc), _ptr(q), len(q),
+                                       _ptr(oc), _ptr(os_), _ptr(of), C.byref(na))
+        assert nc >= 0
         return dict(n_clusters=nc, cluster=oc, strand=os_, founder=of[:nc].copy(), n_aligned=na.value)
 
 

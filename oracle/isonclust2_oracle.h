@@ -91,6 +91,14 @@ typedef struct {
 int64_t orc_cluster_reads(const orc_cluster_params* P, const orc_reads* R, int32_t* out_cluster, int32_t* out_strand,
 			  int32_t* out_founder, int64_t* n_aligned);
 
+/* The same loop on clusters that exist already and whose representatives were replaced (a12 through its caller,
+ * cluster.cpp:279-291): cluster c is seeded from read seeds[c], update u makes read upd_read[u] the representative of
+ * cluster upd_cls[u] (UpdateMinDB, minimizer.cpp:124-160), then queries[0..n_q) are clustered in that order.
+ * out_cluster / out_strand are per query; out_founder needs n_seeds + n_q entries.  Returns the number of clusters. */
+int64_t orc_cluster_seeded(const orc_cluster_params* P, const orc_reads* R, const int32_t* seeds, int64_t n_seeds,
+			   const int32_t* upd_cls, const int32_t* upd_read, int64_t n_upd, const int32_t* queries, int64_t n_q,
+			   int32_t* out_cluster, int32_t* out_strand, int32_t* out_founder, int64_t* n_aligned);
+
 /* a12: UpdateMinDB (minimizer.cpp:124-160) applied to a MinDB built by AddMinimizers; export sorted by key.
  * Returns the number of keys, or -1 - needed if a capacity is too small. */
 int64_t orc_mindb_after_updates(const orc_minimizer* cls_mins, const int64_t* cls_offs, int n_cls, const int32_t* upd_cls,

@@ -4,6 +4,7 @@
 #include <random>
 
 #include "ref_order.h"
+#include "ref_order_hd.h"
 
 struct Cand {
     int32_t id, strand, count, tmapped;
@@ -14,7 +15,7 @@ int main()
     std::mt19937 rng(12345);
     IcbRefOrderScratch S;
     std::vector<IcbSortedCand> got, grp;
-    int bad = 0, bad_group = 0;
+    int bad = 0, bad_group = 0, bad_hd = 0;
     for (int it = 0; it < 3000; it++) {
 	const int ncls = 1 + int(rng() % (it % 7 == 0 ? 9000 : 700));
 	const int nf = 1 + int(rng() % 600), nr = 1 + int(rng() % 600);
@@ -151,8 +152,40 @@ int main()
 	    for (auto x : b)
 		if (uint32_t(x >> 32) == target) g2.push_back(uint32_t(x));
 	    if (g1 != g2) bad_group++;
+	    // the library-free restatement that also runs on the device (ref_order_hd.h)
+	    std::vector<Key> e = a;
+	    icb_sort_hd::introsort_group(e.data(), long(n), target);
+	    std::vector<uint32_t> g3;
+	    for (auto x : e)
+		if (uint32_t(x >> 32) == target) g3.push_back(uint32_t(x));
+	    if (g3 != g2) bad_hd++;
 	}
     }
-    printf("%s: %d of 3000 cases differ, %d group queries differ\n", (bad || bad_group) ? "FAIL" : "ok", bad, bad_group);
-    return (bad || bad_group) ? 1 : 0;
+    // ref_order_hd.h against std::sort on random keys with heavy ties (what candidate lists look like) and on all-distinct keys
+    for (int it = 0; it < 3000; it++) {
+	const int n = 1 + int(rng() % (it % 6 == 0 ? 9000 : 2500));
+	const uint32_t span = it % 3 == 0 ? 6u : (it % 3 == 1 ? 40u : 100000u);
+	std::vector<uint64_t> a(n), b;
+	for (int i = 0; i < n; i++) {
+	    uint32_t v = 1 + rng() % span;
+	    if (it % 4 == 1) while (v > 1 && rng() % 3) v--;  // skewed towards small counts
+	    a[i] = uint64_t(v) << 32 | uint32_t(i);
+	}
+	b = a;
+	std::sort(b.begin(), b.end(), [](uint64_t x, uint64_t y) { return (x >> 32) > (y >> 32); });
+	for (int q = 0; q < 3; q++) {
+	    const uint32_t target = q == 0 ? uint32_t(b[0] >> 32) : uint32_t(b[rng() % n] >> 32);
+	    std::vector<uint64_t> e = a;
+	    icb_sort_hd::introsort_group(e.data(), long(n), target);
+	    std::vector<uint32_t> g2, g3;
+	    for (auto x : b)
+		if (uint32_t(x >> 32) == target) g2.push_back(uint32_t(x));
+	    for (auto x : e)
+		if (uint32_t(x >> 32) == target) g3.push_back(uint32_t(x));
+	    if (g3 != g2) bad_hd++;
+	}
+    }
+    printf("%s: %d of 3000 cases differ, %d group queries differ, %d host/device restatement queries differ\n",
+	   (bad || bad_group || bad_hd) ? "FAIL" : "ok", bad, bad_group, bad_hd);
+    return (bad || bad_group || bad_hd) ? 1 : 0;
 }

@@ -235,6 +235,85 @@ def test_update_representative_equals_fresh_seed(ctx, mode):
         rs.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_update_representative_vs_oracle(port, ctx, mode):
+    """a12 against the ORACLE: clusters seeded, representatives swapped with icb_clusterer_update_representative (the device
+    UpdateMinDB, minimizer.cpp:124-160 + cluster.cpp:279-291), then reads clustered — cluster / strand per read, founders and
+    the alignment count equal the oracle's loop run on a MinDB updated by its UpdateMinDB restatement (which
+    tests/test_oracle.py pins on the reference's own UpdateMinDB)."""
+    k, w = 11, 15
+    seq, qual, offs = synth.make_reads(400, seed=191 + mode, reads_per_gene=8, min_len=300, max_len=900)
+    score, err = port.fill_scores(qual, offs, k)
+    order = port.sort_order(score)
+    sk = port.sketch_batch(seq, qual, offs, k, w)
+    status = sk["status"].copy()
+    for i in range(len(err)):
+        if port.L.orc_quality_filtered(err[i], 7.0):
+            status[i] = 0
+    good = [int(r) for r in order if status[r] == 1]
+    reps = good[0:40:2]
+    upd = [(3, good[41]), (7, good[43]), (3, good[45]), (0, reps[0]), (11, good[47]), (11, reps[11]), (19, good[49]), (5, good[51])]
+    used = set(reps) | {r for _, r in upd}
+    queries = np.array([r for r in good if r not in used], np.int32)
+    pc = port.cluster_seeded(seq, offs, sk, score, err, reps, upd, queries, k, w, mode, pemp.load_p_shared(k, w), status=status)
+    rs = ctx.upload(seq, qual, offs)
+    try:
+        s2, e2 = rs.score(k)
+        rs.sketch_async(k, w, skip=api.quality_filtered(e2, 7.0))
+        cl = api.Clusterer(rs, k, w, mode=mode, chunk_size=32)
+        try:
+            cl.seed(reps)
+            for c, r in upd:
+                cl.update_representative(c, r)
+            c1, s1 = cl.cluster(queries)
+            assert cl.n_clusters == pc["n_clusters"]
+            assert (c1 == pc["cluster"]).all(), np.flatnonzero(c1 != pc["cluster"])[:10]
+            assert (s1 == pc["strand"]).all()
+            assert (cl.founders() == pc["founder"]).all()
+            assert cl.stats()["aln_invoked"] == pc["n_aligned"]
+            assert np.isin(c1, [3, 7, 19, 5]).any() and cl.n_clusters > len(reps)
+        finally:
+            cl.close()
+    finally:
+        rs.close()
+
+
+def _per_slot(rc, order):
+    """(cluster, strand) per sorted slot from the reference's member lists; -1 / 0 for reads it skipped."""
+    slot_of = np.empty(len(order), np.int64)
+    slot_of[order] = np.arange(len(order))
+    c, s = np.full(len(order), -1, np.int32), np.zeros(len(order), np.int32)
+    pos = 0
+    for ci, sz in enumerate(rc["sizes"]):
+        ids = rc["ids"][pos + 1:pos + sz]
+        c[slot_of[ids]] = ci
+        s[slot_of[ids]] = rc["strands"][pos + 1:pos + sz]
+        pos += sz
+    return c, s
+
+
+@pytest.mark.parametrize("mode,n", [(0, 30000), (1, 15000)])
+def test_cluster_benchmark_scale_vs_reference(ref, ctx, mode, n):
+    """Parity at the BENCHMARKED scale: one batch of configs[1]'s generator (the first n reads of bench.py's 1 M-read set:
+    40 000 genes, 8 % error, < 1 read per gene and batch, so most candidates are random hits tied at small counts and a third
+    of the reads go through the reference's candidate-order replay) against the UNMODIFIED reference's ClusterSortedReads.
+    sahlin: a full 30 000-read batch; fast: 15 000 reads (the reference needs 5 minutes for 30 000: ~25 000 clusters)."""
+    k, w = 11, 15
+    seq, qual, offs = synth.make_reads(n, seed=100, err_set=(0.08,), n_genes=40000)
+    rb = ref.sort_and_sketch(seq, qual, offs, k, w)
+    _, _, order = rb.scores()
+    rc = rb.cluster(mode)
+    g = _gpu_cluster(ctx, seq, qual, offs, k, w, mode, 256)
+    assert (g["order"] == order).all()
+    rcl, rst = _per_slot(rc, order)
+    assert g["n_clusters"] == rc["n_clusters"]
+    assert (g["cluster"] == rcl).all(), np.flatnonzero(g["cluster"] != rcl)[:10]
+    assert (g["strand"] == rst).all()
+    assert g["stats"]["aln_invoked"] == rc["n_aligned"]
+    if mode == 0:
+        assert g["stats"]["tie_fallbacks"] > n // 20  # the candidate-order path is exercised at this scale
+
+
 def test_cluster_full_size_properties(ctx):
     """BASELINE-shape property check (no oracle): 120k reads of the configs[1] generator in 4 batches of 30 000, `sahlin`.
     The assignment is a pure function of the sorted order — independent of the chunk size and of how many batches are in

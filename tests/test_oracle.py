@@ -292,3 +292,32 @@ def test_update_mindb_golden(port):
     keys, offs, cls = port.mindb_after_updates(g["cls_mins"], g["cls_offs"], g["upd_cls"], g["upd_mins"], g["upd_offs"])
     assert (keys == g["keys"]).all() and (offs == g["offs"]).all() and (cls == g["cls"]).all()
     assert (offs[1:] == offs[:-1]).any()  # emptied keys are kept
+
+
+def test_cluster_seeded_port_properties(port):
+    """orc_cluster_seeded (the oracle of the device a12 test): without seeds it is orc_cluster_reads; seeding the final
+    representatives directly equals seeding the old ones and applying the UpdateMinDB restatement."""
+    from isonclust2_b200 import pemp, synth
+    k, w = 11, 15
+    seq, qual, offs = synth.make_reads(160, seed=77, reads_per_gene=8, min_len=300, max_len=700)
+    score, err = port.fill_scores(qual, offs, k)
+    order = port.sort_order(score)
+    sk = port.sketch_batch(seq, qual, offs, k, w)
+    ps = pemp.load_p_shared(k, w)
+    for mode in (0, 1):
+        a = port.cluster(seq, offs, sk, score, err, order, k, w, mode, ps)
+        b = port.cluster_seeded(seq, offs, sk, score, err, [], [], order, k, w, mode, ps)
+        assert a["n_clusters"] == b["n_clusters"] and (a["cluster"] == b["cluster"]).all() and (a["strand"] == b["strand"]).all()
+        assert (order[a["founder"]] == b["founder"]).all() and a["n_aligned"] == b["n_aligned"]
+        good = [int(r) for r in order if sk["status"][r] == 1]
+        reps = good[0:20:2]
+        upd = [(2, good[21]), (5, good[23]), (2, good[25]), (0, reps[0])]
+        final = list(reps)
+        for c, r in upd:
+            final[c] = r
+        used = set(reps) | {r for _, r in upd}
+        q = [r for r in good if r not in used]
+        u = port.cluster_seeded(seq, offs, sk, score, err, reps, upd, q, k, w, mode, ps)
+        f = port.cluster_seeded(seq, offs, sk, score, err, final, [], q, k, w, mode, ps)
+        assert u["n_clusters"] == f["n_clusters"] and (u["cluster"] == f["cluster"]).all() and (u["strand"] == f["strand"]).all()
+        assert (u["founder"] == f["founder"]).all() and u["n_clusters"] > len(reps)
