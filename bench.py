@@ -32,8 +32,8 @@ MODE_IDS = {"sahlin": 0, "fast": 1, "furious": 2}
 DIGEST_FILE = os.path.join(ROOT, ".bench_reference_digest.json")  # written by --impl reference, read by the GPU arm
 
 
-def metric_name(mode):
-    return f"reads/sec clustered ({mode})"
+def metric_name(mode, tree=False):
+    return f"reads/sec clustered ({mode}" + (", batches merged as a tree)" if tree else ")")
 
 
 def result_digest(n_clusters, cluster, strand, aln_invoked):
@@ -54,7 +54,7 @@ def digest_key(reads, seed, mode, batch_max_seq, n_genes):
 INT_PIPE_PEAK_GCUPS = 148 * 4 * 16 * 1.965 / 7.5  # SMs x sub-partitions x ALU lanes/clk x GHz / ALU instructions per cell = 2482
 KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_full", "index_insert", "align_dp",
            "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "sketch_reads_cta", "gather_minimizers",
-           "dl_init", "dl_decide", "dl_commit", "dl_gather", "dl_finalize")
+           "dl_init", "dl_decide", "dl_order", "dl_order_large", "dl_commit", "dl_gather", "dl_finalize")
 
 
 def clocks_sampler(stop, out, device):
@@ -180,7 +180,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     pipe = dict(k=K, w=W_, mode=mode, min_qual=MIN_QUAL, batch_kb=BATCH_KB, batch_max_seq=args.batch_max_seq, chunk_size=args.chunk,
-                n_workers=args.workers)
+                n_workers=args.workers, tree=args.tree)
 
     # ---------------- device-resident steps: reads already in HBM
     rs = ctx.upload(seq, qual, offs)
@@ -208,6 +208,13 @@ def run_ours(args):
         times.append(e0.elapsed_time(e1))
     launches = ctx.launch_count() - launches0
     digest = result_digest(res["n_clusters"], res["cluster"], res["strand"], res["stats"]["aln_invoked"])
+    if args.quick:  # tuning runs: the device-resident number and the loop's counters only
+        stop.set()
+        ms = float(np.mean(times))
+        print(json.dumps({"quick": True, "value": world * n_reads / (ms * 1e-3), "ms_per_step": ms, "gpu_launches": int(launches),
+                          "result_digest": digest, "cluster_stats": res["stats"], "env": {k: v for k, v in os.environ.items() if k.startswith("ICB_")}}),
+              flush=True)
+        return
 
     # ---------------- kernel-level passes (not part of the timed steps): event pairs around every launch, ONE stream, so the
     # per-kernel durations do not overlap
@@ -240,7 +247,8 @@ def run_ours(args):
     # (3) alignment kernels saturated: the step's accepted (read, representative) pairs replayed in full launches
     dp_sat = None
     if mode != "fast":
-        pairs = accepted_pairs(res, res["err"], args.replay_pairs)
+        res_b = res if not args.tree else api.run_pipeline(ctx, None, None, None, rs=rs, **{**pipe, "tree": False})
+        pairs = accepted_pairs(res_b, res["err"], args.replay_pairs)
         if len(pairs):
             lens = np.diff(rs.offs)
             cells = int((lens[pairs["read"]].astype(np.int64) * lens[pairs["rep"]].astype(np.int64)).sum())
@@ -320,7 +328,7 @@ def run_ours(args):
     if rank == 0:
         try:
             ref = json.load(open(DIGEST_FILE))
-            key = digest_key(n_reads, 100, mode, args.batch_max_seq, max(1, n_reads // 25))
+            key = digest_key(n_reads, 100, mode, args.batch_max_seq, max(1, n_reads // 25)) + (" tree" if args.tree else "")
             if key in ref:
                 parity = bool(ref[key]["digest"] == digest and digest_e2e == digest)
                 parity_src = f"{os.path.basename(DIGEST_FILE)} written by `bench.py --impl reference` ({ref[key].get('when', '?')})"
@@ -328,10 +336,10 @@ def run_ours(args):
             pass
 
     line = {
-        "metric": metric_name(mode), "value": world * n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(mode, args.tree), "value": world * n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/u32/i32 (+f64 quality chains)", "data": "synthetic",
-        "config": {**workload_config(n_reads, args.batch_max_seq, mode),
+        "config": {**workload_config(n_reads, args.batch_max_seq, mode, args.tree),
                    "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "batches": len(res["batches"]),
                    "clusters": int(sum(res["n_clusters"])), "reads_clustered": clustered,
                    "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"reads sharded x{world}, no collective",
@@ -384,6 +392,78 @@ def _ref_cluster_worker(args):
 
 
 _REF_STATE = {}
+
+
+def _ref_tree_leaf(args):
+    lo, hi, nr, mode_id, path = args
+    b = _REF_STATE["batch"].slice(lo, hi, nr)
+    rc = b.cluster(mode_id)
+    b.save(path)
+    return int(rc["n_aligned"])
+
+
+def _ref_tree_merge(args):
+    import oracle
+    left, right, out, mode_id = args
+    R = oracle.ref()
+    a, b = R.load_batch(left), R.load_batch(right)
+    rc = a.cluster(mode_id, right=b)
+    a.save(out)
+    return int(rc["n_aligned"])
+
+
+def reference_tree_step(seq, qual, offs, batch_max_seq, cores, mode):
+    """The reference's pipeline for configs[4] on the host cores: `sort`, one single-threaded `cluster` job per batch, then the
+    merge tree level by level (`cluster -l A -r B`), `cores` jobs at a time, every job reading and writing `.cer` files as the
+    pipeline does (README.md:105-117).  Returns (seconds, clusters, kind, digest, n_batches)."""
+    import multiprocessing as mp
+    import shutil
+    import tempfile
+
+    import oracle
+    from isonclust2_b200 import api
+
+    n = len(offs) - 1
+    R = oracle.ref()
+    tmp = tempfile.mkdtemp(prefix="icb_ref_tree_")
+    try:
+        t0 = time.perf_counter()
+        batch = R.sort_and_sketch(seq, qual, offs, K, W_, MIN_QUAL)
+        _, _, order = batch.scores()
+        batches = api.split_batches(order, np.diff(offs), BATCH_KB, batch_max_seq)
+        _REF_STATE["batch"] = batch
+        mid = MODE_IDS[mode]
+        nal = 0
+        with mp.get_context("fork").Pool(min(cores, max(1, len(batches)))) as pool:
+            paths = [os.path.join(tmp, f"c_{i}.cer") for i in range(len(batches))]
+            nal += sum(pool.map(_ref_tree_leaf, [(lo, hi - 1, i, mid, paths[i]) for i, (lo, hi) in enumerate(batches)], chunksize=1))
+            level = list(paths)
+            while len(level) > 1:  # adjacent nodes pair up, an odd last node is carried up
+                jobs, nxt = [], []
+                for i in range(0, len(level) - 1, 2):
+                    out = level[i] + ".m"
+                    jobs.append((level[i], level[i + 1], out, mid))
+                    nxt.append(out)
+                if len(level) % 2:
+                    nxt.append(level[-1])
+                nal += sum(pool.map(_ref_tree_merge, jobs, chunksize=1))
+                level = nxt
+        _REF_STATE.clear()
+        root = R.load_batch(level[0])
+        dt = time.perf_counter() - t0
+        rc = root.cluster_lists()
+        slot_of = np.empty(n, np.int64)
+        slot_of[order] = np.arange(n)
+        cl, st = np.full(n, -1, np.int32), np.zeros(n, np.int32)
+        pos = 0
+        for ci, sz in enumerate(rc["sizes"]):
+            m = rc["ids"][pos + 1:pos + sz]
+            cl[slot_of[m]] = ci
+            st[slot_of[m]] = rc["strands"][pos + 1:pos + sz]
+            pos += sz
+        return dt, len(rc["sizes"]), "reference", result_digest([len(rc["sizes"])], cl, st, nal), len(batches)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def reference_step(seq, qual, offs, batch_max_seq, cores, mode):
@@ -464,11 +544,12 @@ def run_reference(args, quiet=False):
     for _ in range(args.warmup):  # a CPU run has nothing to warm but the page cache: one small batch per warm-up step
         m = min(n_reads, 500)
         reference_step(seq[:offs[m]], qual[:offs[m]], offs[:m + 1], m, 1, mode)
+    step_fn = reference_tree_step if (args.tree and oracle.have_ref()) else reference_step
     secs, kind, ncl, dg, nb = [], "port", 0, None, 0
     # one step of the full configuration is minutes of CPU work on every core: steps stop once a minute has been spent
     n_want = min(max(args.steps, 1), 3)
     while len(secs) < n_want:
-        dt, ncl, kind, dg, nb = reference_step(seq, qual, offs, args.batch_max_seq, cores, mode)
+        dt, ncl, kind, dg, nb = step_fn(seq, qual, offs, args.batch_max_seq, cores, mode)
         secs.append(dt)
         if sum(secs) > 60.0:
             break
@@ -483,15 +564,15 @@ def run_reference(args, quiet=False):
                     f"{cores} TBB threads, then {used} single-threaded `cluster -x {mode}` jobs in parallel; {dt:.1f} s per step, "
                     f"{ncl} clusters; {n_steps} step(s) timed" + (f" of the {args.steps} requested" if n_steps != args.steps else ""),
           "digest": dg, "sample_reads": n_reads, "sample_batch_max_seq": args.batch_max_seq}
-    line = {"impl": "reference", "metric": metric_name(mode), "value": v, "unit": "reads/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+    line = {"impl": "reference", "metric": metric_name(mode, args.tree), "value": v, "unit": "reads/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": n_steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u32/i32 (+f64 quality chains)", "data": "synthetic",
-            "config": workload_config(args.reads, args.batch_max_seq, mode), "result_digest": dg,
+            "config": workload_config(args.reads, args.batch_max_seq, mode, args.tree), "result_digest": dg,
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if full and dg:
         try:
             ref = json.load(open(DIGEST_FILE)) if os.path.exists(DIGEST_FILE) else {}
-            ref[digest_key(n_reads, 100, mode, args.batch_max_seq, n_genes)] = {"digest": dg, "clusters": ncl, "kind": kind,
+            ref[digest_key(n_reads, 100, mode, args.batch_max_seq, n_genes) + (" tree" if args.tree else "")] = {"digest": dg, "clusters": ncl, "kind": kind,
                                                                                 "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}
             json.dump(ref, open(DIGEST_FILE, "w"))
         except Exception:
@@ -506,7 +587,7 @@ def cpu_baseline_subprocess(args):
     batches so that every core has one), in a fresh process (no CUDA state is forked)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--reads", str(args.reads),
            "--mode", args.mode, "--sample-reads", str(min(args.reads, args.cpu_baseline_reads)),
-           "--batch-max-seq", str(args.cpu_baseline_batch_reads)]
+           "--batch-max-seq", str(args.cpu_baseline_batch_reads)] + (["--tree"] if args.tree else [])
     try:
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
         for ln in reversed(r.stdout.strip().splitlines()):
@@ -517,9 +598,10 @@ def cpu_baseline_subprocess(args):
         return {"value": None, "unit": "reads/s", "cores": 0, "kind": "failed", "sample": repr(ex)[:300]}
 
 
-def workload_config(reads, batch_max_seq, mode):
+def workload_config(reads, batch_max_seq, mode, tree=False):
     return {"workload": f"configs[1] read set: {reads} synthetic ONT cDNA reads per GPU (~1.3 kb mean, 8% error), k={K} w={W_}, "
-                        f"sort + cluster -x {mode} of every batch (B={BATCH_KB} kb, M={batch_max_seq})"}
+                        f"sort + cluster -x {mode} of every batch (B={BATCH_KB} kb, M={batch_max_seq})" +
+                        (", then the batches merged as a tree (`cluster -l A -r B` level by level: the shape of configs[4])" if tree else "")}
 
 
 def main():
@@ -539,6 +621,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tree", action="store_true", help="configs[4] shape: the clustered batches are merged as a tree (whole pipeline)")
+    ap.add_argument("--quick", action="store_true", help="tuning: device-resident steps only, short line (not the bench contract)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -164,6 +164,12 @@ typedef struct {
     int64_t cands;	   /* candidate records written by the chunk queries (C of the index-probe byte count) */
     int64_t dl_chunks;	   /* chunks decided entirely on the device (device-resident loop) */
     int64_t dl_fallback_chunks; /* chunks the device loop handed back to the host loop */
+    int64_t tree_merges;   /* icb_cluster_tree: merge jobs run */
+    int64_t dl_fallback_reasons; /* bit r set: a chunk was handed back for reason r (1 candidate pool, 2 more candidates than the
+			      order kernel's shared-memory plan, 3 the reference's hit map would rehash, 4 full-list pool, 5 workspace, 6 test hook) */
+    /* device loop: what the read at the commit frontier waited for when a round ended — its full candidate list, its first
+     * alignment, or another alignment (the next tied candidate, or a new first candidate after a founder changed its order) */
+    int64_t dl_stop_full, dl_stop_pair_first, dl_stop_pair_again;
 } icb_cluster_stats;
 
 typedef struct icb_clusterer icb_clusterer;
@@ -199,6 +205,71 @@ int icb_clusterer_stats(const icb_clusterer* cl, icb_cluster_stats* stats);
 int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,
 			int32_t n_batches, int32_t n_workers, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
 			icb_cluster_stats* stats);
+
+/* configs[4] in process: icb_cluster_batches for the leaves, then the merge tree the reference's pipeline runs as
+ * `cluster -l A -r B` jobs over .cer files (README.md:105-117; main.cpp:238-382, cluster.cpp:67-106): adjacent nodes are
+ * paired left to right level by level (an odd last node is carried up), and a merge clusters the right node's clusters, in
+ * id order and through their representatives, against the left node's — on clusterers that stay RESIDENT between levels
+ * (index, representatives, cluster ids), so nothing is re-parsed, re-uploaded, re-sketched or re-indexed.  cluster_of[slot]
+ * / strand_of[slot] are the read's cluster and strand in the ROOT; *n_clusters the root's cluster count.  min_cls_size is
+ * CmdArgs::MinClsSize of `sort` (args.h:21, default 3): clusters of a MERGED right node with fewer reads are dropped from the
+ * merge and from the output (cluster.cpp:120-124), their reads end with cluster -1.  Equal to running
+ * the reference's tree on the same batches (tests/test_tree_gpu.py). */
+int icb_cluster_tree(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds, int32_t n_batches,
+		     int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
+		     icb_cluster_stats* stats);
+
+/* ------------------------------------------------------------------ per-primitive face
+ * One entry point per reference function of the path, on HOST arrays, for a host that keeps its own ClusterSortedReads
+ * (cluster.cpp:67-322) and containers, and for the C++ header shim include/isonclust2_compat/ (hpc.h, kmer_index.h,
+ * minimizer.h, qualscore.h, cluster.h, p_emp_prob.h with the reference's signatures) that the reference's unit test
+ * test/isONclust2_test.cpp compiles against.  Each call is one small launch; the batched entry points above are the
+ * throughput path. */
+/* HomopolymerCompress (hpc.cpp:4-32) of n flat reads (offs[0] = 0): compressed read i is written at offs[i] of hpc_seq /
+ * hpc_qual (n_bases bytes each), hpc_len[i] long; qualities are the maximum over each run. */
+int icb_hpc_compress(icb_ctx* ctx, const char* seq, const char* qual, const int64_t* offs, int64_t n, char* hpc_seq, char* hpc_qual,
+		     int32_t* hpc_len);
+/* KmerEncodeSeq (kmer_index.cpp:5-17): k-mers i = 0 .. len-k-1 (the reference drops the last one) as 2-bit values,
+ * BaseToNumber semantics for characters outside ACGT.  out needs len-k entries. */
+int icb_kmer_encode(icb_ctx* ctx, const char* seq, int64_t len, int kmer_size, uint32_t* out, int64_t* n_out);
+/* GetKmerMinimizers (minimizer.cpp:78-123): leftmost minimum of every window of w-k+1 k-mers, emitted when its position
+ * changes.  out needs n entries. */
+int icb_kmer_minimizers(icb_ctx* ctx, const uint32_t* kmers, int64_t n, int kmer_size, int window_size, icb_minimizer* out,
+			int64_t* n_out);
+/* CalcErrorRate (qualscore.cpp:147-154) of n quality strings with the given 129-entry table */
+int icb_calc_error_rate(icb_ctx* ctx, const char* qual, const int64_t* offs, int64_t n, const double tab[129], double* out);
+/* MinimizerDB (minimizer.h:60-61) on the device.  icb_index_add = AddMinimizers (minimizer.cpp:31-42; cluster ids must be
+ * added in increasing order, as ClusterSortedReads does), icb_index_update_cluster = UpdateMinDB (minimizer.cpp:124-160),
+ * icb_index_query_hits = GetMinimizerHits (minimizer.cpp:44-76): every (read minimizer, cluster) hit in the order the
+ * reference appends them; *n_out > cap means nothing was written, ask again with room for *n_out hits. */
+typedef struct icb_index icb_index;
+typedef struct {
+    uint32_t cls;
+    int32_t strand; /* +1 / -1 */
+    uint32_t pos, index; /* MinimizerHit {Pos, Index} (minimizer.h:63-66) */
+} icb_hit;
+int icb_index_create(icb_ctx* ctx, icb_index** index);
+void icb_index_destroy(icb_index* index);
+int icb_index_add(icb_index* index, uint32_t cls, const icb_minimizer* mins, int64_t n);
+int icb_index_update_cluster(icb_index* index, uint32_t cls, const icb_minimizer* old_mins, int64_t n_old, const icb_minimizer* new_mins,
+			     int64_t n_new);
+int icb_index_query_hits(icb_index* index, const icb_minimizer* mins, int64_t n, const icb_minimizer* rev_mins, int64_t n_rev, icb_hit* out,
+			 int64_t cap, int64_t* n_out);
+/* totalMapped of getMappedRatio (cluster.cpp:324-353) for one candidate's hits (ascending Index): a run of g missed
+ * minimizers is bridged iff g <= n_max, the largest g with pow(pError, g) >= minProbNoHits (host libm);
+ * the caller divides by hpc_len. */
+int icb_mapped_length(icb_ctx* ctx, const uint32_t* hit_pos, const uint32_t* hit_index, int64_t n_hits, int64_t n_minimizers, int64_t hpc_len,
+		      int32_t n_max, int64_t* total_mapped);
+/* getAlnRatio's window count (cluster.cpp:442-459) of a comparison string: windows of k columns, all but the last one,
+ * with at least `limit` = floor((1-e)*k) match marks (0x7C) */
+int icb_count_windows(icb_ctx* ctx, const char* comp, int64_t len, int kmer_size, int limit, int64_t* aligned);
+/* ParasailAlign (cluster.cpp:408-423) + parasail_result_get_traceback (traceback_template.c:13-190) of ONE pair with the
+ * comparison string materialised: comp (cap bytes, may be NULL) receives the traceback's `comp` line (0x7C match, blank
+ * otherwise, free end gaps included), result->comp_len its length. */
+int icb_align_traceback(icb_readset* rs, const icb_pair* pair, int kmer_size, icb_align_result* result, char* comp, int64_t cap);
+/* InitMinSharedMap (p_emp_prob.cpp:22-47) as the 15 x 15 grid icb_cluster_params wants: path NULL = $ICB_PEMP_TABLE, else
+ * data/p_emp_prob.bin next to this library.  Cells without a row are NaN. */
+int icb_load_p_shared(const char* path, int kmer_size, int window_size, double p_shared[225]);
 
 #ifdef __cplusplus
 }

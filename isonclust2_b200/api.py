@@ -79,7 +79,9 @@ class ClusterStats(C.Structure):
                                          "tie_fallbacks", "decisions")] + \
                [(n, C.c_double) for n in ("ms_query", "ms_full", "ms_align", "ms_insert", "ms_host", "ms_cpu", "ms_order")] + \
                [("order_calls", C.c_int64), ("aln_calls_ref", C.c_int64), ("ms_batch_max", C.c_double), ("ms_wall", C.c_double), ("hyp_decisions", C.c_int64),
-                ("hits", C.c_int64), ("cands", C.c_int64), ("dl_chunks", C.c_int64), ("dl_fallback_chunks", C.c_int64)]
+                ("hits", C.c_int64), ("cands", C.c_int64), ("dl_chunks", C.c_int64), ("dl_fallback_chunks", C.c_int64),
+                ("tree_merges", C.c_int64), ("dl_fallback_reasons", C.c_int64),
+                ("dl_stop_full", C.c_int64), ("dl_stop_pair_first", C.c_int64), ("dl_stop_pair_again", C.c_int64)]
 
 
 MODES = {"sahlin": 0, "fast": 1, "furious": 2}
@@ -113,6 +115,22 @@ def cluster_batches(rs, order, bounds, k, w, n_workers=0, **params):
     c.check(c.L.icb_cluster_batches(rs.h, C.byref(P), order.ctypes.data, bounds.ctypes.data, nb, n_workers, cl.ctypes.data,
                                     st.ctypes.data, ncl.ctypes.data, C.byref(stats)))
     return cl, st, ncl[:nb], {n: getattr(stats, n) for n, _ in ClusterStats._fields_}
+
+
+def cluster_tree(rs, order, bounds, k, w, n_workers=0, min_cls_size=3, **params):
+    """configs[4] in process: every batch clustered, then merged as a tree (`cluster -l A -r B` level by level) on clusterers
+    that stay resident on the device.  Returns (cluster per slot in the ROOT, strand per slot, clusters of the root, stats)."""
+    c = rs.ctx
+    P = make_params(k, w, **params)
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    bounds = np.ascontiguousarray(bounds, dtype=np.int64)
+    nb = len(bounds) - 1
+    cl, st = np.full(len(order), -1, np.int32), np.zeros(len(order), np.int32)
+    ncl = C.c_int64()
+    stats = ClusterStats()
+    c.check(c.L.icb_cluster_tree(rs.h, C.byref(P), order.ctypes.data, bounds.ctypes.data, nb, n_workers, min_cls_size, cl.ctypes.data,
+                                 st.ctypes.data, C.byref(ncl), C.byref(stats)))
+    return cl, st, ncl.value, {n: getattr(stats, n) for n, _ in ClusterStats._fields_}
 
 
 class Clusterer:
@@ -318,10 +336,12 @@ def split_batches(order, lengths, batch_kb=50000, batch_max_seq=30000):
 
 
 def run_pipeline(ctx, seq, qual, offs, k=11, w=15, mode="sahlin", min_qual=7.0, batch_kb=50000, batch_max_seq=30000,
-                 chunk_size=0, rs=None, keep=False, n_workers=0, **cluster_kw):
+                 chunk_size=0, rs=None, keep=False, n_workers=0, tree=False, min_cls_size=3, **cluster_kw):
     """`isONclust2 sort` + one `isONclust2 cluster -x <mode>` per batch, on one device, without the files in between.
+    tree=True: the batches are then merged as a tree (`cluster -l A -r B` level by level) on resident clusterers.
 
-    Returns dict(order, batches, cluster (per sorted slot, batch-local ids), strand, n_clusters per batch, stats)."""
+    Returns dict(order, batches, cluster (per sorted slot; batch-local ids, or the root's with tree=True), strand,
+    n_clusters per batch (tree=True: [clusters of the root]), stats)."""
     own = rs is None
     if own:
         rs = ctx.upload(seq, qual, offs)
@@ -343,8 +363,13 @@ def run_pipeline(ctx, seq, qual, offs, k=11, w=15, mode="sahlin", min_qual=7.0, 
         batches = split_batches(order, lengths, batch_kb, batch_max_seq)
         bounds = np.array([a for a, _ in batches] + [batches[-1][1] if batches else 0], dtype=np.int64)
         phases["sketch_split"] = lap()
-        cluster, strand, ncl, tot = cluster_batches(rs, order, bounds, k, w, n_workers=n_workers, mode=mode, min_qual=min_qual,
-                                                    chunk_size=chunk_size, **cluster_kw)
+        if tree:
+            cluster, strand, nroot, tot = cluster_tree(rs, order, bounds, k, w, n_workers=n_workers, min_cls_size=min_cls_size, mode=mode,
+                                                       min_qual=min_qual, chunk_size=chunk_size, **cluster_kw)
+            ncl = [nroot]
+        else:
+            cluster, strand, ncl, tot = cluster_batches(rs, order, bounds, k, w, n_workers=n_workers, mode=mode, min_qual=min_qual,
+                                                        chunk_size=chunk_size, **cluster_kw)
         phases["cluster"] = lap()
         ncl = [int(x) for x in ncl]
         return dict(order=order, batches=batches, cluster=cluster, strand=strand, n_clusters=ncl, stats=tot, score=score, err=err,

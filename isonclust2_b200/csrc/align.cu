@@ -47,12 +47,12 @@ __device__ __forceinline__ uint32_t shf_in(uint32_t acc, int signsrc)
 // Traceback of one pair by a whole warp (lane-uniform control flow).  Mirrors parasail_result_get_traceback
 // (traceback_template.c:72-175) and feeds getAlnRatio's window count (cluster.cpp:442-459).
 __device__ icb_align_result traceback_warp(const uint8_t* __restrict__ seq, const IcbPairDesc& d, const uint4* tr, int ncg,
-					   int k, int score, int ei, int ej)
+					   int k, int score, int ei, int ej, uint8_t* rec)
 {
     const int lane = threadIdx.x & 31;
     const int n = d.n, m = d.m;
     IcbWindowCounter st;
-    st.init(k, d.limit);
+    st.init(k, d.limit, rec);
     int i = ei, j = ej;
     // free tail (traceback_template.c:72-94)
     if (i + 1 == n) st.push_zeros(m - 1 - j);
@@ -120,7 +120,7 @@ __device__ icb_align_result traceback_warp(const uint8_t* __restrict__ seq, cons
 __global__ void __launch_bounds__(AL_THREADS)
 icb_k_align32_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, int n_pairs, uint4* __restrict__ trace,
 	       int* __restrict__ lines, int k, icb_align_result* __restrict__ out, unsigned long long* __restrict__ ticket,
-	       const int32_t* __restrict__ n_pairs_dev, int32_t* __restrict__ aln_out)
+	       const int32_t* __restrict__ n_pairs_dev, int32_t* __restrict__ aln_out, uint8_t* __restrict__ comp_rec)
 {
     const int lane = threadIdx.x & 31;
     if (n_pairs_dev) n_pairs = *n_pairs_dev;  // device-built pair queue (dloop.cu)
@@ -309,7 +309,7 @@ icb_k_align32_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	}
 	// ---- traceback by the same warp while the trace tiles are still in L2 (all lanes walk in lockstep; the
 	// tiles of a 4x4-tile window and the 32 query / reference characters it spans are held across the lanes)
-	icb_align_result res = traceback_warp(seq, d, tr, ncg, k, score, ei, ej);
+	icb_align_result res = traceback_warp(seq, d, tr, ncg, k, score, ei, ej, p == 0 ? comp_rec : nullptr);
 	if (lane == 0) {
 	    if (aln_out) aln_out[d.out] = res.aligned;
 	    else out[d.out] = res;
@@ -397,7 +397,7 @@ int icb_align32_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, c
     unsigned grid = unsigned((warps + AL_WARPS - 1) / AL_WARPS);
     ICB_LAUNCH(ctx, "align_dp32",
 	       icb_k_align32_dp<<<grid, AL_THREADS, 0, st>>>(d_seq, ws.d_descs, int(cnt), reinterpret_cast<uint4*>(ws.d_trace), ws.d_lines,
-							       k, ws.d_out, ws.d_ticket, nullptr, nullptr));
+							       k, ws.d_out, ws.d_ticket, nullptr, nullptr, nullptr));
     return ICB_OK;
 }
 
@@ -413,7 +413,7 @@ int icb_align32_run_dev(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_se
     unsigned grid = unsigned((warps + AL_WARPS - 1) / AL_WARPS);
     ICB_LAUNCH(ctx, "align_dp32",
 	       icb_k_align32_dp<<<grid, AL_THREADS, 0, st>>>(d_seq, d_descs, 0, reinterpret_cast<uint4*>(ws.d_trace), ws.d_lines, k, nullptr,
-							       ws.d_ticket, d_count, aln_out));
+							       ws.d_ticket, d_count, aln_out, nullptr));
     return ICB_OK;
 }
 
@@ -537,6 +537,56 @@ int icb_align_pairs_on(icb_ctx* ctx, icb_readset* rs, const icb_pair* pairs, int
 }
 
 extern "C" {
+
+int icb_align_traceback(icb_readset* rs, const icb_pair* pair, int kmer_size, icb_align_result* result, char* comp, int64_t cap)
+{
+    if (!rs || !pair || !result || cap < 0 || (cap > 0 && !comp)) return ICB_ERR_ARG;
+    icb_ctx* ctx = rs->ctx;
+    if (kmer_size < 1 || kmer_size > 32) return ctx->fail(ICB_ERR_ARG, "kmer_size must be in [1,32]");
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (pair->read < 0 || pair->read >= rs->n_reads || pair->rep < 0 || pair->rep >= rs->n_reads)
+	return ctx->fail(ICB_ERR_ARG, "pair index outside the read set");
+    if (!ctx->align_ws) ctx->align_ws = new IcbAlignWorkspace;
+    IcbAlignWorkspace& ws = *ctx->align_ws;
+    cudaStream_t st = ctx->stream;
+    IcbPairDesc d{};
+    d.q_off = rs->h_offs[pair->read];
+    d.r_off = rs->h_offs[pair->rep];
+    d.n = int32_t(rs->h_offs[pair->read + 1] - rs->h_offs[pair->read]);
+    d.m = int32_t(rs->h_offs[pair->rep + 1] - rs->h_offs[pair->rep]);
+    if (d.n < 1 || d.m < 1) return ctx->fail(ICB_ERR_ARG, "empty sequence in an alignment pair");
+    d.rc = pair->strand == -1;
+    d.open = pair->gap_open;
+    d.limit = pair->limit;
+    d.ncg = (d.m + 7) >> 3;
+    const int64_t tiles = int64_t((d.n + 7) >> 3) * d.ncg;
+    const int64_t words = 3 * int64_t(d.m) + ((d.n + 7) & ~7) + 8;
+    int rc = ws.ensure(ctx, size_t(tiles) * 32 + 64, size_t(words) * 4 + 64, 1);
+    if (rc) return rc;
+    uint8_t* d_rec = nullptr;
+    const int64_t rec_len = int64_t(d.n) + d.m + 8;
+    ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&d_rec, size_t(rec_len)));
+    ws.h_descs[0] = d;
+    ICB_CUDA(ctx, cudaMemsetAsync(ws.d_ticket, 0, 8, st));
+    ICB_CUDA(ctx, cudaMemcpyAsync(ws.d_descs, ws.h_descs, sizeof(IcbPairDesc), cudaMemcpyHostToDevice, st));
+    ICB_LAUNCH(ctx, "align_dp32",
+	       icb_k_align32_dp<<<1, AL_THREADS, 0, st>>>(rs->d_seq, ws.d_descs, 1, reinterpret_cast<uint4*>(ws.d_trace), ws.d_lines,
+							    kmer_size, ws.d_out, ws.d_ticket, nullptr, nullptr, d_rec));
+    ICB_CUDA(ctx, cudaMemcpyAsync(ws.h_out, ws.d_out, sizeof(icb_align_result), cudaMemcpyDeviceToHost, st));
+    ICB_CUDA(ctx, ctx->wait());
+    *result = ws.h_out[0];
+    const int64_t len = result->comp_len;
+    if (comp && len > 0 && len <= rec_len) {
+	std::vector<char> tmp;
+	tmp.resize(size_t(len));
+	ICB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_rec, size_t(len), cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, ctx->wait());
+	const int64_t w = std::min(len, cap);
+	for (int64_t i = 0; i < w; i++) comp[i] = tmp[size_t(len - 1 - i)];  // recorded in traceback order
+    }
+    icb_dfree(ctx, d_rec);
+    return ICB_OK;
+}
 
 int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size, icb_align_result* results)
 {

@@ -58,8 +58,10 @@ struct IcbWindowCounter {
     int k, limit;
     long long pushed;
     int aligned;
-    __device__ __forceinline__ void init(int kk, int lim)
+    uint8_t* rec;  // icb_align_traceback only: the comparison string, one byte per column, in traceback (reverse) order
+    __device__ __forceinline__ void init(int kk, int lim, uint8_t* record = nullptr)
     {
+	rec = record;
 	reg = 0;
 	mask = kk >= 32 ? 0xffffffffu : ((1u << kk) - 1u);
 	k = kk;
@@ -71,6 +73,7 @@ struct IcbWindowCounter {
     {
 	reg = ((reg << 1) | bit) & mask;
 	if (pushed >= k && __popc(reg) >= limit) aligned++;
+	if (rec) rec[pushed] = bit ? uint8_t('|') : uint8_t(' ');
 	pushed++;
     }
     __device__ void push_zeros(long long g)
@@ -83,6 +86,8 @@ struct IcbWindowCounter {
 	    long long counted = rest;
 	    if (pushed < k) counted -= (k - pushed);
 	    if (counted > 0 && 0 >= limit) aligned += int(counted);
+	    if (rec)
+		for (long long t = 0; t < rest; t++) rec[pushed + t] = uint8_t(' ');
 	    pushed += rest;
 	}
     }

@@ -114,11 +114,28 @@ struct icb_clusterer {
 
     // device-resident loop (dloop.cu): the chunk's records, pools and work queues
     bool use_dloop = true;
+    int dl_reason = 0;
+    bool dl_retry = false;   // the device loop enlarged a pool: the chunk goes through it again
+    int force_fallback = 0;  // test hook (ICB_DLOOP_FORCE_FALLBACK=m): chunks with (C0 + N) % m == 0 go back to the host loop
     IcbDLoopView V{};
     IcbQueryHeader* d_hdr_full = nullptr;
     int32_t* d_n_ins = nullptr;
     uint32_t cand_cap = 0;
     unsigned long long full_cap = 0;
+    // one round of the device loop as a captured graph: one driver call instead of ~17 launches per round (35 worker threads
+    // launching kernel by kernel are bound by the driver's launch rate, not by the device)
+    struct RoundKey {
+	const void* p[12];
+	size_t smem_f;
+	int nb_f, smem_cnt_f, iters, mode, max_m, k, spec;
+	bool operator==(const RoundKey& o) const { return memcmp(this, &o, sizeof(RoundKey)) == 0; }
+    };
+    cudaGraphExec_t round_exec = nullptr;
+    RoundKey round_key{};
+    int round_nodes = 0;
+    int qf_bound = 0;		       // snapshot size the full-list query's launch configuration is planned for
+    IcbQueryArgs* d_qf_args = nullptr;
+    IcbQueryArgs* h_qf_args = nullptr;  // pinned
     IcbDLoopState* h_state = nullptr;  // pinned
     int32_t* h_out = nullptr;	       // pinned: 3 * chunk_cap (cluster, strand, founder positions)
     double rounds_avg = 3.0;
@@ -149,8 +166,16 @@ struct icb_clusterer {
     {
 	bool handled = false;
 	if (use_dloop) {
-	    int rc = process_chunk_device(chunk, slots, cluster_of, strand_of, handled);
-	    if (rc) return rc;
+	    for (int attempt = 0; attempt < 6 && !handled; attempt++) {
+		dl_retry = false;
+		int rc = process_chunk_device(chunk, slots, cluster_of, strand_of, handled);
+		if (rc) return rc;
+		if (!dl_retry) break;
+	    }
+	    if (!handled) {
+		stats.dl_fallback_chunks++;
+		stats.dl_fallback_reasons |= int64_t(1) << (dl_reason & 31);
+	    }
 	}
 	return handled ? ICB_OK : process_chunk(chunk, slots, cluster_of, strand_of);
     }
@@ -237,8 +262,10 @@ int icb_clusterer::init_dloop()
 {
     const int cs = chunk_cap;
     const int mw = (cs + 31) / 32;
-    static const bool off = getenv("ICB_HOST_LOOP") != nullptr;
+    // read per clusterer (tests switch engines inside one process)
+    const bool off = getenv("ICB_HOST_LOOP") != nullptr;
     use_dloop = !off && mw <= DL_MAXW;
+    force_fallback = getenv("ICB_DLOOP_FORCE_FALLBACK") ? atoi(getenv("ICB_DLOOP_FORCE_FALLBACK")) : 0;
     V = IcbDLoopView{};
     V.mw = mw;
     auto dm = [&](void** p, size_t bytes) { return icb_dmalloc(ctx, p, bytes); };
@@ -246,6 +273,7 @@ int icb_clusterer::init_dloop()
     ICB_CUDA(ctx, dm((void**)&V.hdr, sizeof(IcbQueryHeader) * cs));
     ICB_CUDA(ctx, dm((void**)&d_hdr_full, sizeof(IcbQueryHeader) * cs));
     ICB_CUDA(ctx, dm((void**)&V.founder_cls, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.view_cls, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.outcome, cs));
     ICB_CUDA(ctx, dm((void**)&V.flags, cs));
     ICB_CUDA(ctx, dm((void**)&V.dec_cls, 4 * cs));
@@ -253,7 +281,13 @@ int icb_clusterer::init_dloop()
     ICB_CUDA(ctx, dm((void**)&V.aln_calls, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.plan_n, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.plan_i, 4 * cs));
-    ICB_CUDA(ctx, dm((void**)&V.need_slot, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.need_slot, 4 * cs * DL_SPEC));
+    ICB_CUDA(ctx, dm((void**)&V.need_n, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.req_count, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.ord_req, cs));
+    ICB_CUDA(ctx, dm((void**)&V.ord_target, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.order_list_s, 4 * cs));
+    ICB_CUDA(ctx, dm((void**)&V.order_list_l, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.full_off, 8 * cs));
     ICB_CUDA(ctx, dm((void**)&V.full_n, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.depmask, size_t(4) * cs * mw));
@@ -261,13 +295,15 @@ int icb_clusterer::init_dloop()
     ICB_CUDA(ctx, dm((void**)&V.out_cls, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.out_strand, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.founder_pos, 4 * cs));
-    ICB_CUDA(ctx, dm((void**)&V.descs16, sizeof(IcbPairDesc) * cs));
-    ICB_CUDA(ctx, dm((void**)&V.descs32, sizeof(IcbPairDesc) * cs));
+    ICB_CUDA(ctx, dm((void**)&V.descs16, sizeof(IcbPairDesc) * cs * DL_SPEC));
+    ICB_CUDA(ctx, dm((void**)&V.descs32, sizeof(IcbPairDesc) * cs * DL_SPEC));
     ICB_CUDA(ctx, dm((void**)&V.full_list, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.full_list_off, 8 * cs));
     ICB_CUDA(ctx, dm((void**)&V.ins_reads, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&V.ins_ids, 4 * cs));
     ICB_CUDA(ctx, dm((void**)&d_n_ins, 16));
+    ICB_CUDA(ctx, dm((void**)&d_qf_args, sizeof(IcbQueryArgs)));
+    ICB_CUDA(ctx, cudaMallocHost((void**)&h_qf_args, sizeof(IcbQueryArgs)));
     ICB_CUDA(ctx, cudaMallocHost((void**)&h_state, sizeof(IcbDLoopState)));
     ICB_CUDA(ctx, cudaMallocHost((void**)&h_out, sizeof(int32_t) * 3 * cs));
     cand_cap = 0;
@@ -280,10 +316,16 @@ int icb_clusterer::init_dloop()
 
 void icb_clusterer::free_dloop()
 {
-    void* ps[] = {V.st, V.hdr, d_hdr_full, V.founder_cls, V.outcome, V.flags, V.dec_cls, V.dec_strand, V.aln_calls, V.plan_n, V.plan_i,
-		  V.need_slot, V.full_off, V.full_n, V.depmask, V.seenmask, V.out_cls, V.out_strand, V.founder_pos, V.descs16, V.descs32,
+    void* ps[] = {V.st, V.hdr, d_hdr_full, V.founder_cls, V.view_cls, V.outcome, V.flags, V.dec_cls, V.dec_strand, V.aln_calls, V.plan_n, V.plan_i,
+		  V.need_slot, V.need_n, V.req_count, V.ord_req, V.ord_target, V.order_list_s, V.order_list_l, V.full_off, V.full_n, V.depmask, V.seenmask, V.out_cls, V.out_strand, V.founder_pos, V.descs16, V.descs32,
 		  V.full_list, V.full_list_off, V.ins_reads, V.ins_ids, d_n_ins, V.cands, V.aln, V.plan, V.full};
     for (void* p : ps) icb_dfree(ctx, p);
+    icb_dfree(ctx, d_qf_args);
+    d_qf_args = nullptr;
+    if (round_exec) cudaGraphExecDestroy(round_exec);
+    round_exec = nullptr;
+    cudaFreeHost(h_qf_args);
+    h_qf_args = nullptr;
     cudaFreeHost(h_state);
     cudaFreeHost(h_out);
     V = IcbDLoopView{};
@@ -1082,7 +1124,7 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
 	const size_t L = size_t(std::max<int64_t>(rs->max_len, 64));
 	const size_t one = ((L + 7) / 8) * ((L + 71) / 8 + 1) * 32 + 4096;
 	const size_t lines_one = (4 * L + 64) * 4;
-	rc = ws.ensure(ctx, std::max(trace_mb << 20, one), std::max(lines_one * size_t(N), size_t(4) << 20), 2 * int64_t(N) + 16);
+	rc = ws.ensure(ctx, std::max(trace_mb << 20, one), std::max(lines_one * size_t(N), size_t(4) << 20), int64_t(DL_SPEC) * chunk_cap + 16);
 	if (rc) return rc;
     }
     const unsigned long long tiles_cap = ws.trace_bytes / 32 - 4, words_cap = ws.lines_bytes / 4 - 32;
@@ -1099,7 +1141,13 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
     qa.dl_depmask = V.depmask;
     qa.dl_mw = V.mw;
     query_base(this, qf, N, C0);
-    rc = plan_query(Ctot, 0, 1, qf, N, nb_f, smem_f);  // same scratch block as the pool-mode plan: the two never overlap in time
+    // the full-list query is launched from the round graph: its launch configuration is planned for a snapshot size with
+    // headroom, so that it (and the graph) only changes when the clusterer has outgrown it
+    if (Ctot > qf_bound) {
+	qf_bound = 4096;
+	while (qf_bound < Ctot + Ctot / 4) qf_bound *= 2;
+    }
+    rc = plan_query(qf_bound, 0, 1, qf, chunk_cap, nb_f, smem_f);  // same scratch block as the pool-mode plan: never used at the same time
     if (rc) return rc;
     if (qa.g_stride > 0) qa.g_scratch = d_scratch;  // the second plan may have enlarged (moved) the scratch block
     qf.g_scratch = d_scratch;
@@ -1112,6 +1160,8 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
     qf.dl_mw = V.mw;
     qf.dl_full_off = V.full_off;
     qf.dl_full_n = V.full_n;
+    const int max_m = int(std::min<int64_t>(rs->max_len, 8000));
+    static const int commit_iters = getenv("ICB_DLOOP_COMMIT_ITERS") ? std::max(1, atoi(getenv("ICB_DLOOP_COMMIT_ITERS"))) : 2;
     // the view's per-run pointers
     V.chunk_reads = d_chunk_reads;
     V.offs = rs->d_offs;
@@ -1127,8 +1177,11 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
     V.min_frac = P.min_fraction;
     V.mapped_th = P.mapped_threshold;
     V.aligned_th = P.aligned_threshold;
-    static const int force = getenv("ICB_DLOOP_FORCE_FALLBACK") ? atoi(getenv("ICB_DLOOP_FORCE_FALLBACK")) : 0;
-    V.force_fallback = force;
+    V.force_fallback = force_fallback;
+    static const int spec_pairs = getenv("ICB_DLOOP_SPEC_PAIRS") ? std::max(1, std::min(DL_SPEC, atoi(getenv("ICB_DLOOP_SPEC_PAIRS")))) : 1;
+    V.spec_pairs = spec_pairs;
+    static const int spec_window = getenv("ICB_DLOOP_SPEC_WINDOW") ? atoi(getenv("ICB_DLOOP_SPEC_WINDOW")) : 1 << 20;
+    V.spec_window = spec_window;
     // ---- chunk index: every read of the chunk as a provisional founder (id = C0 + position)
     for (int i = 0; i < N; i++) {
 	h_i32[i] = chunk[i];
@@ -1152,24 +1205,80 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
     if (rc) return rc;
     rc = icb_dl_decide(ctx, V, N);
     if (rc) return rc;
-    const int max_m = int(std::min<int64_t>(rs->max_len, 8000));
+    // the full-list query reads its arguments from device memory
+    *h_qf_args = qf;
+    ICB_CUDA(ctx, cudaMemcpyAsync(d_qf_args, h_qf_args, sizeof(IcbQueryArgs), cudaMemcpyHostToDevice, st));
+    const int G = chunk_cap;  // grids of the round's kernels: the chunk capacity (positions past the chunk's end return at once)
+    const int GP = chunk_cap * V.spec_pairs;  // capacity of the pair queues = grid of the alignment kernels
+    auto enqueue_round = [&]() -> int {
+	// commit the decided prefix, re-decide what the new founders invalidated (in parallel), commit on: the walk only
+	// stops for good at a read that waits for an alignment or for its full candidate list
+	for (int it = 0; it < commit_iters; it++) {
+	    int r2 = icb_dl_commit(ctx, V);
+	    if (r2) return r2;
+	    r2 = icb_dl_decide(ctx, V, G);
+	    if (r2) return r2;
+	}
+	int r2 = icb_dl_gather(ctx, V, GP);
+	if (r2) return r2;
+	r2 = icb_query_launch_ptr(ctx, d_qf_args, qf.smem_cnt != 0, nb_f, smem_f);
+	if (r2) return r2;
+	if (P.mode != 1) {
+	    r2 = icb_align16_run_dev(ctx, ws, rs->d_seq, V.descs16, &V.st->n_pairs16, GP, max_m, k, V.aln);
+	    if (r2) return r2;
+	    // pairs the packed kernel cannot take (longer than 8000, or refused for a character outside ACGT)
+	    r2 = icb_align32_run_dev(ctx, ws, rs->d_seq, V.descs32, &V.st->n_pairs32, GP, k, V.aln);
+	    if (r2) return r2;
+	}
+	return ICB_OK;
+    };
+    static const bool no_graph = getenv("ICB_NO_GRAPH") != nullptr;
+    const bool use_graph = !no_graph && !ctx->timing;
+    if (use_graph) {
+	RoundKey key;
+	memset(&key, 0, sizeof key);
+	const void* ptrs[12] = {V.st, V.cands, V.full, V.cls_founder, ws.d_trace, ws.d_lines, ws.d_ends, ws.d_ticket, rs->d_seq, rs->d_bkt, d_qf_args,
+				V.hdr};
+	memcpy(key.p, ptrs, sizeof ptrs);
+	key.smem_f = smem_f;
+	key.nb_f = nb_f;
+	key.smem_cnt_f = qf.smem_cnt;
+	key.iters = commit_iters;
+	key.mode = P.mode;
+	key.max_m = max_m;
+	key.k = k;
+	key.spec = V.spec_window * 8 + V.spec_pairs;
+	if (!round_exec || !(key == round_key)) {
+	    if (round_exec) cudaGraphExecDestroy(round_exec);
+	    round_exec = nullptr;
+	    const int64_t lc0 = ctx->launch_count;
+	    ICB_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+	    const int rcap = enqueue_round();
+	    cudaGraph_t g = nullptr;
+	    const cudaError_t e = cudaStreamEndCapture(st, &g);
+	    round_nodes = int(ctx->launch_count - lc0);
+	    ctx->launch_count = lc0;
+	    if (rcap) {
+		if (g) cudaGraphDestroy(g);
+		return rcap;
+	    }
+	    ICB_CUDA(ctx, e);
+	    const cudaError_t e2 = cudaGraphInstantiate(&round_exec, g, 0);
+	    cudaGraphDestroy(g);
+	    ICB_CUDA(ctx, e2);
+	    round_key = key;
+	}
+    }
     int enqueued = 0;
     for (;;) {
 	const int R = std::max(2, std::min(16, int(rounds_avg + 1.5) - enqueued));
 	for (int q = 0; q < R; q++) {
-	    rc = icb_dl_commit(ctx, V);
-	    if (rc) return rc;
-	    rc = icb_dl_decide(ctx, V, N);
-	    if (rc) return rc;
-	    rc = icb_dl_gather(ctx, V, N);
-	    if (rc) return rc;
-	    rc = icb_query_launch(ctx, qf, nb_f, smem_f);
-	    if (rc) return rc;
-	    if (P.mode != 1) {
-		rc = icb_align16_run_dev(ctx, ws, rs->d_seq, V.descs16, &V.st->n_pairs16, N, max_m, k, V.aln);
-		if (rc) return rc;
-		// pairs the packed kernel cannot take (longer than 8000, or refused for a character outside ACGT)
-		rc = icb_align32_run_dev(ctx, ws, rs->d_seq, V.descs32, &V.st->n_pairs32, N, k, V.aln);
+	    if (use_graph) {
+		ICB_CUDA(ctx, cudaGraphLaunch(round_exec, st));
+		ctx->launch_count += round_nodes;
+	    }
+	    else {
+		rc = enqueue_round();
 		if (rc) return rc;
 	    }
 	}
@@ -1190,16 +1299,21 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
     }
     stats.ms_align += sw.lap();
     if (h_state->fallback) {
-	stats.dl_fallback_chunks++;
-	if (h_state->fallback == DL_FB_POOL) {
-	    rc = grow_cand_pool(uint32_t(std::min<uint64_t>(uint64_t(cand_cap) * 4, 0xfffffff0ull)));
+	// handled stays false: nothing was applied (the founders' insert is skipped unless the chunk finished).  A pool that
+	// was too small is enlarged and the chunk goes through the device loop once more; anything else is the host loop's.
+	dl_retry = false;
+	dl_reason = h_state->fallback;
+	if (h_state->fallback == DL_FB_POOL && cand_cap < 0x40000000u) {
+	    rc = grow_cand_pool(cand_cap * 4);
 	    if (rc) return rc;
+	    dl_retry = true;
 	}
-	if (h_state->fallback == DL_FB_FULLPOOL) {
+	if (h_state->fallback == DL_FB_FULLPOOL && full_cap < (1ull << 31)) {
 	    rc = grow_full_pool(full_cap * 4);
 	    if (rc) return rc;
+	    dl_retry = true;
 	}
-	return ICB_OK;	// handled stays false: nothing was applied (the founders' insert is skipped unless the chunk finished)
+	return ICB_OK;
     }
     // ---- apply
     const IcbDLoopState& S = *h_state;
@@ -1228,6 +1342,9 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
     stats.order_calls += S.order_calls;
     stats.hits += S.hits;
     stats.cands += S.cands;
+    stats.dl_stop_full += S.stop_full;
+    stats.dl_stop_pair_first += S.stop_pair_first;
+    stats.dl_stop_pair_again += S.stop_pair_again;
     handled = true;
     return ICB_OK;
 }
@@ -1351,7 +1468,8 @@ static void add_stats(icb_cluster_stats& t, const icb_cluster_stats& s)
     t.decisions += s.decisions; t.ms_query += s.ms_query; t.ms_full += s.ms_full; t.ms_align += s.ms_align;
     t.ms_insert += s.ms_insert; t.ms_host += s.ms_host; t.ms_cpu += s.ms_cpu; t.ms_order += s.ms_order; t.order_calls += s.order_calls;
     t.aln_calls_ref += s.aln_calls_ref; t.hyp_decisions += s.hyp_decisions; t.hits += s.hits; t.cands += s.cands;
-    t.dl_chunks += s.dl_chunks; t.dl_fallback_chunks += s.dl_fallback_chunks;
+    t.dl_chunks += s.dl_chunks; t.dl_fallback_chunks += s.dl_fallback_chunks; t.dl_fallback_reasons |= s.dl_fallback_reasons;
+    t.dl_stop_full += s.dl_stop_full; t.dl_stop_pair_first += s.dl_stop_pair_first; t.dl_stop_pair_again += s.dl_stop_pair_again;
 }
 
 void icb_worker_pool_release(icb_ctx* ctx)
@@ -1492,6 +1610,232 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
     }
     if (stats) stats->ms_wall = wall.lap();
     if (first_err.load()) icb_worker_pool_release(ctx);  // a failed worker's buffers are in an unknown state
+    if (first_err.load()) {
+	for (auto& e : werr)
+	    if (!e.empty()) return ctx->fail(first_err.load(), e);
+	return ctx->fail(first_err.load(), "worker failed");
+    }
+    return ICB_OK;
+}
+
+// configs[4] in process: leaf clustering of every sorted batch, then the merge tree the reference's pipeline runs as
+// `cluster -l A -r B` jobs over .cer files (README.md:105-117, main.cpp:238-382, cluster.cpp:67-106), on RESIDENT
+// clusterers: a node's index, representatives and cluster ids stay on the device between levels, and a merge is
+// icb_cluster_reads on the left node's clusterer over the right node's representatives in the right node's cluster order
+// (what cluster.cpp:108-261 does with rightBatch->Cls[i][REP]).  Nothing is re-uploaded, re-sketched or re-indexed.
+int icb_cluster_tree(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds, int32_t n_batches,
+		     int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
+		     icb_cluster_stats* stats)
+{
+    if (!rs || !params || n_batches < 0 || (n_batches > 0 && (!order || !bounds || !cluster_of || !strand_of))) return ICB_ERR_ARG;
+    icb_ctx* ctx = rs->ctx;
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (stats) *stats = icb_cluster_stats{};
+    if (n_clusters) *n_clusters = 0;
+    if (n_batches == 0) return ICB_OK;
+    Stopwatch wall;
+    if (!rs->scored || !rs->sketched) return ctx->fail(ICB_ERR_STATE, "icb_cluster_tree needs scored and sketched reads");
+    for (int b = 0; b < n_batches; b++)
+	if (bounds[b] < 0 || bounds[b + 1] < bounds[b]) return ctx->fail(ICB_ERR_ARG, "batch bounds must be non-decreasing");
+    int rc = icb_readset_prepare_host(rs);
+    if (rc) return rc;
+    ICB_CUDA(ctx, ctx->wait());
+    int nw = n_workers > 0 ? n_workers : std::min(std::max(8, 3 * icb_host_cores()), 48);
+    nw = std::min(nw, int(n_batches));
+    while (int(ctx->pool_ctx.size()) < nw) {
+	icb_ctx* kid = icb_ctx_create_child(ctx);
+	if (!kid) return ctx->fail(ICB_ERR_CUDA, "cannot create a worker stream");
+	ctx->pool_ctx.push_back(kid);
+	ctx->pool_cl.push_back(nullptr);
+    }
+    for (int w = 0; w < nw; w++) {
+	ctx->pool_ctx[w]->timing = ctx->timing;
+	ctx->pool_ctx[w]->trace_base = ctx->trace_base;
+    }
+    // one node per batch: its clusterer (left operands keep it), its representatives, the worker whose stream it lives on
+    struct Node {
+	icb_clusterer* cl = nullptr;
+	std::vector<int32_t> reps;
+	std::vector<int32_t> csize;  // reads per cluster (the reference's Cls[i]->size() - 1: the list holds the representative's copy too)
+	int worker = -1, lo = 0, hi = 0, depth = 0;
+    };
+    std::vector<Node> nodes(static_cast<size_t>(n_batches));
+    // local cluster id of a leaf -> (cluster of the node that holds the leaf now, strand sign)
+    std::vector<std::vector<int32_t>> lmap(static_cast<size_t>(n_batches)), lsign(static_cast<size_t>(n_batches));
+    std::atomic<int> first_err(0);
+    std::vector<std::string> werr(static_cast<size_t>(nw));
+    std::vector<icb_cluster_stats> wstats(static_cast<size_t>(nw));
+    auto fail_worker = [&](int w, int rcw, icb_ctx* c) {
+	int z = 0;
+	first_err.compare_exchange_strong(z, rcw);
+	werr[size_t(w)] = c->last_error;
+    };
+    // a node that is only ever a RIGHT operand of the plan below keeps nothing but its representatives
+    std::vector<char> is_left(static_cast<size_t>(n_batches), 0);
+    {
+	std::vector<int> cur(static_cast<size_t>(n_batches));
+	for (int b = 0; b < n_batches; b++) cur[size_t(b)] = b;
+	while (cur.size() > 1) {
+	    std::vector<int> nxt;
+	    for (size_t i = 0; i + 1 < cur.size(); i += 2) {
+		is_left[size_t(cur[i])] = 1;
+		nxt.push_back(cur[i]);
+	    }
+	    if (cur.size() % 2) nxt.push_back(cur.back());
+	    cur.swap(nxt);
+	}
+	is_left[0] = 1;	 // the root keeps its clusterer until the counts are read
+    }
+    // ---- leaves
+    {
+	std::atomic<int> next(0);
+	auto work = [&](int w) {
+	    icb_ctx* c = ctx->pool_ctx[size_t(w)];
+	    cudaSetDevice(c->device);
+	    for (;;) {
+		const int b = next.fetch_add(1);
+		if (b >= n_batches || first_err.load()) break;
+		Node& nd = nodes[size_t(b)];
+		nd.worker = w;
+		nd.lo = nd.hi = b;
+		int rcw = clusterer_create_on(c, rs, params, &nd.cl);
+		if (!rcw)
+		    rcw = icb_cluster_reads(nd.cl, order + bounds[b], bounds[b + 1] - bounds[b], cluster_of + bounds[b], strand_of + bounds[b]);
+		if (rcw) {
+		    fail_worker(w, rcw, c);
+		    break;
+		}
+		nd.reps = nd.cl->founder;
+		add_stats(wstats[size_t(w)], nd.cl->stats);
+		nd.cl->stats = icb_cluster_stats{};
+		lmap[size_t(b)].resize(nd.reps.size());
+		lsign[size_t(b)].assign(nd.reps.size(), 1);
+		for (size_t q = 0; q < nd.reps.size(); q++) lmap[size_t(b)][q] = int32_t(q);
+		nd.csize.assign(nd.reps.size(), 0);
+		for (int64_t t = bounds[b]; t < bounds[b + 1]; t++)
+		    if (cluster_of[t] >= 0) nd.csize[size_t(cluster_of[t])]++;
+		if (!is_left[size_t(b)]) {
+		    icb_clusterer_destroy(nd.cl);
+		    nd.cl = nullptr;
+		}
+	    }
+	};
+	std::vector<std::thread> th;
+	for (int w = 0; w < nw; w++) th.emplace_back(work, w);
+	for (auto& t : th) t.join();
+    }
+    // ---- merge levels: adjacent nodes are paired left to right, an odd last node is carried up (it only ever becomes a
+    // right operand: the reference requires the left batch not to be shallower than the right one, cluster.cpp:80-90)
+    std::vector<int> cur(static_cast<size_t>(n_batches));
+    for (int b = 0; b < n_batches; b++) cur[size_t(b)] = b;
+    int64_t merges = 0;
+    while (cur.size() > 1 && !first_err.load()) {
+	struct Job {
+	    int left, right;
+	};
+	std::vector<Job> jobs;
+	std::vector<int> nxt;
+	for (size_t i = 0; i + 1 < cur.size(); i += 2) {
+	    jobs.push_back(Job{cur[i], cur[i + 1]});
+	    nxt.push_back(cur[i]);
+	}
+	if (cur.size() % 2) nxt.push_back(cur.back());
+	// a job runs on the stream its left clusterer lives on
+	std::vector<std::vector<int>> per_worker(static_cast<size_t>(nw));
+	for (size_t j = 0; j < jobs.size(); j++) per_worker[size_t(nodes[size_t(jobs[j].left)].worker)].push_back(int(j));
+	auto work = [&](int w) {
+	    icb_ctx* c = ctx->pool_ctx[size_t(w)];
+	    cudaSetDevice(c->device);
+	    for (int j : per_worker[size_t(w)]) {
+		if (first_err.load()) break;
+		Node& L = nodes[size_t(jobs[size_t(j)].left)];
+		Node& R = nodes[size_t(jobs[size_t(j)].right)];
+		const int64_t nr = int64_t(R.reps.size());
+		// clusters of a MERGED right batch with fewer than MinClsSize reads are left out of the merge — and of the output
+		// (cluster.cpp:120-124)
+		std::vector<int32_t> el_reps, el_idx;
+		for (int64_t q = 0; q < nr; q++)
+		    if (!(R.depth > 0 && min_cls_size > 1 && R.csize[size_t(q)] < min_cls_size)) {
+			el_reps.push_back(R.reps[size_t(q)]);
+			el_idx.push_back(int32_t(q));
+		    }
+		const int64_t ne = int64_t(el_reps.size());
+		std::vector<int32_t> ec(static_cast<size_t>(ne)), es(static_cast<size_t>(ne));
+		const int rcw = icb_cluster_reads(L.cl, el_reps.data(), ne, ec.data(), es.data());
+		if (rcw) {
+		    fail_worker(w, rcw, c);
+		    break;
+		}
+		add_stats(wstats[size_t(w)], L.cl->stats);
+		L.cl->stats = icb_cluster_stats{};
+		std::vector<int32_t> tc(static_cast<size_t>(nr), -1), ts(static_cast<size_t>(nr), 0);
+		L.csize.resize(L.cl->founder.size(), 0);
+		for (int64_t q = 0; q < ne; q++) {
+		    tc[size_t(el_idx[size_t(q)])] = ec[size_t(q)];
+		    ts[size_t(el_idx[size_t(q)])] = es[size_t(q)];
+		    if (ec[size_t(q)] >= 0) L.csize[size_t(ec[size_t(q)])] += R.csize[size_t(el_idx[size_t(q)])];
+		}
+		// every leaf under the right node: its clusters are where the right node's clusters went
+		for (int b = R.lo; b <= R.hi; b++) {
+		    auto& m = lmap[size_t(b)];
+		    auto& sg = lsign[size_t(b)];
+		    for (size_t q = 0; q < m.size(); q++) {
+			const int32_t g = m[q];
+			if (g < 0) continue;
+			m[q] = tc[size_t(g)];
+			sg[q] = ts[size_t(g)] == -1 ? -sg[q] : sg[q];
+		    }
+		}
+		L.reps = L.cl->founder;
+		L.hi = R.hi;
+		L.depth++;
+		std::vector<int32_t>().swap(R.reps);  // the right node's clusterer is released after the level (its stream may be busy)
+	    }
+	};
+	std::vector<std::thread> th;
+	for (int w = 0; w < nw; w++)
+	    if (!per_worker[size_t(w)].empty()) th.emplace_back(work, w);
+	for (auto& t : th) t.join();
+	for (auto& j : jobs) {
+	    Node& R = nodes[size_t(j.right)];
+	    if (R.cl) {
+		icb_clusterer_destroy(R.cl);
+		R.cl = nullptr;
+	    }
+	}
+	merges += int64_t(jobs.size());
+	cur.swap(nxt);
+    }
+    // ---- final ids: a read's leaf cluster, mapped through every merge its leaf went through as part of a right operand
+    if (!first_err.load()) {
+	for (int b = 0; b < n_batches; b++) {
+	    const auto& m = lmap[size_t(b)];
+	    const auto& sg = lsign[size_t(b)];
+	    for (int64_t s = bounds[b]; s < bounds[b + 1]; s++) {
+		const int32_t c = cluster_of[s];
+		if (c < 0) continue;
+		cluster_of[s] = m[size_t(c)];
+		strand_of[s] = m[size_t(c)] < 0 ? 0 : strand_of[s] * sg[size_t(c)];
+	    }
+	}
+	if (n_clusters) *n_clusters = int64_t(nodes[0].reps.size());
+    }
+    for (auto& nd : nodes)
+	if (nd.cl) {
+	    icb_clusterer_destroy(nd.cl);
+	    nd.cl = nullptr;
+	}
+    for (int w = 0; w < nw; w++) {
+	if (stats) {
+	    add_stats(*stats, wstats[size_t(w)]);
+	    stats->ms_batch_max = std::max(stats->ms_batch_max, wstats[size_t(w)].ms_batch_max);
+	}
+	icb_ctx_fold_child(ctx, ctx->pool_ctx[size_t(w)]);
+    }
+    if (stats) {
+	stats->ms_wall = wall.lap();
+	stats->tree_merges = merges;
+    }
     if (first_err.load()) {
 	for (auto& e : werr)
 	    if (!e.empty()) return ctx->fail(first_err.load(), e);

@@ -99,6 +99,7 @@ icb_ctx* icb_ctx_create_child(icb_ctx* parent)
     auto ctx = new icb_ctx;
     ctx->device = parent->device;
     ctx->sm_count = parent->sm_count;
+    ctx->hi_priority = parent->hi_priority;
     ctx->timing = parent->timing;
     ctx->trace_base = parent->trace_base;
     ctx->blocking_wait = true;
@@ -180,6 +181,10 @@ int icb_ctx_create(int device, icb_ctx** out)
 	return ICB_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {
+	int least = 0, greatest = 0;
+	if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) ctx->hi_priority = greatest;
+    }
     {
 	// memory returned to the stream-ordered pool stays cached in it (no trimming at synchronisation points)
 	cudaMemPool_t pool;

@@ -4,9 +4,16 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
 #include <numeric>
+#include <string>
 #include <thread>
 #include <vector>
+
+#include <dlfcn.h>
 
 #include "helpers.h"
 #include "isonclust2_b200.h"
@@ -28,6 +35,53 @@ void parallel_ranges(int64_t n, int64_t grain, F fn)
 }  // namespace
 
 extern "C" {
+
+// InitMinSharedMap (p_emp_prob.cpp:22-47) for (k, w): rows with the same k and |w_row - w| <= 2, later rows overwriting
+// earlier ones, symmetric in (e1, e2); the table ships as data/p_emp_prob.bin (tools/make_p_emp_table.py)
+int icb_load_p_shared(const char* path, int kmer_size, int window_size, double p_shared[225])
+{
+    if (!p_shared) return ICB_ERR_ARG;
+    for (int i = 0; i < 225; i++) p_shared[i] = std::numeric_limits<double>::quiet_NaN();
+    std::string file;
+    if (path) file = path;
+    else if (const char* env = getenv("ICB_PEMP_TABLE")) file = env;
+    else {
+	Dl_info info;
+	if (!dladdr(reinterpret_cast<void*>(&icb_load_p_shared), &info) || !info.dli_fname) return ICB_ERR_STATE;
+	std::string so(info.dli_fname);
+	const size_t s = so.rfind('/');
+	file = (s == std::string::npos ? std::string(".") : so.substr(0, s)) + "/data/p_emp_prob.bin";
+    }
+    FILE* f = fopen(file.c_str(), "rb");
+    if (!f) return ICB_ERR_ARG;
+    char magic[8];
+    uint32_t n = 0;
+    struct __attribute__((packed)) Row {
+	uint8_t k, w, c1, c2;
+	double p;
+    };
+    std::vector<Row> rows;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "ICBPEMP1", 8) == 0 && fread(&n, 4, 1, f) == 1;
+    if (ok) {
+	try {
+	    rows.resize(n);
+	}
+	catch (...) {
+	    fclose(f);
+	    return ICB_ERR_NOMEM;
+	}
+	ok = fread(rows.data(), sizeof(Row), n, f) == n;
+    }
+    fclose(f);
+    if (!ok) return ICB_ERR_ARG;
+    for (const Row& r : rows) {
+	if (int(r.k) != kmer_size || std::abs(int(r.w) - window_size) > 2) continue;
+	if (r.c1 < 1 || r.c1 > 15 || r.c2 < 1 || r.c2 > 15) continue;
+	p_shared[(r.c1 - 1) * 15 + (r.c2 - 1)] = r.p;
+	p_shared[(r.c2 - 1) * 15 + (r.c1 - 1)] = r.p;
+    }
+    return ICB_OK;
+}
 
 // InitQualTab / InitQualTabNomin (reference qualscore.cpp:156-180)
 void icb_init_qual_tab(double tab[129], int nomin)

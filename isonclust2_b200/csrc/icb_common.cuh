@@ -23,6 +23,7 @@ struct icb_ctx {
     int device = 0;
     IcbAlignWorkspace* align_ws = nullptr;  // stage 3 buffers (align.cuh), created on first use
     int sm_count = ICB_SM_COUNT_FALLBACK;
+    int hi_priority = 0;  // greatest launch priority of the device (cudaDeviceGetStreamPriorityRange)
     cudaStream_t stream = nullptr;
     std::string last_error;
     bool timing = false;
@@ -69,6 +70,25 @@ inline cudaError_t icb_dfree(icb_ctx* ctx, void* p) { return p ? cudaFreeAsync(p
 	if ((ctx)->timing) (ctx)->timer_end(name);                            \
 	ICB_CUDA(ctx, cudaGetLastError());                                    \
     } while (0)
+
+// A launch with an execution priority (also recorded in a captured graph node).  The device loop's small kernels (commit /
+// decide / order / gather / full-list query) run at the device's greatest priority: the alignment kernels of the other
+// batches in flight fill every SM's register file, and a pending small CTA must not queue behind their backlog.
+template <class... KArgs, class... Args>
+inline cudaError_t icb_launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = prio;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 struct icb_readset {
     icb_ctx* ctx = nullptr;

@@ -221,7 +221,25 @@ __global__ void icb_k_classify(const double* __restrict__ err, const int32_t* __
 }
 
 template <bool SMEM_CNT>
+__device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a);
+
+template <bool SMEM_CNT>
 __global__ void __launch_bounds__(Q_THREADS) icb_k_query(IcbQueryArgs a)
+{
+    icb_query_body<SMEM_CNT>(a);
+}
+
+// the same with the arguments in device memory: the launch is part of a captured graph (dloop: one graph per round), what
+// changes from chunk to chunk (snapshot size, index views, scratch) is rewritten by a small copy instead of a new capture
+template <bool SMEM_CNT>
+__global__ void __launch_bounds__(Q_THREADS) icb_k_query_ptr(const IcbQueryArgs* __restrict__ ap)
+{
+    const IcbQueryArgs a = *ap;
+    icb_query_body<SMEM_CNT>(a);
+}
+
+template <bool SMEM_CNT>
+__device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a)
 {
     extern __shared__ uint32_t sm[];
     __shared__ int s_red[Q_THREADS / 32];
@@ -703,6 +721,28 @@ int icb_query_launch(icb_ctx* ctx, const IcbQueryArgs& a, int n_blocks, size_t s
     else {
 	ICB_LAUNCH(ctx, a.mode ? "index_query_full" : "index_query",
 		   icb_k_query<false><<<n_blocks, Q_THREADS, smem_bytes, ctx->stream>>>(a));
+    }
+    return ICB_OK;
+}
+
+int icb_query_launch_ptr(icb_ctx* ctx, const IcbQueryArgs* d_args, bool smem_cnt, int n_blocks, size_t smem_bytes)
+{
+    if (n_blocks <= 0) return ICB_OK;
+    static std::once_flag once;
+    static cudaError_t once_err = cudaSuccess;
+    std::call_once(once, [] {
+	once_err = cudaFuncSetAttribute(icb_k_query_ptr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	if (once_err == cudaSuccess)
+	    once_err = cudaFuncSetAttribute(icb_k_query_ptr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    ICB_CUDA(ctx, once_err);
+    if (smem_cnt) {
+	ICB_LAUNCH(ctx, "index_query_full",
+		   ICB_CUDA(ctx, icb_launch_prio(icb_k_query_ptr<true>, dim3(n_blocks), dim3(Q_THREADS), smem_bytes, ctx->stream, ctx->hi_priority, d_args)));
+    }
+    else {
+	ICB_LAUNCH(ctx, "index_query_full",
+		   ICB_CUDA(ctx, icb_launch_prio(icb_k_query_ptr<false>, dim3(n_blocks), dim3(Q_THREADS), smem_bytes, ctx->stream, ctx->hi_priority, d_args)));
     }
     return ICB_OK;
 }

@@ -99,4 +99,6 @@ int icb_index_insert_dev(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, con
 			 int n_max);
 int icb_index_update(icb_ctx* ctx, IcbIndex& idx, const icb_readset* rs, int r_old, int r_new, int cls, int nf_old, int nf_new);
 int icb_query_launch(icb_ctx* ctx, const IcbQueryArgs& a, int n_blocks, size_t smem_bytes);
+// arguments in device memory (the launch configuration is what a captured graph bakes in)
+int icb_query_launch_ptr(icb_ctx* ctx, const IcbQueryArgs* d_args, bool smem_cnt, int n_blocks, size_t smem_bytes);
 int icb_classify_errors(icb_ctx* ctx, const double* d_err, const int32_t* d_status, int64_t n, uint8_t* d_class);

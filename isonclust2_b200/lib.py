@@ -76,9 +76,25 @@ def load():
     L.icb_clusterer_seed.argtypes = [_p, _p, _i64]
     L.icb_clusterer_update_representative.argtypes = [_p, C.c_int32, C.c_int32]
     L.icb_cluster_batches.argtypes = [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]
+    L.icb_cluster_tree.argtypes = [_p, _p, _p, _p, _i32, _i32, _i32, _p, _p, C.POINTER(_i64), _p]
     L.icb_init_qual_tab.argtypes = [_p, _i32]
     L.icb_init_qual_tab.restype = None
     L.icb_quality_filter.argtypes = [_p, _i64, _dbl, _p]
     L.icb_sort_by_score.argtypes = [_p, _i64, _p]
+    # per-primitive face
+    L.icb_hpc_compress.argtypes = [_p, _p, _p, _p, _i64, _p, _p, _p]
+    L.icb_kmer_encode.argtypes = [_p, _p, _i64, _i32, _p, C.POINTER(_i64)]
+    L.icb_kmer_minimizers.argtypes = [_p, _p, _i64, _i32, _i32, _p, C.POINTER(_i64)]
+    L.icb_calc_error_rate.argtypes = [_p, _p, _p, _i64, _p, _p]
+    L.icb_index_create.argtypes = [_p, C.POINTER(_p)]
+    L.icb_index_destroy.argtypes = [_p]
+    L.icb_index_destroy.restype = None
+    L.icb_index_add.argtypes = [_p, C.c_uint32, _p, _i64]
+    L.icb_index_update_cluster.argtypes = [_p, C.c_uint32, _p, _i64, _p, _i64]
+    L.icb_index_query_hits.argtypes = [_p, _p, _i64, _p, _i64, _p, _i64, C.POINTER(_i64)]
+    L.icb_mapped_length.argtypes = [_p, _p, _p, _i64, _i64, _i64, C.c_int32, C.POINTER(_i64)]
+    L.icb_count_windows.argtypes = [_p, _p, _i64, _i32, _i32, C.POINTER(_i64)]
+    L.icb_align_traceback.argtypes = [_p, _p, _i32, _p, _p, _i64]
+    L.icb_load_p_shared.argtypes = [C.c_char_p, _i32, _i32, _p]
     _lib = L
     return L

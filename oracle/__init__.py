@@ -319,6 +319,8 @@ class Ref:
         L.ref_cluster.restype = _i32
         L.ref_cluster.argtypes = [_p, _p, _i32, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _i32]
         L.ref_aln_invoked.restype = C.c_uint
+        L.ref_n_clusters.restype = _i32
+        L.ref_n_clusters.argtypes = [_p]
         L.ref_cluster_sizes.argtypes = [_p, _p]
         L.ref_cluster_members.argtypes = [_p, _p, _p]
         L.ref_mindb_size.restype = _i64
@@ -406,6 +408,10 @@ class Ref:
     def mindb_after_updates(self, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs):
         return _mindb_after_updates(self.L.ref_mindb_after_updates, cls_mins, cls_offs, upd_cls, upd_mins, upd_offs)
 
+    def load_batch(self, path):
+        """LoadBatch (serialize.cpp:12-27) of a `.cer` written by RefBatch.save or by either CLI."""
+        return RefBatch(self, self.L.ref_load_batch(path.encode()), 0)
+
     def sorted_hits(self, cls_mins, cls_offs, mins, rev_mins):
         cm = np.ascontiguousarray(cls_mins); co = np.ascontiguousarray(cls_offs, np.int64)
         a = np.ascontiguousarray(mins); b = np.ascontiguousarray(rev_mins)
@@ -458,6 +464,16 @@ class RefBatch:
         self.ref.L.ref_cluster_members(self.h, _ptr(ids), _ptr(strands))
         return dict(n_clusters=nc, sizes=sizes, ids=ids, strands=strands,
                     n_aligned=self.ref.L.ref_aln_invoked() - before)
+
+    def cluster_lists(self):
+        """The cluster lists of a batch as it stands (e.g. loaded from a `.cer`): sizes, member read ids, strands."""
+        nc = self.ref.L.ref_n_clusters(self.h)
+        sizes = np.zeros(nc, np.int32)
+        self.ref.L.ref_cluster_sizes(self.h, _ptr(sizes))
+        tot = int(sizes.sum())
+        ids, strands = np.zeros(tot, np.int32), np.zeros(tot, np.int32)
+        self.ref.L.ref_cluster_members(self.h, _ptr(ids), _ptr(strands))
+        return dict(n_clusters=nc, sizes=sizes, ids=ids, strands=strands)
 
     def mindb(self):
         t = _i64()

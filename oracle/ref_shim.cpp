@@ -431,6 +431,9 @@ unsigned ref_aln_invoked() { return AlnInvoked(); }
 // cluster membership: for cluster c, members (original read indices parsed
 // from ProcSeq::Id) and their MatchStrand, INCLUDING the synthetic rep at
 // slot 0 (its Id is the founder's).  sizes[c] = members in cluster c.
+// number of clusters of a (loaded or clustered) batch
+int ref_n_clusters(void* h) { return int(static_cast<RefBatch*>(h)->batch->Cls.size()); }
+
 void ref_cluster_sizes(void* h, int32_t* sizes)
 {
     auto rb = static_cast<RefBatch*>(h);

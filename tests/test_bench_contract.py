@@ -90,3 +90,11 @@ def test_traffic_ratio_and_cpu_share():
         assert share == max(2, cores // 4)
     finally:
         del os.environ["LOCAL_WORLD_SIZE"]
+
+
+def test_reference_arm_tree():
+    """--tree: the reference's pipeline with the merge tree over `.cer` files; prints the digest of the root's assignment."""
+    r = _run(["--tree", "--batch-max-seq", "150"])
+    assert r.returncode == 0, r.stderr[-800:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert "merged as a tree" in line["metric"] and len(line["result_digest"]) == 64 and "4 batches" in line["cpu_baseline"]["sample"]

@@ -39,6 +39,8 @@ def _port_cluster(port, seq, qual, offs, k, w, mode, **kw):
 
 
 def _same(g, p):
+    # decided on the device (the host loop only takes chunks the device loop hands back: none in these cases)
+    assert g["stats"]["dl_chunks"] == g["stats"]["chunks"] > 0 and g["stats"]["dl_fallback_chunks"] == 0, g["stats"]
     assert (g["order"] == p["order"]).all()
     assert g["n_clusters"] == p["n_clusters"]
     assert (g["cluster"] == p["cluster"]).all(), np.flatnonzero(g["cluster"] != p["cluster"])[:10]
@@ -312,6 +314,34 @@ def test_cluster_benchmark_scale_vs_reference(ref, ctx, mode, n):
     assert g["stats"]["aln_invoked"] == rc["n_aligned"]
     if mode == 0:
         assert g["stats"]["tie_fallbacks"] > n // 20  # the candidate-order path is exercised at this scale
+    # decided on the device; the host loop may take the odd chunk in which the reference's hit map would rehash (reason 3)
+    assert g["stats"]["dl_chunks"] >= g["stats"]["chunks"] - 2 and (g["stats"]["dl_fallback_reasons"] & ~(1 << 3)) == 0, g["stats"]
+
+
+@pytest.mark.parametrize("engine", ["host", "mixed"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cluster_engines_agree_with_reference(ref, ctx, mode, engine, monkeypatch):
+    """The host loop (ICB_HOST_LOOP: decisions on the host, the engine the device loop hands unsupported chunks to) and a run in
+    which every third chunk is handed back (ICB_DLOOP_FORCE_FALLBACK) against the UNMODIFIED reference on a batch with
+    many tied candidates."""
+    k, w = 11, 15
+    n = 4000
+    seq, qual, offs = synth.make_reads(n, seed=100, err_set=(0.08,), n_genes=40000)
+    rb = ref.sort_and_sketch(seq, qual, offs, k, w)
+    _, _, order = rb.scores()
+    rc = rb.cluster(mode)
+    if engine == "host":
+        monkeypatch.setenv("ICB_HOST_LOOP", "1")
+    else:
+        monkeypatch.setenv("ICB_DLOOP_FORCE_FALLBACK", "3")
+    g = _gpu_cluster(ctx, seq, qual, offs, k, w, mode, 64)
+    rcl, rst = _per_slot(rc, order)
+    assert g["n_clusters"] == rc["n_clusters"] and (g["cluster"] == rcl).all() and (g["strand"] == rst).all()
+    assert g["stats"]["aln_invoked"] == rc["n_aligned"]
+    if engine == "host":
+        assert g["stats"]["dl_chunks"] == 0
+    else:
+        assert 0 < g["stats"]["dl_fallback_chunks"] < g["stats"]["chunks"] and g["stats"]["dl_chunks"] > 0
 
 
 def test_cluster_full_size_properties(ctx):
