@@ -39,8 +39,8 @@ static bool VERBOSE = false;
 static void print_help_sort()
 {
     std::cout << "\nsort - sort reads and write out batches:\n"
-		 "\t-B --batch-size        Batch size in kilobases (default: 50000).\n"
-		 "\t-M --batch-max-seq     Maximum number of sequences per batch (default: 30000).\n"
+		 "\t-B --batch-size        Batch size in kilobases (default: 50000)\n"
+		 "\t-M --batch-max-seq     Maximum number of sequences per batch (default: 3000).\n"
 		 "\t-k --kmer-size         Kmer size (default: 11).\n"
 		 "\t-w --window-size       Window size (default: 15).\n"
 		 "\t-m --min-shared        Minimum number of minimizers shared between read and cluster (default: 5).\n"
@@ -48,11 +48,11 @@ static void print_help_sort()
 		 "\t-x --mode  Clustering mode:\n"
 		 "\t           * sahlin (default): use minimizers first, alignment second \n"
 		 "\t           * fast: use minimizers only\n"
-		 "\t           * furious: use alignment only\n"
-		 "\t-g --low-cons-size     Use all sequences for consensus below this size (default: 50).\n"
-		 "\t-c --max-cons-size     Maximum number of sequences used for consensus (default: -150, disabled).\n"
-		 "\t-P --cons-period       Do not recalculate consensus after this many seqeunces added (default: 500).\n"
-		 "\t-r --mapped-threshold  Minimum mapped fraction of read to be included in cluster (default: 0.65).\n"
+		 "\t           * furious: always use alignment\n"
+		 "\t-g --low-cons-size     Use all sequences for consensus below this size (default: 20).\n"
+		 "\t-c --max-cons-size     Maximum number of sequences used for consensus (default: 150).\n"
+		 "\t-P --cons-period       Do not recalculate consensus after this many seuqences added (default: 500).\n"
+		 "\t-r --mapped-threshold  Minmum mapped fraction of read to be \tincluded in cluster (default: 0.65).\n"
 		 "\t-a --aligned-threshold Minimum aligned fraction of read to be included in cluster (default: 0.2).\n"
 		 "\t-f --min-fraction      Minimum fraction of minimizers shared compared to best hit, in order to continue "
 		 "mapping (default: 0.8).\n"

@@ -29,6 +29,11 @@
 #include "index.cuh"
 #include "helpers.h"
 #include "ref_order.h"
+#include "ref_order_hd.h"
+
+// reads per chunk of the greedy loop when the caller does not say: fewer, longer rounds of the device loop than 256 (7.4 k
+// instead of 12.4 k rounds per 1 M reads) at a few more candidate-order evaluations per read
+#define ICB_DEFAULT_CHUNK 512
 
 namespace {
 
@@ -125,6 +130,7 @@ struct icb_clusterer {
     // one round of the device loop as a captured graph: one driver call instead of ~17 launches per round (35 worker threads
     // launching kernel by kernel are bound by the driver's launch rate, not by the device)
     struct RoundKey {
+	IcbDLoopView view;  // every pointer and parameter the kernels of the round take by value
 	const void* p[12];
 	size_t smem_f;
 	int nb_f, smem_cnt_f, iters, mode, max_m, k, spec;
@@ -428,7 +434,7 @@ int icb_clusterer::plan_query(int Ctot, int cap, int mode, IcbQueryArgs& a, int 
 	words_smem = 2 * int64_t(cap) + bmWords;
 	stride += Ctot;
     }
-    if (mode == 1) stride += 2 * int64_t(Ctot);
+    if (mode == 1 || mode == 2) stride += 2 * int64_t(Ctot);  // first-hit table
     if (words_smem > smem_limit_words) return ctx->fail(ICB_ERR_ARG, "a read has too many minimizers for the candidate query");
     a.cap = cap;
     a.mode = mode;
@@ -1140,6 +1146,14 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
     qa.dl_pool_aln = V.aln;
     qa.dl_depmask = V.depmask;
     qa.dl_mw = V.mw;
+    // measured on configs[1] (1 M reads): fewer rounds (6.7 k instead of 7.4 k) but more candidate orders computed ahead of
+    // need and more speculative alignments: 395 k instead of 420 k reads/s -> off unless asked for
+    static const bool early_full = getenv("ICB_DLOOP_EARLY_FULL") != nullptr;
+    if (early_full && P.mode != 1) {
+	qa.dl_full_pool = V.full;
+	qa.dl_full_off = V.full_off;
+	qa.dl_full_n = V.full_n;
+    }
     query_base(this, qf, N, C0);
     // the full-list query is launched from the round graph: its launch configuration is planned for a snapshot size with
     // headroom, so that it (and the graph) only changes when the clusterer has outgrown it
@@ -1240,6 +1254,7 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
 	const void* ptrs[12] = {V.st, V.cands, V.full, V.cls_founder, ws.d_trace, ws.d_lines, ws.d_ends, ws.d_ticket, rs->d_seq, rs->d_bkt, d_qf_args,
 				V.hdr};
 	memcpy(key.p, ptrs, sizeof ptrs);
+	memcpy(&key.view, &V, sizeof V);
 	key.smem_f = smem_f;
 	key.nb_f = nb_f;
 	key.smem_cnt_f = qf.smem_cnt;
@@ -1398,6 +1413,68 @@ int icb_readset_prepare_host(icb_readset* rs)
     return ICB_OK;
 }
 
+// The candidate-order emulation (ref_order.h, ref_order_hd.h and their device form in dloop.cu) restates what THIS
+// libstdc++ does (bucket counts, list order of _Hashtable, introsort).  Once per process it is checked against the real
+// std::unordered_map + std::sort on random candidate lists; a library that behaves differently makes every clusterer
+// creation fail loudly instead of clustering differently from the reference built with it.
+static bool icb_ref_order_selfcheck()
+{
+    static const bool ok = [] {
+	struct C4 {
+	    int32_t id, strand, count, tmapped;
+	};
+	uint64_t s = 0x243F6A8885A308D3ull;
+	auto rnd = [&]() {
+	    s ^= s << 13;
+	    s ^= s >> 7;
+	    s ^= s << 17;
+	    return uint32_t(s >> 11);
+	};
+	IcbRefOrderScratch S;
+	std::vector<IcbSortedCand> grp;
+	for (int it = 0; it < 24; it++) {
+	    const int ncls = 40 + int(rnd() % 1500), nf = 50 + int(rnd() % 500), nr = 50 + int(rnd() % 500);
+	    const size_t hint = size_t(20) * size_t(nf + nr);
+	    std::vector<C4> v;
+	    for (int id = 0; id < ncls; id++)
+		for (int sd = 0; sd < 2; sd++)
+		    if (rnd() % 3) v.push_back(C4{id, sd ? -1 : 1, 1 + int(rnd() % 5), int(rnd() % (sd ? nr : nf))});
+	    std::vector<C4> ins(v);
+	    std::stable_sort(ins.begin(), ins.end(), [](const C4& a, const C4& b) {
+		if (a.strand != b.strand) return a.strand > b.strand;
+		return a.tmapped < b.tmapped;
+	    });
+	    std::unordered_map<std::pair<int, int>, unsigned, IcbPairHash> m(hint);
+	    for (auto& c : ins) m[std::make_pair(c.id, c.strand)] = unsigned(c.count);
+	    std::vector<IcbSortedCand> want;
+	    std::vector<icb_sort_hd::Key> keys;
+	    for (auto& kv : m) {
+		keys.push_back(icb_sort_hd::Key(kv.second) << 32 | icb_sort_hd::Key(want.size()));
+		want.push_back(IcbSortedCand{kv.second, unsigned(kv.first.first), kv.first.second});
+	    }
+	    const std::vector<IcbSortedCand> iter_order(want);
+	    std::sort(want.begin(), want.end(), [](const IcbSortedCand& a, const IcbSortedCand& b) { return a.Size > b.Size; });
+	    const unsigned target = want.empty() ? 0 : want[0].Size;
+	    icb_reference_order_group(v.data(), int(v.size()), hint, target, S, grp);
+	    icb_sort_hd::introsort_group(keys.data(), long(keys.size()), target);
+	    size_t q = 0, q2 = 0;
+	    for (auto& w : want)
+		if (w.Size == target) {
+		    if (q >= grp.size() || grp[q].Cls != w.Cls || grp[q].Strand != w.Strand) return false;
+		    q++;
+		    while (q2 < keys.size() && uint32_t(keys[q2] >> 32) != target) q2++;
+		    if (q2 >= keys.size()) return false;
+		    const IcbSortedCand& e = iter_order[uint32_t(keys[q2])];
+		    if (e.Cls != w.Cls || e.Strand != w.Strand) return false;
+		    q2++;
+		}
+	    if (q != grp.size()) return false;
+	}
+	return true;
+    }();
+    return ok;
+}
+
 // parameters of a clustering run -> clusterer (validated; the n_max table is evaluated with the HOST libm)
 static int clusterer_configure(icb_ctx* ctx, icb_clusterer* cl, icb_readset* rs, const icb_cluster_params* p)
 {
@@ -1407,10 +1484,13 @@ static int clusterer_configure(icb_ctx* ctx, icb_clusterer* cl, icb_readset* rs,
     if (p->mode < 0 || p->mode > 2) return ctx->fail(ICB_ERR_ARG, "mode must be 0 (sahlin), 1 (fast) or 2 (furious)");
     if (!rs->host_ready) return ctx->fail(ICB_ERR_STATE, "read set host mirror missing");
     if (rs->max_m >= 32768) return ctx->fail(ICB_ERR_ARG, "a read has 32768 or more minimizers per strand");
+    if (!icb_ref_order_selfcheck())
+	return ctx->fail(ICB_ERR_STATE, "the C++ library's unordered_map / std::sort do not behave like the ones the candidate-order "
+					"emulation restates (libstdc++): results would differ from a reference built with this library");
     cl->ctx = ctx;
     cl->rs = rs;
     cl->P = *p;
-    if (cl->P.chunk_size <= 0) cl->P.chunk_size = 256;
+    if (cl->P.chunk_size <= 0) cl->P.chunk_size = ICB_DEFAULT_CHUNK;
     // n_max table (cluster.cpp:335-349: pow(pError, n) >= minProbNoHits with the HOST libm; monotone in n)
     if (p->mode != 2) {
 	for (int c = 0; c < 225; c++) {
@@ -1418,7 +1498,10 @@ static int clusterer_configure(icb_ctx* ctx, icb_clusterer* cl, icb_readset* rs,
 	    if (!(ps == ps)) return ctx->fail(ICB_ERR_NO_PEMP, "Empirical probability lookup failure!");
 	    double pe = 1.0 - ps;
 	    int32_t n = -1;
-	    for (int32_t t = 0; t < (1 << 20); t++) {
+	    // a run of missed minimizers is never longer than a sketch: the scan stops there (with pError = 1, or
+	    // minProbNoHits <= 0, every run is bridged and the scan would otherwise walk to its cap for all 225 classes)
+	    const int32_t t_max = rs->max_m + 1;
+	    for (int32_t t = 0; t <= t_max; t++) {
 		if (std::pow(pe, double(t)) >= p->min_prob_no_hits) n = t;
 		else break;
 	    }
@@ -1519,7 +1602,7 @@ int icb_clusterer_update_representative(icb_clusterer* cl, int32_t cluster, int3
     return cl->update_representative(cluster, rep_read);
 }
 
-int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,
+static int cluster_batches_impl(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,
 			int32_t n_batches, int32_t n_workers, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
 			icb_cluster_stats* stats)
 {
@@ -1549,7 +1632,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 	ctx->pool_ctx.push_back(kid);
 	ctx->pool_cl.push_back(nullptr);
     }
-    const int want_chunk = params->chunk_size > 0 ? params->chunk_size : 256;
+    const int want_chunk = params->chunk_size > 0 ? params->chunk_size : ICB_DEFAULT_CHUNK;
     for (int w = 0; w < nw; w++) {
 	icb_ctx* c = ctx->pool_ctx[w];
 	c->timing = ctx->timing;
@@ -1623,7 +1706,7 @@ int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const
 // clusterers: a node's index, representatives and cluster ids stay on the device between levels, and a merge is
 // icb_cluster_reads on the left node's clusterer over the right node's representatives in the right node's cluster order
 // (what cluster.cpp:108-261 does with rightBatch->Cls[i][REP]).  Nothing is re-uploaded, re-sketched or re-indexed.
-int icb_cluster_tree(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds, int32_t n_batches,
+static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds, int32_t n_batches,
 		     int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
 		     icb_cluster_stats* stats)
 {
@@ -1899,6 +1982,37 @@ int icb_clusterer_stats(const icb_clusterer* cl, icb_cluster_stats* out)
     if (!cl || !out) return ICB_ERR_ARG;
     *out = cl->stats;
     return ICB_OK;
+}
+
+// the C ABI never throws: a failing thread start (std::system_error) or allocation inside becomes an error code
+int icb_cluster_batches(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds,
+			int32_t n_batches, int32_t n_workers, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
+			icb_cluster_stats* stats)
+{
+    try {
+	return cluster_batches_impl(rs, params, order, bounds, n_batches, n_workers, cluster_of, strand_of, n_clusters, stats);
+    }
+    catch (const std::bad_alloc&) {
+	return rs ? rs->ctx->fail(ICB_ERR_NOMEM, "out of host memory") : ICB_ERR_NOMEM;
+    }
+    catch (const std::exception& e) {
+	return rs ? rs->ctx->fail(ICB_ERR_STATE, e.what()) : ICB_ERR_STATE;
+    }
+}
+
+int icb_cluster_tree(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds, int32_t n_batches,
+		     int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
+		     icb_cluster_stats* stats)
+{
+    try {
+	return cluster_tree_impl(rs, params, order, bounds, n_batches, n_workers, min_cls_size, cluster_of, strand_of, n_clusters, stats);
+    }
+    catch (const std::bad_alloc&) {
+	return rs ? rs->ctx->fail(ICB_ERR_NOMEM, "out of host memory") : ICB_ERR_NOMEM;
+    }
+    catch (const std::exception& e) {
+	return rs ? rs->ctx->fail(ICB_ERR_STATE, e.what()) : ICB_ERR_STATE;
+    }
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ constexpr int DL_MAXW = 32;	   // words of a chunk-position bitmask: chunks of u
 constexpr int DL_SPEC = 3;	   // alignments a read with tied candidates may have in flight at once (the next ones of its plan)
 constexpr int DL_THREADS = 256;	   // CTA size of the decision kernels
 constexpr int DL_NMAX_S = 4096;   // candidates (cluster, strand) of one read the order emulation sorts in shared memory: the usual
-constexpr int DL_NMAX_L = 12288;  // kernel, and the one for reads that hit a large (merged) index
+constexpr int DL_NMAX_L = 8192;   // kernel, and the one for reads that hit a large (merged) index (powers of two: bitonic padding)
 
 enum : uint8_t { DL_NONE = 0, DL_JOIN = 1, DL_NEW = 2, DL_NEED_PAIR = 3, DL_NEED_FULL = 4, DL_NEED_ORDER = 5 };
 enum : int32_t { DL_ALN_UNKNOWN = -1, DL_ALN_REDO32 = -3 };

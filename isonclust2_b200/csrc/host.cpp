@@ -9,6 +9,7 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -95,7 +96,7 @@ void icb_init_qual_tab(double tab[129], int nomin)
 }
 
 // the read filter of PrepareSortedBatch / ClusterSortedReads (qualscore.cpp:56, cluster.cpp:157)
-int icb_quality_filter(const double* err, int64_t n, double min_qual, uint8_t* filtered)
+static int quality_filter_impl(const double* err, int64_t n, double min_qual, uint8_t* filtered)
 {
     if (n < 0 || (n > 0 && (!err || !filtered))) return ICB_ERR_ARG;
     parallel_ranges(n, 1 << 16, [&](int64_t a, int64_t b) {
@@ -108,7 +109,7 @@ int icb_quality_filter(const double* err, int64_t n, double min_qual, uint8_t* f
 // strict weak ordering is unique — (score descending, index ascending) — so sorted runs merged stably give the same
 // permutation as one std::stable_sort; with a NaN among the scores the comparator is no strict weak ordering and the
 // single library call is kept.
-int icb_sort_by_score(const double* score, int64_t n, int32_t* order)
+static int sort_by_score_impl(const double* score, int64_t n, int32_t* order)
 {
     if (n < 0 || n > 0x7fffffff || (n > 0 && (!score || !order))) return ICB_ERR_ARG;
     std::iota(order, order + n, 0);
@@ -140,6 +141,33 @@ int icb_sort_by_score(const double* score, int64_t n, int32_t* order)
     }
     if (src != order) std::copy(src, src + n, order);
     return ICB_OK;
+}
+
+// the C ABI never throws: thread creation (std::system_error) or allocation failures inside become error codes
+int icb_quality_filter(const double* err, int64_t n, double min_qual, uint8_t* filtered)
+{
+    try {
+	return quality_filter_impl(err, n, min_qual, filtered);
+    }
+    catch (const std::bad_alloc&) {
+	return ICB_ERR_NOMEM;
+    }
+    catch (...) {
+	return ICB_ERR_STATE;
+    }
+}
+
+int icb_sort_by_score(const double* score, int64_t n, int32_t* order)
+{
+    try {
+	return sort_by_score_impl(score, n, order);
+    }
+    catch (const std::bad_alloc&) {
+	return ICB_ERR_NOMEM;
+    }
+    catch (...) {
+	return ICB_ERR_STATE;
+    }
 }
 
 }  // extern "C"

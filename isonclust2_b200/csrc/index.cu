@@ -247,6 +247,7 @@ __device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a)
     __shared__ int s_red3[Q_THREADS / 32];
     __shared__ int s_n;
     __shared__ uint32_t s_off;
+    __shared__ unsigned long long s_off64;
     __shared__ int s_ok;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Ctot = a.C0 + a.n_chunk;
@@ -263,8 +264,11 @@ __device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a)
 	const int nf = a.nf[r], nr = a.nr[r];
 	const icb_minimizer* mins = a.arena + a.min_off[r];
 	__syncthreads();
+	// first-hit table: the full-list mode, and the pool mode of the device loop (which emits the full list right away for
+	// reads whose best candidates are tied, see below)
+	const bool want_first = a.mode == 1 || (a.mode == 2 && a.dl_full_pool != nullptr);
 	for (int i = tid; i < Ctot; i += Q_THREADS) cnt[i] = 0;
-	if (a.mode == 1)
+	if (want_first)
 	    for (int i = tid; i < 2 * Ctot; i += Q_THREADS) first[i] = 0xFFFFFFFFu;
 	if (tid == 0) s_n = 0;
 	__syncthreads();
@@ -275,12 +279,12 @@ __device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a)
 	    const uint32_t inc = 1u << (16 * half);
 	    for_each_posting(a.main_idx, m.Min, [&](uint32_t id) {
 		atomicAdd(&cnt[id], inc);
-		if (a.mode == 1) atomicMin(&first[2 * id + half], m.Index);
+		if (want_first) atomicMin(&first[2 * id + half], m.Index);
 	    });
 	    for_each_posting(a.chunk_idx, m.Min, [&](uint32_t id) {
 		if (int(id) - a.C0 < pos) {
 		    atomicAdd(&cnt[id], inc);
-		    if (a.mode == 1) atomicMin(&first[2 * id + half], m.Index);
+		    if (want_first) atomicMin(&first[2 * id + half], m.Index);
 		}
 	    });
 	}
@@ -315,10 +319,10 @@ __device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a)
 	    hits += s_red3[i];
 	}
 	IcbQueryHeader* hdr = a.hdr + item;
-	if (a.mode == 1) {
-	    // records in ascending id order (the host's counting sort relies on it): thread t owns a contiguous id range and
-	    // its output offset is the exclusive prefix of the live keys before that range
-	    IcbCand* out = a.cands + a.full_off[item];
+	// every (cluster, strand) with a hit as a record {id, strand, count, first hit}, in ascending id order (the host's counting
+	// sort relies on it): thread t owns a contiguous id range, its output offset is the exclusive prefix of the live keys
+	// before that range.  Leaves the number of records in s_n.
+	auto emit_full = [&](IcbCand* out) {
 	    const int per = (Ctot + Q_THREADS - 1) / Q_THREADS;
 	    const int lo = min(Ctot, tid * per), hi = min(Ctot, lo + per);
 	    int mine = 0;
@@ -354,8 +358,12 @@ __device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a)
 		    }
 		}
 	    }
+	    __syncthreads();
 	    if (tid == Q_THREADS - 1) s_n = slot;
 	    __syncthreads();
+	};
+	if (a.mode == 1) {
+	    emit_full(a.cands + a.full_off[item]);
 	    if (tid == 0) {
 		hdr->top_snap = top;
 		hdr->n_cand = s_n;
@@ -370,6 +378,56 @@ __device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a)
 		}
 	    }
 	    continue;
+	}
+	if (a.mode == 2 && a.dl_full_pool) {
+	    // ---- reads whose best candidates are tied will need the reference's candidate ORDER, hence their full candidate
+	    // list: it is emitted now, while the counts are at hand (the device loop would otherwise come back for it a round
+	    // trip later).  Best = over snapshot and provisional candidates alike; a tie the committed founders only reveal later
+	    // still takes the separate full-list query.
+	    int ta = 0;
+	    for (int i = tid; i < Ctot; i += Q_THREADS) {
+		const uint32_t v = cnt[i];
+		ta = max(ta, max(int(v & 0xffff), int(v >> 16)));
+	    }
+#pragma unroll
+	    for (int d = 16; d; d >>= 1) ta = max(ta, __shfl_xor_sync(0xffffffffu, ta, d));
+	    __syncthreads();
+	    if (lane == 0) s_red[warp] = ta;
+	    __syncthreads();
+	    ta = 0;
+	    for (int i = 0; i < Q_THREADS / 32; i++) ta = max(ta, s_red[i]);
+	    int nt = 0;
+	    for (int i = tid; i < Ctot; i += Q_THREADS) {
+		const uint32_t v = cnt[i];
+		nt += (int(v & 0xffff) == ta) + (int(v >> 16) == ta);
+	    }
+#pragma unroll
+	    for (int d = 16; d; d >>= 1) nt += __shfl_xor_sync(0xffffffffu, nt, d);
+	    __syncthreads();
+	    if (lane == 0) s_red[warp] = nt;
+	    __syncthreads();
+	    if (tid == 0) {
+		int n2 = 0;
+		for (int i = 0; i < Q_THREADS / 32; i++) n2 += s_red[i];
+		s_ok = 0;
+		if (ta > 0 && n2 >= 2 && !(unsigned(ta) < unsigned(a.min_shared))) {
+		    const unsigned long long off = atomicAdd(&a.dl_state->full_cursor, (unsigned long long)live);
+		    if (off + (unsigned long long)live <= a.dl_state->full_cap) {
+			s_ok = 1;
+			s_off64 = off;
+		    }
+		}
+	    }
+	    __syncthreads();
+	    if (s_ok) {
+		emit_full(a.dl_full_pool + s_off64);
+		if (tid == 0) {
+		    a.dl_full_n[pos] = s_n;
+		    a.dl_full_off[pos] = int64_t(s_off64);
+		    s_n = 0;
+		}
+	    }
+	    __syncthreads();
 	}
 	if (a.mode == 2) {
 	    // ---- pool mode (device-resident loop): the relevant candidates of mode 0, written as records into the chunk's

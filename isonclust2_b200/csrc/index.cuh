@@ -87,6 +87,7 @@ struct IcbQueryArgs {
     const int32_t* dl_n_list;		// number of entries of `list`, written by the gather kernel
     IcbCand* dl_pool;			// mode 2: candidate pool (records) ...
     int32_t* dl_pool_aln;		// ... and its alignment results, reset to "unknown"
+    IcbCand* dl_full_pool;		// mode 2: full-list pool; reads whose best candidates are tied get their full list right away
     uint32_t* dl_depmask;		// [pos][dl_mw] provisional founders among the read's candidates
     int32_t dl_mw;
     int64_t* dl_full_off;		// mode 1: per chunk position, where the read's full list starts / its length

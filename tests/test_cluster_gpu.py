@@ -314,8 +314,9 @@ def test_cluster_benchmark_scale_vs_reference(ref, ctx, mode, n):
     assert g["stats"]["aln_invoked"] == rc["n_aligned"]
     if mode == 0:
         assert g["stats"]["tie_fallbacks"] > n // 20  # the candidate-order path is exercised at this scale
-    # decided on the device; the host loop may take the odd chunk in which the reference's hit map would rehash (reason 3)
-    assert g["stats"]["dl_chunks"] >= g["stats"]["chunks"] - 2 and (g["stats"]["dl_fallback_reasons"] & ~(1 << 3)) == 0, g["stats"]
+    # decided on the device; the host loop may take the odd chunk in which a read's candidate list exceeds the order kernel's
+    # shared-memory plan (reason 2) or the reference's hit map would rehash (reason 3): fast mode against > 10 000 clusters
+    assert g["stats"]["dl_chunks"] >= 0.8 * g["stats"]["chunks"] and (g["stats"]["dl_fallback_reasons"] & ~((1 << 2) | (1 << 3))) == 0, g["stats"]
 
 
 @pytest.mark.parametrize("engine", ["host", "mixed"])
