@@ -52,7 +52,7 @@ def digest_key(reads, seed, mode, batch_max_seq, n_genes):
 
 
 INT_PIPE_PEAK_GCUPS = 148 * 4 * 16 * 1.965 / 7.5  # SMs x sub-partitions x ALU lanes/clk x GHz / ALU instructions per cell = 2482
-KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_full", "index_insert", "align_dp",
+KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_pool", "index_query_full", "index_insert", "align_dp",
            "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "sketch_reads_cta", "gather_minimizers",
            "dl_init", "dl_decide", "dl_order", "dl_order_large", "dl_commit", "dl_gather", "dl_finalize")
 
@@ -210,10 +210,18 @@ def run_ours(args):
     digest = result_digest(res["n_clusters"], res["cluster"], res["strand"], res["stats"]["aln_invoked"])
     if args.quick:  # tuning runs: the device-resident number and the loop's counters only
         stop.set()
-        ms = float(np.mean(times))
-        print(json.dumps({"quick": True, "value": world * n_reads / (ms * 1e-3), "ms_per_step": ms, "gpu_launches": int(launches),
-                          "result_digest": digest, "cluster_stats": res["stats"], "env": {k: v for k, v in os.environ.items() if k.startswith("ICB_")}}),
-              flush=True)
+        tq = torch.tensor([float(np.mean(times))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        ms = float(tq[0])
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": world * n_reads / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world,
+                              "gpu_launches": int(launches), "result_digest": digest, "cluster_stats": res["stats"],
+                              "host_cores_per_rank": share, "clocks": summarize_clocks(samples),
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("ICB_")}}), flush=True)
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     # ---------------- kernel-level passes (not part of the timed steps): event pairs around every launch, ONE stream, so the
@@ -300,9 +308,9 @@ def run_ours(args):
                     "traffic_source": t_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms}
     # index probe kernel (SURVEY 8d bytes: minimizers in 12 B + bucket heads 8 B per probe, 8 B per posting node walked —
     # twice: counts, then the bitmaps of the relevant candidates —, 16 B per candidate record out)
-    q_n, q_ms = ks["index_query"]
+    q_n, q_ms = ks["index_query_pool"]
     probe_bytes = 20 * ser_mins + 2 * 8 * ser_stats["hits"] + 16 * ser_stats["cands"]
-    index_probe = {"bound": "hbm", "kernel": "icb_k_query (index_query)", "launches": q_n, "kernel_ms": q_ms,
+    index_probe = {"bound": "hbm", "kernel": "icb_k_query, pool mode (index_query_pool)", "launches": q_n, "kernel_ms": q_ms,
                    "reads": ser_reads, "hits": ser_stats["hits"], "candidates": ser_stats["cands"],
                    "algorithmic_bytes": probe_bytes, "achieved": probe_bytes / (q_ms * 1e-3) / 1e9 if q_ms > 0 else 0.0, "peak": peak,
                    "unit": "GB/s", "frac": (probe_bytes / (q_ms * 1e-3) / 1e9 / peak) if q_ms > 0 else 0.0,
@@ -559,7 +567,7 @@ def run_reference(args, quiet=False):
     used = min(cores, nb) if kind == "reference" else 1
     full = n_reads == args.reads
     cb = {"value": v, "unit": "reads/s", "cores": cores if kind == "reference" else 1, "kind": kind,
-          "sample": (f"the whole workload ({n_reads} reads" if full else f"the first {n_reads} of the workload's {args.reads} reads (") +
+          "sample": (f"the whole workload ({n_reads} reads, " if full else f"the first {n_reads} of the workload's {args.reads} reads (") +
                     f"{'' if full else 'same gene set, '}{nb} batches by the main.cpp:149-199 rule, M={args.batch_max_seq}): sort + sketch on "
                     f"{cores} TBB threads, then {used} single-threaded `cluster -x {mode}` jobs in parallel; {dt:.1f} s per step, "
                     f"{ncl} clusters; {n_steps} step(s) timed" + (f" of the {args.steps} requested" if n_steps != args.steps else ""),

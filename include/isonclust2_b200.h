@@ -219,6 +219,21 @@ int icb_cluster_tree(icb_readset* rs, const icb_cluster_params* params, const in
 		     int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
 		     icb_cluster_stats* stats);
 
+/* The same with every decision kept, for a caller that rebuilds the batch of every node — cluster lists in the order the
+ * reference appends them, its MinDB, its `.cer` (the CLI's `tree`): the leaves' own decisions per sorted slot (batch-local
+ * cluster ids: a read founds a cluster iff its id equals the number of clusters before it), and per merge job, in the order
+ * a sequential driver runs them (level by level, left to right; nodes are named by their first batch), where each cluster
+ * of the right node went: -1 dropped by MinClsSize, an id >= the left node's cluster count at that moment = founded there. */
+typedef struct icb_tree_trace icb_tree_trace;
+int icb_cluster_tree_traced(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds, int32_t n_batches,
+			    int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
+			    icb_cluster_stats* stats, icb_tree_trace** trace);
+void icb_tree_trace_destroy(icb_tree_trace* trace);
+int32_t icb_tree_trace_jobs(const icb_tree_trace* trace);
+int icb_tree_trace_leaves(const icb_tree_trace* trace, const int32_t** cluster_of, const int32_t** strand_of);
+int icb_tree_trace_job(const icb_tree_trace* trace, int32_t j, int32_t* left_batch, int32_t* right_batch, int64_t* n_right,
+		       const int32_t** cluster_of, const int32_t** strand_of);
+
 /* ------------------------------------------------------------------ per-primitive face
  * One entry point per reference function of the path, on HOST arrays, for a host that keeps its own ClusterSortedReads
  * (cluster.cpp:67-322) and containers, and for the C++ header shim include/isonclust2_compat/ (hpc.h, kmer_index.h,

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -1555,6 +1556,16 @@ static void add_stats(icb_cluster_stats& t, const icb_cluster_stats& s)
     t.dl_stop_full += s.dl_stop_full; t.dl_stop_pair_first += s.dl_stop_pair_first; t.dl_stop_pair_again += s.dl_stop_pair_again;
 }
 
+// what icb_cluster_tree_traced keeps for a caller that rebuilds the batches of every node (the CLI's `tree`)
+struct icb_tree_trace {
+    struct Job {
+	int32_t left, right, level;
+	std::vector<int32_t> cluster_of, strand_of;  // per cluster of the right node: -1 = dropped (MinClsSize), else its cluster in the merged node
+    };
+    std::vector<int32_t> leaf_cluster, leaf_strand;  // per sorted slot: the leaf's own decision (batch-local ids)
+    std::vector<Job> jobs;
+};
+
 void icb_worker_pool_release(icb_ctx* ctx)
 {
     for (size_t w = 0; w < ctx->pool_ctx.size(); w++) {
@@ -1708,7 +1719,7 @@ static int cluster_batches_impl(icb_readset* rs, const icb_cluster_params* param
 // (what cluster.cpp:108-261 does with rightBatch->Cls[i][REP]).  Nothing is re-uploaded, re-sketched or re-indexed.
 static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds, int32_t n_batches,
 		     int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
-		     icb_cluster_stats* stats)
+		     icb_cluster_stats* stats, icb_tree_trace* trace)
 {
     if (!rs || !params || n_batches < 0 || (n_batches > 0 && (!order || !bounds || !cluster_of || !strand_of))) return ICB_ERR_ARG;
     icb_ctx* ctx = rs->ctx;
@@ -1769,6 +1780,12 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
 	}
 	is_left[0] = 1;	 // the root keeps its clusterer until the counts are read
     }
+    if (trace) {
+	trace->leaf_cluster.assign(size_t(bounds[n_batches]), -1);
+	trace->leaf_strand.assign(size_t(bounds[n_batches]), 0);
+	trace->jobs.clear();
+    }
+    std::mutex trace_mutex;
     // ---- leaves
     {
 	std::atomic<int> next(0);
@@ -1797,6 +1814,10 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
 		nd.csize.assign(nd.reps.size(), 0);
 		for (int64_t t = bounds[b]; t < bounds[b + 1]; t++)
 		    if (cluster_of[t] >= 0) nd.csize[size_t(cluster_of[t])]++;
+		if (trace) {  // the leaf's own decisions (batch-local cluster ids), before the merges rename them
+		    std::copy(cluster_of + bounds[b], cluster_of + bounds[b + 1], trace->leaf_cluster.begin() + bounds[b]);
+		    std::copy(strand_of + bounds[b], strand_of + bounds[b + 1], trace->leaf_strand.begin() + bounds[b]);
+		}
 		if (!is_left[size_t(b)]) {
 		    icb_clusterer_destroy(nd.cl);
 		    nd.cl = nullptr;
@@ -1812,7 +1833,9 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
     std::vector<int> cur(static_cast<size_t>(n_batches));
     for (int b = 0; b < n_batches; b++) cur[size_t(b)] = b;
     int64_t merges = 0;
+    int level_no = 0;
     while (cur.size() > 1 && !first_err.load()) {
+	level_no++;
 	struct Job {
 	    int left, right;
 	};
@@ -1869,6 +1892,16 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
 			sg[q] = ts[size_t(g)] == -1 ? -sg[q] : sg[q];
 		    }
 		}
+		if (trace) {
+		    std::lock_guard<std::mutex> g(trace_mutex);
+		    icb_tree_trace::Job tj;
+		    tj.left = jobs[size_t(j)].left;
+		    tj.right = jobs[size_t(j)].right;
+		    tj.level = level_no;
+		    tj.cluster_of = tc;
+		    tj.strand_of = ts;
+		    trace->jobs.push_back(std::move(tj));
+		}
 		L.reps = L.cl->founder;
 		L.hi = R.hi;
 		L.depth++;
@@ -1919,6 +1952,10 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
 	stats->ms_wall = wall.lap();
 	stats->tree_merges = merges;
     }
+    if (trace)  // the order a sequential driver would run them in: level by level, left to right
+	std::sort(trace->jobs.begin(), trace->jobs.end(), [](const icb_tree_trace::Job& a, const icb_tree_trace::Job& b) {
+	    return a.level != b.level ? a.level < b.level : a.left < b.left;
+	});
     if (first_err.load()) {
 	for (auto& e : werr)
 	    if (!e.empty()) return ctx->fail(first_err.load(), e);
@@ -2005,7 +2042,7 @@ int icb_cluster_tree(icb_readset* rs, const icb_cluster_params* params, const in
 		     icb_cluster_stats* stats)
 {
     try {
-	return cluster_tree_impl(rs, params, order, bounds, n_batches, n_workers, min_cls_size, cluster_of, strand_of, n_clusters, stats);
+	return cluster_tree_impl(rs, params, order, bounds, n_batches, n_workers, min_cls_size, cluster_of, strand_of, n_clusters, stats, nullptr);
     }
     catch (const std::bad_alloc&) {
 	return rs ? rs->ctx->fail(ICB_ERR_NOMEM, "out of host memory") : ICB_ERR_NOMEM;
@@ -2013,6 +2050,53 @@ int icb_cluster_tree(icb_readset* rs, const icb_cluster_params* params, const in
     catch (const std::exception& e) {
 	return rs ? rs->ctx->fail(ICB_ERR_STATE, e.what()) : ICB_ERR_STATE;
     }
+}
+
+int icb_cluster_tree_traced(icb_readset* rs, const icb_cluster_params* params, const int32_t* order, const int64_t* bounds, int32_t n_batches,
+			    int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
+			    icb_cluster_stats* stats, icb_tree_trace** trace)
+{
+    if (!trace) return ICB_ERR_ARG;
+    *trace = nullptr;
+    try {
+	std::unique_ptr<icb_tree_trace> t(new icb_tree_trace);
+	const int rc = cluster_tree_impl(rs, params, order, bounds, n_batches, n_workers, min_cls_size, cluster_of, strand_of, n_clusters, stats,
+					 t.get());
+	if (rc) return rc;
+	*trace = t.release();
+	return ICB_OK;
+    }
+    catch (const std::bad_alloc&) {
+	return rs ? rs->ctx->fail(ICB_ERR_NOMEM, "out of host memory") : ICB_ERR_NOMEM;
+    }
+    catch (const std::exception& e) {
+	return rs ? rs->ctx->fail(ICB_ERR_STATE, e.what()) : ICB_ERR_STATE;
+    }
+}
+
+void icb_tree_trace_destroy(icb_tree_trace* t) { delete t; }
+
+int32_t icb_tree_trace_jobs(const icb_tree_trace* t) { return t ? int32_t(t->jobs.size()) : 0; }
+
+int icb_tree_trace_leaves(const icb_tree_trace* t, const int32_t** cluster_of, const int32_t** strand_of)
+{
+    if (!t || !cluster_of || !strand_of) return ICB_ERR_ARG;
+    *cluster_of = t->leaf_cluster.data();
+    *strand_of = t->leaf_strand.data();
+    return ICB_OK;
+}
+
+int icb_tree_trace_job(const icb_tree_trace* t, int32_t j, int32_t* left_batch, int32_t* right_batch, int64_t* n_right,
+		       const int32_t** cluster_of, const int32_t** strand_of)
+{
+    if (!t || j < 0 || size_t(j) >= t->jobs.size() || !left_batch || !right_batch || !n_right || !cluster_of || !strand_of) return ICB_ERR_ARG;
+    const icb_tree_trace::Job& job = t->jobs[size_t(j)];
+    *left_batch = job.left;
+    *right_batch = job.right;
+    *n_right = int64_t(job.cluster_of.size());
+    *cluster_of = job.cluster_of.data();
+    *strand_of = job.strand_of.data();
+    return ICB_OK;
 }
 
 }  // extern "C"

@@ -773,11 +773,11 @@ int icb_query_launch(icb_ctx* ctx, const IcbQueryArgs& a, int n_blocks, size_t s
     });
     ICB_CUDA(ctx, once_err);
     if (a.smem_cnt) {
-	ICB_LAUNCH(ctx, a.mode ? "index_query_full" : "index_query",
+	ICB_LAUNCH(ctx, a.mode == 0 ? "index_query" : (a.mode == 1 ? "index_query_full" : "index_query_pool"),
 		   icb_k_query<true><<<n_blocks, Q_THREADS, smem_bytes, ctx->stream>>>(a));
     }
     else {
-	ICB_LAUNCH(ctx, a.mode ? "index_query_full" : "index_query",
+	ICB_LAUNCH(ctx, a.mode == 0 ? "index_query" : (a.mode == 1 ? "index_query_full" : "index_query_pool"),
 		   icb_k_query<false><<<n_blocks, Q_THREADS, smem_bytes, ctx->stream>>>(a));
     }
     return ICB_OK;

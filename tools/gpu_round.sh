@@ -1,6 +1,7 @@
 #!/bin/bash
 # Dev tool: one full evidence pass on the B200 box (run through gpurun from the repo root).
-#   tools/gpu_round.sh <tag> [tests] [bench] [ref] [launches] [ncu_sketch] [ncu_align] [ncu_query]
+#   tools/gpu_round.sh <tag> [tests] [bench] [ref] [launches] [ncu_sketch] [ncu_align] [ncu_query] [ncu_order]
+# (ncu passes launch the device loop's kernels one by one, ICB_NO_GRAPH: the same kernels, individually visible)
 # Everything lands in gpurun_out/<tag>_*; copy what should be judged into profiles/.
 tag=${1:-run}; shift
 what=${*:-tests bench ref launches ncu_sketch ncu_align}
@@ -21,8 +22,8 @@ if has ref; then
     tail -c 400 $O/${tag}_bench_reference.json
 fi
 if has launches; then
-    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${tag}_launches.csv \
-        python bench.py --reads 20000 --steps 1 --warmup 3 --no-cpu-baseline > $O/${tag}_launches_bench.log 2>&1
+    ICB_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file $O/${tag}_launches.csv \
+        python bench.py --reads 20000 --steps 1 --warmup 3 --quick > $O/${tag}_launches_bench.log 2>&1
     echo "launches exit $?"
 fi
 if has ncu_sketch; then
@@ -38,9 +39,15 @@ if has ncu_align; then
     ncu -i $O/${tag}_align16.ncu-rep --page raw --csv > $O/${tag}_align16_raw.csv 2>/dev/null
     echo "ncu align exit $?"
 fi
+if has ncu_order; then
+    ICB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:icb_k_dl_order -s 40 -c 3 -f -o $O/${tag}_order \
+        python bench.py --reads 30000 --steps 1 --warmup 3 --quick > $O/${tag}_ncu_order.log 2>&1
+    ncu -i $O/${tag}_order.ncu-rep --page raw --csv > $O/${tag}_order_raw.csv 2>/dev/null
+    echo "ncu order exit $?"
+fi
 if has ncu_query; then
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:icb_k_query -s 60 -c 4 -f -o $O/${tag}_query \
-        python bench.py --reads 20000 --steps 1 --warmup 3 --no-cpu-baseline > $O/${tag}_ncu_query.log 2>&1
+    ICB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:icb_k_query -s 60 -c 4 -f -o $O/${tag}_query \
+        python bench.py --reads 20000 --steps 1 --warmup 3 --quick > $O/${tag}_ncu_query.log 2>&1
     ncu -i $O/${tag}_query.ncu-rep --page raw --csv > $O/${tag}_query_raw.csv 2>/dev/null
     echo "ncu query exit $?"
 fi
