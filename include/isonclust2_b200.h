@@ -59,6 +59,11 @@ int icb_ctx_timing_reset(icb_ctx* ctx);
 int icb_ctx_kernel_time(icb_ctx* ctx, const char* name, int64_t* launches, double* total_ms);
 /* total kernel launches issued by this context since creation (always counted) */
 int64_t icb_ctx_launch_count(icb_ctx* ctx);
+/* Diagnostics: while the log runs, every CTA of the packed alignment kernel (kind 1) and every warp of its traceback (kind 2)
+ * leaves one record of four 32-bit words {kind | SM id << 8, start, end, n | m << 16}, times in units of 1.024 us of the
+ * device's global timer (tools/residency.py rebuilds the occupancy of the SMs over a step from them).  dump stops the log. */
+int icb_debug_residency_start(icb_ctx* ctx, int64_t capacity);
+int icb_debug_residency_dump(icb_ctx* ctx, uint32_t* records, int64_t capacity, int64_t* n_records);
 
 /* ------------------------------------------------------------------ host-side helpers (no device work)
  * The three expressions of the path the reference evaluates with the HOST libm / libstdc++; they stay on the

@@ -20,12 +20,38 @@
 //   Reads longer than 2048 rows take several passes; the bottom row of a pass goes through a global line.
 //   Trace: 4 bits per cell, one 32-byte tile per (8 rows x 8 steps) written as two 16-byte stores, addressed in
 //   the kernel's own skewed coordinates (u = j + 2*(rowblock mod 32) + half), which the traceback undoes.
-// icb_k_align16_trace — one warp per pair walks the tiles back from the end cell (a 4x4-tile window is held across
-//   the lanes) and feeds the k-bit window register.
-// Roofline class: integer ALU (GCUPS); trace traffic 0.5 B/cell written once, ~64 B per traceback step read.
+// icb_k_align16_trace — one warp per pair walks back from the end cell a RUN at a time (the lanes look ahead along the
+//   diagonal / the gap, one ballot ends the run) and feeds the k-bit window register 32 columns at a time.
+// Roofline class: integer ALU (GCUPS); trace traffic 0.5 B/cell written once, one 32-byte sector per 8 lanes and run read.
 #include <algorithm>
+#include <cstdlib>
 
 #include "align.cuh"
+
+// Diagnostics (icb_debug_residency_start / _dump): when enabled, every alignment CTA (DP) / warp (traceback) leaves one
+// record {kind | smid << 8, start, end, n | m << 16} with the times in units of 1.024 us of the global timer, from which
+// tools/residency.py rebuilds how many alignment CTAs each SM held over a step.
+struct IcbResidencyLog {
+    uint4* rec;
+    unsigned int* count;
+    unsigned int cap;
+};
+__device__ IcbResidencyLog g_icb_residency = {nullptr, nullptr, 0u};
+__device__ __forceinline__ unsigned int icb_res_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return static_cast<unsigned int>(t >> 10);
+}
+__device__ __forceinline__ void icb_res_record(int kind, unsigned int t0, int n, int m)
+{
+    const IcbResidencyLog L = g_icb_residency;
+    if (!L.rec) return;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    const unsigned int at = atomicAdd(L.count, 1u);
+    if (at < L.cap) L.rec[at] = make_uint4(unsigned(kind) | (smid << 8), t0, icb_res_now(), unsigned(n) | (unsigned(m) << 16));
+}
 
 namespace {
 
@@ -76,9 +102,10 @@ struct Pass16 {
 };
 
 // EDGE: some thread of the warp is outside its column range or at a boundary column in this block.
-// SPECIAL: the warp is the first of the CTA (its thread 0 takes the row above from the matrix edge / the previous pass)
-// or the last of a pass that is followed by another (its thread 31 writes the line).
-template <int Q, bool EDGE>
+// PLAIN: the warp is not the first of the CTA (its thread 0 takes the row above from the ring, never from the matrix edge /
+// the previous pass), holds no thread with the last query row and does not write the line of a following pass: the
+// per-step tests of those three cases drop out of its inner loop.
+template <int Q, bool EDGE, bool PLAIN>
 __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl, const uint32_t* __restrict__ Wp, const uint2* __restrict__ rd,
 				       uint2* __restrict__ wr)
 {
@@ -91,7 +118,7 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl, const
     uint32_t y = __shfl_up_sync(FULL, S.fb, 1);
     {
 	uint32_t x0, y0;
-	if (P.top == 0) {  // from the warp above
+	if (PLAIN || P.top == 0) {  // from the warp above
 	    const uint2 v = rd[Q];
 	    x0 = v.x;
 	    y0 = v.y;
@@ -176,7 +203,7 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl, const
 		}
 	    }
 	}
-	if (P.owner) {
+	if (!PLAIN && P.owner) {
 	    const int r = P.owner_rr & 3;
 	    const uint32_t hv = r == 0 ? S.H[0] : r == 1 ? S.H[1] : r == 2 ? S.H[2] : S.H[3];
 	    const bool hi = P.owner_rr >= 4;
@@ -187,7 +214,7 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl, const
 		S.rbj = col;
 	    }
 	}
-	if (P.write_line) {  // last thread of a pass that is not the last: its bottom row feeds the next pass
+	if (!PLAIN && P.write_line) {  // last thread of a pass that is not the last: its bottom row feeds the next pass
 	    const int jh = jl - 1;
 	    if (jh >= 0 && jh < P.m) __stcg(P.line + jh, (S.hb >> 16) | (S.fb & 0xffff0000u));
 	}
@@ -200,7 +227,7 @@ __device__ __forceinline__ void step16(Lane16& S, const Pass16& P, int sl, const
 }
 
 // four steps (sl0 is a multiple of 4) and the 16-byte half tile they fill
-template <bool EDGE>
+template <bool EDGE, bool PLAIN>
 __device__ __forceinline__ void quad16(Lane16& S, const Pass16& P, int sl0, uint4* __restrict__ half_tile, bool store)
 {
     const int sg0 = sl0 + A16_LAG * P.warp;  // global step of the quad start
@@ -211,18 +238,19 @@ __device__ __forceinline__ void quad16(Lane16& S, const Pass16& P, int sl0, uint
 #pragma unroll
 	for (int r = 0; r < 4; r++) S.T[r] = 0;
     }
-    step16<0, EDGE>(S, P, sl0 + 0, Wp, rd, wr);
-    step16<1, EDGE>(S, P, sl0 + 1, Wp, rd, wr);
-    step16<2, EDGE>(S, P, sl0 + 2, Wp, rd, wr);
-    step16<3, EDGE>(S, P, sl0 + 3, Wp, rd, wr);
+    step16<0, EDGE, PLAIN>(S, P, sl0 + 0, Wp, rd, wr);
+    step16<1, EDGE, PLAIN>(S, P, sl0 + 1, Wp, rd, wr);
+    step16<2, EDGE, PLAIN>(S, P, sl0 + 2, Wp, rd, wr);
+    step16<3, EDGE, PLAIN>(S, P, sl0 + 3, Wp, rd, wr);
     if (store) *half_tile = make_uint4(S.T[0], S.T[1], S.T[2], S.T[3]);
 }
 
 __global__ void __launch_bounds__(A16_THREADS, 4)
 icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, uint4* __restrict__ trace,
-		 uint32_t* __restrict__ lines, IcbAlignEnd* __restrict__ ends, const int32_t* __restrict__ n_pairs_dev)
+		 uint32_t* __restrict__ lines, IcbAlignEnd* __restrict__ ends, const int32_t* __restrict__ n_pairs_dev, int allow_plain)
 {
     if (n_pairs_dev && int(blockIdx.x) >= *n_pairs_dev) return;  // device-built pair queue (dloop.cu): the grid is its capacity
+    const unsigned int res_t0 = g_icb_residency.rec ? icb_res_now() : 0u;
     extern __shared__ uint32_t smW[];  // m + 1 words
     __shared__ uint2 s_ring[A16_WARPS * A16_RING];
     __shared__ int s_red[A16_WARPS * 2];
@@ -280,6 +308,9 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	P.write_line = pass + 1 < npass && tid == A16_THREADS - 1;
 	P.owner = (last / A16_PASS_ROWS == pass) && (((last % A16_PASS_ROWS) >> 3) == tid);
 	P.owner_rr = last & 7;
+	// (warp-uniform) none of the special cases of step16 can occur in this warp during this pass
+	const bool plain = allow_plain && warp > 0 && !((last / A16_PASS_ROWS == pass) && (((last % A16_PASS_ROWS) >> 8) == warp)) &&
+			   !(pass + 1 < npass && warp == A16_WARPS - 1);
 	// per-thread constants: the score selectors of its 8 rows
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
@@ -307,11 +338,15 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 		uint4* dst = tr + (int64_t(rowblock) * d.ncg + (sl0 >> 3)) * 2;
 		if (edge) {
 #pragma unroll 1
-		    for (int hq = 0; hq < 2; hq++) quad16<true>(S, P, sl0 + 4 * hq, dst + hq, store);
+		    for (int hq = 0; hq < 2; hq++) quad16<true, false>(S, P, sl0 + 4 * hq, dst + hq, store);
+		}
+		else if (plain) {
+#pragma unroll 1
+		    for (int hq = 0; hq < 2; hq++) quad16<false, true>(S, P, sl0 + 4 * hq, dst + hq, store);
 		}
 		else {
 #pragma unroll 1
-		    for (int hq = 0; hq < 2; hq++) quad16<false>(S, P, sl0 + 4 * hq, dst + hq, store);
+		    for (int hq = 0; hq < 2; hq++) quad16<false, false>(S, P, sl0 + 4 * hq, dst + hq, store);
 		}
 	    }
 	    // a slot written in tile b is read in tile b + A16_DELAY / 8: one barrier per A16_DELAY / 8 tiles keeps them apart
@@ -362,13 +397,389 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	    }
 	    e.status = 0;
 	    ends[blockIdx.x] = e;
+	    icb_res_record(1, res_t0, n, m);
 	}
     }
 }
 
+// ------------------------------------------------------------------------------------------------ one warp per pair
+// icb_k_align16w_dp — the same recurrence, lane layout (8 rows per lane as two packed halves, lane l two columns behind
+// lane l - 1) and trace tiles as icb_k_align16_dp, but ONE WARP walks the whole matrix in strips of 256 rows: no CTA
+// barrier, no ring between warps, no stagger between them (the ramp is 64 steps per strip instead of 80 per warp of the
+// CTA), and every warp of an SM works on its own pair, so the four schedulers carry the same load whatever the read
+// length.  What the CTA kernel takes from shared memory comes through registers here: the one-hot score word of a
+// column travels down the lanes with the column (one more shuffle per step), lane 0 takes it — and the bottom row of the
+// strip above — from a 32-step feed the warp refills with coalesced loads one group ahead, and lane 31 leaves the strip's
+// bottom row in a 32-step buffer flushed with one coalesced store.
+constexpr int AW_GROUP = 32;  // steps per feed / flush group
+
+struct PassW {
+    int m, n, lane;
+    int row0;		 // first query row of this lane in this strip
+    uint32_t NEGO, C2O;	 // packed -open, packed 2-open
+    bool owner;		 // this lane holds the last query row (last strip only)
+    int owner_rr;
+};
+
+// LAST: the strip that holds the last query row (tracks the row maximum, leaves no bottom row behind)
+template <int Q, bool EDGE, bool LAST>
+__device__ __forceinline__ void stepw(Lane16& S, uint32_t& Whl, const PassW& P, int sl, const uint2 v, uint32_t* __restrict__ outb)
+{
+    // v = this step's feed entry, outb = this quad's four entries (offsets below are compile-time)
+    const int lane = P.lane;
+    const int jl = sl - 2 * lane;
+    uint32_t x = __shfl_up_sync(FULL, S.hb, 1);
+    uint32_t y = __shfl_up_sync(FULL, S.fb, 1);
+    uint32_t wl = __shfl_up_sync(FULL, Whl, 1);  // the score word of the column the lane above has just finished in its high half
+    if (lane == 0) {  // row above the strip (matrix edge: H = 0, F = -inf; or the bottom row of the strip before) and W[sl]
+	x = v.x << 16;
+	y = v.x & 0xffff0000u;
+	wl = v.y;
+    }
+    uint32_t hup = prmt(x, S.hb, 0x5432);  // low half <- the rows above (previous lane's high half), high half <- own low half
+    uint32_t fup = prmt(y, S.fb, 0x5432);
+    uint32_t hd = S.hup_prev;
+    S.hup_prev = hup;
+    const bool active = EDGE ? (jl >= 0 && jl <= P.m) : true;
+    if (active) {
+	const uint32_t Wlo = wl;
+	const uint32_t Whi = S.Wprev;
+	S.Wprev = Wlo;
+	Whl = Whi;
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+	    const uint32_t sc = prmt(Wlo, Whi, S.SEL[r]);
+	    const uint32_t D = hd + sc;
+	    const uint32_t fx = fup - ONE2;
+	    const uint32_t F = __viaddmax_s16x2(hup, P.NEGO, fx);
+	    const uint32_t ex = S.E[r] + ONE2;
+	    const uint32_t En = __viaddmax_s16x2(S.H[r], P.C2O, ex);
+	    const uint32_t Hn = __vimax3_s16x2(D, En, F);
+	    // trace nibble: 8 = H != diagonal, 4 = H != F, 2 = E opened here, 1 = F opened here
+	    const uint32_t bu = __vmins2(Hn - D, ONE2);
+	    const uint32_t bv = __vmins2(Hn - F, ONE2);
+	    const uint32_t bx = __vmins2(En - ex, ONE2);
+	    const uint32_t by = __vmins2(F - fx, ONE2);
+	    const uint32_t nib = ((bu * 2u + bv) * 2u + bx) * 2u + by;
+	    S.T[r] = (Q == 0 && !EDGE) ? nib : S.T[r] * 16u + nib;  // 4 steps x 4 bits per half, first step in the top nibble
+	    hd = S.H[r];
+	    S.H[r] = Hn;
+	    S.E[r] = En;
+	    hup = Hn;
+	    fup = F;
+	}
+	S.hb = hup;
+	S.fb = fup;
+	if (EDGE) {
+	    if (jl == 0) {
+		// the high half just "computed" column -1: put the left boundary back (H[i][-1] = 0, E = -inf)
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+		    S.H[r] = (S.H[r] & 0xffffu) | (uint32_t(A16_BIAS - 2) << 16);
+		    S.E[r] = (S.E[r] & 0xffffu) | 0x00010000u;
+		}
+		S.hb = S.H[3];
+	    }
+	    if (jl == P.m - 1) {
+		const int unb = 2 * (P.m - 1) + A16_BIAS;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+		    const int v = int(S.H[r] & 0xffffu) - unb;
+		    if (P.row0 + r < P.n && v > S.cbest) {
+			S.cbest = v;
+			S.ci = P.row0 + r;
+		    }
+		}
+	    }
+	    if (jl == P.m) {
+		const int unb = 2 * (P.m - 1) + A16_BIAS;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+		    const int v = int(S.H[r] >> 16) - unb;
+		    if (P.row0 + 4 + r < P.n && v > S.cbest) {
+			S.cbest = v;
+			S.ci = P.row0 + 4 + r;
+		    }
+		}
+	    }
+	}
+	if (LAST && P.owner) {
+	    const int r = P.owner_rr & 3;
+	    const uint32_t hv = r == 0 ? S.H[0] : r == 1 ? S.H[1] : r == 2 ? S.H[2] : S.H[3];
+	    const bool hi = P.owner_rr >= 4;
+	    const int col = hi ? jl - 1 : jl;
+	    const int v = int(hi ? (hv >> 16) : (hv & 0xffffu)) - 2 * col - A16_BIAS;
+	    if (col >= 0 && col < P.m && v > S.rbest) {
+		S.rbest = v;
+		S.rbj = col;
+	    }
+	}
+    }
+    else if (EDGE) {
+	// keep the nibble positions of the half tile aligned with the step index
+#pragma unroll
+	for (int r = 0; r < 4; r++) S.T[r] *= 16u;
+    }
+    // the strip's bottom row at column jl - 1 (the flush drops what lies outside the matrix)
+    if (!LAST && lane == 31) outb[Q] = (S.hb >> 16) | (S.fb & 0xffff0000u);
+}
+
+template <bool EDGE, bool LAST>
+__device__ __forceinline__ void quadw(Lane16& S, uint32_t& Whl, const PassW& P, int sl0, const uint2* __restrict__ feed, uint32_t* __restrict__ outb,
+				      uint4* __restrict__ half_tile, bool store)
+{
+    if (EDGE) {
+#pragma unroll
+	for (int r = 0; r < 4; r++) S.T[r] = 0;
+    }
+    // the four feed entries are taken up front (every lane reads the same words): lane 0's row above is on the critical
+    // path of each step, its load must not be
+    const uint2 v0 = feed[0], v1 = feed[1], v2 = feed[2], v3 = feed[3];
+    stepw<0, EDGE, LAST>(S, Whl, P, sl0 + 0, v0, outb);
+    stepw<1, EDGE, LAST>(S, Whl, P, sl0 + 1, v1, outb);
+    stepw<2, EDGE, LAST>(S, Whl, P, sl0 + 2, v2, outb);
+    stepw<3, EDGE, LAST>(S, Whl, P, sl0 + 3, v3, outb);
+    if (store) *half_tile = make_uint4(S.T[0], S.T[1], S.T[2], S.T[3]);
+}
+
+// s_prog[w] = strip * 65536 + columns of that strip's bottom row warp w has put in the line (monotone): strip s + 1, in the
+// next warp, reads a column of the line only after strip s wrote it.
+template <bool LAST>
+__device__ __forceinline__ void stripw(Lane16& S, PassW& P, const uint8_t* __restrict__ seq, const IcbPairDesc& d, int pass, uint4* __restrict__ tr,
+				       uint32_t* __restrict__ line, uint2* __restrict__ s_feed, uint32_t* __restrict__ s_out,
+				       volatile int* __restrict__ s_prog, int warp, int nwarps)
+{
+    const int lane = P.lane, n = P.n, m = P.m;
+    const int nloc = (m + 64 + 7) & ~7;	 // lane 31 finishes column m at step m + 62
+    P.row0 = pass * (32 * 8) + lane * 8;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+	const int ilo = P.row0 + r, ihi = P.row0 + 4 + r;
+	const int alo = ilo < n ? (code5(seq[d.q_off + ilo]) & 3) : 0;
+	const int ahi = ihi < n ? (code5(seq[d.q_off + ihi]) & 3) : 0;
+	S.SEL[r] = uint32_t(alo) | 0x80u | (uint32_t(4 + ahi) << 8) | 0x8000u;
+	S.H[r] = pack2(A16_BIAS - 2, A16_BIAS - 2);  // H[i][-1] = 0 at column -1
+	S.E[r] = ONE2;				     // E[i][-1] = -inf
+	S.T[r] = 0;
+    }
+    S.hb = pack2(A16_BIAS - 2, A16_BIAS - 2);
+    S.fb = ONE2;
+    S.hup_prev = pack2(A16_BIAS - 2, A16_BIAS - 2);
+    S.Wprev = 0;
+    uint32_t Whl = 0;
+    const int rowblock = pass * 32 + lane;
+    const bool rows_valid = P.row0 < n;
+    __syncwarp();  // this warp's strip before is done with the feed
+    const int above = (warp + nwarps - 1) % nwarps;  // the warp that computes strip pass - 1
+    // what lane 0 needs at step c: the row above at column c and the score word of column c; `upto` columns of the
+    // strip above must be in the line
+    auto load_feed = [&](int c, int upto) {
+	uint2 v;
+	if (pass > 0) {
+	    const int need = (pass - 1) * 65536 + min(m, upto);
+	    while (s_prog[above] < need) __nanosleep(64);
+	}
+	v.x = (pass > 0 && c < m) ? __ldcg(line + c) : (uint32_t(2 * c + A16_BIAS) | 0x00010000u);
+	v.y = c < m ? (4u << (8 * (code5(icb_ref_char(seq, d, c)) & 3))) : 0u;
+	return v;
+    };
+    uint2 pre = load_feed(lane, AW_GROUP);
+    const int nblk = nloc >> 3;
+    for (int blk = 0; blk < nblk; blk++) {
+	const int sl0 = blk * 8;
+	if ((blk & 3) == 0) {  // a new group of 32 steps: publish its feed, fetch the next one
+	    const int g = blk >> 2;
+	    s_feed[(g & 1) * AW_GROUP + lane] = pre;
+	    __syncwarp();
+	    pre = load_feed((g + 1) * AW_GROUP + lane, (g + 2) * AW_GROUP);
+	}
+	const uint2* feed = s_feed + ((blk >> 2) & 1) * AW_GROUP + (sl0 & (AW_GROUP - 1));
+	uint32_t* outb = s_out + (sl0 & (AW_GROUP - 1));
+	const bool edge = sl0 < 63 || sl0 + 7 > m - 2;
+	const bool store = rows_valid && sl0 + 7 >= 2 * lane && sl0 <= 2 * lane + m;
+	uint4* dst = tr + (int64_t(rowblock) * d.ncg + blk) * 2;
+	if (edge) {
+#pragma unroll 1
+	    for (int hq = 0; hq < 2; hq++) quadw<true, LAST>(S, Whl, P, sl0 + 4 * hq, feed + 4 * hq, outb + 4 * hq, dst + hq, store);
+	}
+	else {
+#pragma unroll 1
+	    for (int hq = 0; hq < 2; hq++) quadw<false, LAST>(S, Whl, P, sl0 + 4 * hq, feed + 4 * hq, outb + 4 * hq, dst + hq, store);
+	}
+	if (!LAST && ((blk & 3) == 3 || blk + 1 == nblk)) {
+	    // entry e of the buffer belongs to step (sl0 & ~31) + e, i.e. to column that step - 63
+	    __syncwarp();
+	    const int base = sl0 & ~(AW_GROUP - 1);
+	    const int c = base + lane - 63;
+	    if (c >= 0 && c < m && base + lane <= sl0 + 7) __stcg(line + c, s_out[lane]);
+	    if (nwarps > 1) __threadfence();  // the line is read by another warp, through L2
+	    __syncwarp();
+	    if (lane == 0) s_prog[warp] = pass * 65536 + (blk + 1 == nblk ? m : max(0, min(m, sl0 + 8 - 63)));
+	}
+    }
+}
+
+constexpr int AW_MAXW = 8;  // warps per pair, at most
+
+// blockDim.x / 32 warps per pair: warp w computes strips w, w + W, w + 2W, ... each as soon as the strip above has its
+// first columns in the line (a pipeline of warps through L2, ~160 steps apart, without any CTA barrier).  W = 1 gives the
+// most pairs per second, a larger W the shorter time per pair the device loop's rounds wait for.
+__global__ void __launch_bounds__(32 * AW_MAXW, 3)
+icb_k_align16w_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, uint4* __restrict__ trace,
+		  uint32_t* __restrict__ lines, IcbAlignEnd* __restrict__ ends, const int32_t* __restrict__ n_pairs_dev)
+{
+    if (n_pairs_dev && int(blockIdx.x) >= *n_pairs_dev) return;  // device-built pair queue (dloop.cu): the grid is its capacity
+    const unsigned int res_t0 = g_icb_residency.rec ? icb_res_now() : 0u;
+    __shared__ uint2 s_feed[AW_MAXW][2 * AW_GROUP];
+    __shared__ uint32_t s_out[AW_MAXW][AW_GROUP];
+    __shared__ int s_prog[AW_MAXW];
+    __shared__ int s_red[AW_MAXW * 2];
+    __shared__ int s_row[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const IcbPairDesc d = descs[blockIdx.x];
+    const int n = d.n, m = d.m;
+    // refuse anything outside ACGT (parasail scores it 0): the 32-bit kernel takes the pair
+    int bad = 0;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) bad |= code5(seq[d.r_off + j]) > 3;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) bad |= code5(seq[d.q_off + i]) > 3;
+    if (lane == 0) s_prog[warp] = 0;
+    if (__syncthreads_or(bad)) {
+	if (threadIdx.x == 0) {
+	    IcbAlignEnd e;
+	    e.score = 0;
+	    e.ei = e.ej = 0;
+	    e.status = 1;
+	    ends[blockIdx.x] = e;
+	}
+	return;
+    }
+    Lane16 S;
+    S.rbest = -(1 << 30);
+    S.rbj = m - 1;
+    S.cbest = -(1 << 30);
+    S.ci = n - 1;
+    PassW P;
+    P.m = m;
+    P.n = n;
+    P.lane = lane;
+    P.NEGO = pack2(-d.open, -d.open);
+    P.C2O = pack2(2 - d.open, 2 - d.open);
+    const int last = n - 1;
+    P.owner = ((last & 255) >> 3) == lane;
+    P.owner_rr = last & 7;
+    const int npass = (n + 255) >> 8;
+    uint4* tr = trace + d.trace_off * 2;
+    uint32_t* line = lines + d.line_off;
+    for (int pass = warp; pass < npass; pass += nwarps) {
+	if (pass + 1 < npass) stripw<false>(S, P, seq, d, pass, tr, line, s_feed[warp], s_out[warp], s_prog, warp, nwarps);
+	else stripw<true>(S, P, seq, d, pass, tr, line, s_feed[warp], s_out[warp], s_prog, warp, nwarps);
+    }
+    // ---- end cell (sg_trace_scan_avx2_256_16.c:355-395): first maximum of the last row, then the last column:
+    // strictly larger wins, the smallest row among equals; a tie with the row maximum only moves the end if
+    // that maximum sits in the corner.
+    const int ol = (last & 255) >> 3;
+    if (warp == (npass - 1) % nwarps && lane == ol) {
+	s_row[0] = S.rbest;
+	s_row[1] = S.rbj;
+    }
+    int cb = S.cbest, ci = S.ci;
+#pragma unroll
+    for (int dlt = 16; dlt; dlt >>= 1) {
+	const int ov = __shfl_xor_sync(FULL, cb, dlt), oi = __shfl_xor_sync(FULL, ci, dlt);
+	if (ov > cb || (ov == cb && oi < ci)) {
+	    cb = ov;
+	    ci = oi;
+	}
+    }
+    if (lane == 0) {
+	s_red[2 * warp] = cb;
+	s_red[2 * warp + 1] = ci;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+	for (int w = 1; w < nwarps; w++) {
+	    const int ov = s_red[2 * w], oi = s_red[2 * w + 1];
+	    if (ov > cb || (ov == cb && oi < ci)) {
+		cb = ov;
+		ci = oi;
+	    }
+	}
+	const int best = s_row[0], bj = s_row[1];
+	IcbAlignEnd e;
+	e.score = best;
+	e.ei = n - 1;
+	e.ej = bj;
+	if (cb > best || (cb == best && bj == m - 1)) {
+	    e.score = cb;
+	    e.ei = ci;
+	    e.ej = m - 1;
+	}
+	e.status = 0;
+	ends[blockIdx.x] = e;
+	icb_res_record(1, res_t0, n, m);
+    }
+}
+
+// getAlnRatio's window count (cluster.cpp:442-459), fed up to 32 comparison-string columns at a time: the same sequence of
+// states as IcbWindowCounter::push column by column (align.cuh), every lane holding the same state and lane p evaluating
+// the window that closes at the p-th new column.
+struct WarpWindowCounter {
+    uint32_t reg, mask;
+    int k, limit;
+    long long pushed;
+    int aligned;
+    __device__ __forceinline__ void init(int kk, int lim)
+    {
+	reg = 0;
+	mask = kk >= 32 ? 0xffffffffu : ((1u << kk) - 1u);
+	k = kk;
+	limit = lim;
+	pushed = 0;
+	aligned = 0;
+    }
+    // bits: bit t = the t-th new column is a match; cnt <= 32 columns (warp-uniform arguments)
+    __device__ __forceinline__ void push_bits(uint32_t bits, int cnt, int lane)
+    {
+	if (cnt <= 0) return;
+	const uint32_t upto = bits & ((2u << lane) - 1u);				   // columns 0..lane
+	const uint32_t fresh = __brev(upto) >> (31 - lane);				   // column 0 in bit `lane`, column `lane` in bit 0
+	const uint32_t w = ((lane == 31 ? 0u : (reg << (lane + 1))) | fresh) & mask;	   // the register after column `lane`
+	const bool counts = lane < cnt && pushed + lane >= k && __popc(w) >= limit;
+	aligned += __popc(__ballot_sync(FULL, counts));
+	reg = __shfl_sync(FULL, w, cnt - 1);
+	pushed += cnt;
+    }
+    __device__ void push_zeros(long long g, int lane)
+    {
+	const int first = int(g < k ? g : k);
+	push_bits(0u, first, lane);
+	const long long rest = g - first;
+	if (rest > 0) {
+	    // the register is all zero now; every further column closes an all-blank window
+	    long long counted = rest;
+	    if (pushed < k) counted -= (k - pushed);
+	    if (counted > 0 && 0 >= limit) aligned += int(counted);
+	    pushed += rest;
+	}
+    }
+};
+
+// the 4 trace bits of cell (i, j): icb_k_align16_dp's tile layout (row block i / 8, skewed step u = j + 2 * (rowblock mod 32) + half)
+__device__ __forceinline__ uint32_t trace_nibble(const uint32_t* __restrict__ tr, int ncg, int i, int j)
+{
+    const int gg = i >> 3, half = (i >> 2) & 1, r = i & 3;
+    const int u = j + 2 * (gg & 31) + half;
+    const uint32_t word = __ldcg(tr + ((int64_t(gg) * ncg + (u >> 3)) * 2 + ((u >> 2) & 1)) * 4 + r);
+    return (word >> (16 * half + 4 * (3 - (u & 3)))) & 15u;
+}
+
 // ------------------------------------------------------------------------------------------------ traceback
 // Mirrors parasail_result_get_traceback (traceback_template.c:72-175) and feeds getAlnRatio's window count
-// (cluster.cpp:442-459).  One warp per pair, lane-uniform control flow.
+// (cluster.cpp:442-459).  One warp per pair; the walk itself is serial, so the warp looks AHEAD instead: in the diagonal
+// state lane t reads the trace bits (and the two characters) of cell (i - t, j - t), in a gap state those of the t-th
+// cell along the gap; one ballot finds where the run ends, the whole run goes into the window count at once, and the
+// cell that ended a diagonal run also yields the first step of the gap it opens.  One round of loads per run (a dozen
+// columns on ONT reads) instead of one dependent shuffle chain per column.
 constexpr int TB_WARPS = 4;
 
 __global__ void __launch_bounds__(TB_WARPS * 32)
@@ -396,85 +807,65 @@ icb_k_align16_trace(const uint8_t* __restrict__ seq, const IcbPairDesc* __restri
 	return;
     }
     const int n = d.n, m = d.m, ncg = d.ncg;
-    const uint4* tr = trace + d.trace_off * 2;
-    IcbWindowCounter st;
+    const unsigned int res_t0 = g_icb_residency.rec ? icb_res_now() : 0u;
+    const uint32_t* tr = reinterpret_cast<const uint32_t*>(trace + d.trace_off * 2);
+    WarpWindowCounter st;
     st.init(k, d.limit);
     int i = en.ei, j = en.ej;
     // free tail (traceback_template.c:72-94)
-    if (i + 1 == n) st.push_zeros(m - 1 - j);
-    else st.push_zeros(n - 1 - i);
+    if (i + 1 == n) st.push_zeros(m - 1 - j, lane);
+    else st.push_zeros(n - 1 - i, lane);
     int where = 0;  // 0 diag, 1 ins (consumes reference), 2 del (consumes query)
-    // window: row blocks g0..g0+3, for row block g0+a the tiles ub[a]..ub[a]+3; lane = (a*4 + b)*2 + half-tile
-    int g0 = 1 << 28;
-    int ub0 = 0, ub1 = 0, ub2 = 0, ub3 = 0;
-    uint4 wt = make_uint4(0, 0, 0, 0);
-    uint32_t qc = 0, rc = 0;
-    int qbase = 0, cbase = 1 << 28;
-    const int la = lane >> 3, lb = (lane >> 1) & 3, lh = lane & 1;
-    bool pend = false;
-    uint32_t pa = 0, pb = 0;
-    while (i >= 0 || j >= 0) {
-	if (pend) {
-	    st.push(pa == pb ? 1u : 0u);  // traceback.c match_char, case-insensitive
-	    pend = false;
-	}
-	if (i < 0) {
-	    st.push_zeros(j + 1);
-	    break;
-	}
-	if (j < 0) {
-	    st.push_zeros(i + 1);
-	    break;
-	}
-	const int gg = i >> 3, rr = i & 7, half = rr >> 2, r = rr & 3;
-	const int u = j + 2 * (gg & 31) + half, ug = u >> 3, q = u & 7;
-	int a = gg - g0;
-	int ub = a == 0 ? ub0 : a == 1 ? ub1 : a == 2 ? ub2 : ub3;
-	if (a < 0 || a > 3 || ug < ub || ug > ub + 3 || j < cbase) {
-	    // new window with the current cell in its bottom-right corner
-	    g0 = gg - 3;
-	    ub0 = ((j + 2 * ((g0 + 0) & 31) + 1) >> 3) - 3;
-	    ub1 = ((j + 2 * ((g0 + 1) & 31) + 1) >> 3) - 3;
-	    ub2 = ((j + 2 * ((g0 + 2) & 31) + 1) >> 3) - 3;
-	    ub3 = ((j + 2 * ((g0 + 3) & 31) + 1) >> 3) - 3;
-	    const int myg = g0 + la;
-	    const int myu = (la == 0 ? ub0 : la == 1 ? ub1 : la == 2 ? ub2 : ub3) + lb;
-	    if (myg >= 0 && myu >= 0 && myu < ncg) wt = __ldcg(tr + (int64_t(myg) * ncg + myu) * 2 + lh);
-	    qbase = g0 * 8;
-	    cbase = j - 31;
-	    const int qi = qbase + lane, rj = cbase + lane;
-	    qc = (qi >= 0 && qi < n) ? icb_up_char(seq[d.q_off + qi]) : 0u;
-	    rc = (rj >= 0 && rj < m) ? icb_up_char(icb_ref_char(seq, d, rj)) : 1u;
-	    a = 3;
-	    ub = ub3;
-	}
-	const uint32_t comp = r == 0 ? wt.x : r == 1 ? wt.y : r == 2 ? wt.z : wt.w;
-	const uint32_t word = __shfl_sync(FULL, comp, ((a << 2) + (ug - ub)) * 2 + (q >> 2));
-	const uint32_t nib = (word >> (16 * half + 4 * (3 - (q & 3)))) & 15u;
+    while (i >= 0 && j >= 0) {
 	// nib bits: 8 = H != diagonal, 4 = H != F, 2 = E opened here (DIAG_E), 1 = F opened here (DIAG_F)
 	if (where == 0) {
-	    if (!(nib & 8u)) {
-		pa = __shfl_sync(FULL, qc, i - qbase);
-		pb = __shfl_sync(FULL, rc, j - cbase);
-		pend = true;
-		i--;
-		j--;
+	    const int ii = i - lane, jj = j - lane;
+	    const bool valid = ii >= 0 && jj >= 0;
+	    uint32_t nib = 8u, qc = 0u, rc = 1u;
+	    if (valid) {
+		nib = trace_nibble(tr, ncg, ii, jj);
+		qc = icb_up_char(seq[d.q_off + ii]);
+		rc = icb_up_char(icb_ref_char(seq, d, jj));
 	    }
-	    else if (nib & 4u) where = 1;  // neither diagonal nor F: INS (traceback_template.c:118-120)
-	    else where = 2;
-	}
-	else if (where == 1) {
-	    st.push(0);
-	    j--;
-	    where = (nib & 2u) ? 0 : 1;
+	    const uint32_t stops = __ballot_sync(FULL, (nib & 8u) != 0u);
+	    const uint32_t same = __ballot_sync(FULL, qc == rc);  // traceback.c match_char, case-insensitive
+	    const int run = stops ? __ffs(stops) - 1 : 32;
+	    st.push_bits(run == 32 ? same : (same & ((1u << run) - 1u)), run, lane);
+	    i -= run;
+	    j -= run;
+	    if (run < 32 && i >= 0 && j >= 0) {
+		// neither diagonal nor F: INS (traceback_template.c:118-120); the gap's first column is this very cell
+		const uint32_t sn = __shfl_sync(FULL, nib, run);
+		st.push_bits(0u, 1, lane);
+		if (sn & 4u) {
+		    j--;
+		    where = (sn & 2u) ? 0 : 1;
+		}
+		else {
+		    i--;
+		    where = (sn & 1u) ? 0 : 2;
+		}
+	    }
 	}
 	else {
-	    st.push(0);
-	    i--;
-	    where = (nib & 1u) ? 0 : 2;
+	    const int ii = where == 1 ? i : i - lane, jj = where == 1 ? j - lane : j;
+	    const bool valid = ii >= 0 && jj >= 0;
+	    const uint32_t closes = where == 1 ? 2u : 1u;
+	    const uint32_t nib = valid ? trace_nibble(tr, ncg, ii, jj) : closes;
+	    const uint32_t stops = __ballot_sync(FULL, (nib & closes) != 0u);
+	    const int first = stops ? __ffs(stops) - 1 : 32;
+	    const int left = where == 1 ? j + 1 : i + 1;  // cells before the matrix edge
+	    // the closing cell is itself a gap column; an edge ends the gap without one
+	    const int cols = first == 32 ? 32 : (first < left ? first + 1 : first);
+	    st.push_bits(0u, cols, lane);
+	    if (where == 1) j -= cols;
+	    else i -= cols;
+	    if (first < 32) where = 0;
 	}
     }
-    if (pend) st.push(pa == pb ? 1u : 0u);
+    if (i < 0 && j >= 0) st.push_zeros(j + 1, lane);
+    else if (j < 0 && i >= 0) st.push_zeros(i + 1, lane);
+    if (lane == 0) icb_res_record(2, res_t0, n, m);
     if (aln_out) {
 	if (lane == 0) aln_out[d.out] = st.pushed >= k ? st.aligned : 0;
 	return;
@@ -492,6 +883,25 @@ icb_k_align16_trace(const uint8_t* __restrict__ seq, const IcbPairDesc* __restri
 
 }  // namespace
 
+static int a16_allow_plain()
+{
+    static const int v = getenv("ICB_A16_NOPLAIN") ? 0 : 1;
+    return v;
+}
+// ICB_A16_CTA=1: the CTA-per-pair wavefront kernel instead of the warp-per-pair one (same results, same trace tiles)
+static bool a16_use_cta()
+{
+    static const bool v = getenv("ICB_A16_CTA") != nullptr;
+    return v;
+}
+// warps per pair of the warp-pipeline kernel (ICB_A16_WARPS; latency-first contexts: ICB_A16_WARPS_LATENCY)
+static int a16_warps(bool latency)
+{
+    static const int w = getenv("ICB_A16_WARPS") ? std::max(1, std::min(AW_MAXW, atoi(getenv("ICB_A16_WARPS")))) : 2;
+    static const int wl = getenv("ICB_A16_WARPS_LATENCY") ? std::max(1, std::min(AW_MAXW, atoi(getenv("ICB_A16_WARPS_LATENCY")))) : 8;
+    return latency ? wl : w;
+}
+
 int icb_align16_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, const IcbPairDesc* descs, int64_t cnt,
 		    int64_t tiles, int64_t line_words, int max_m, int k)
 {
@@ -501,9 +911,14 @@ int icb_align16_run(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, c
     if (rc) return rc;
     ICB_CUDA(ctx, cudaMemcpyAsync(ws.d_descs, descs, sizeof(IcbPairDesc) * cnt, cudaMemcpyHostToDevice, st));
     const size_t smem = size_t(max_m + 1) * 4;
-    ICB_LAUNCH(ctx, "align_dp",
-	       icb_k_align16_dp<<<unsigned(cnt), A16_THREADS, smem, st>>>(d_seq, ws.d_descs, reinterpret_cast<uint4*>(ws.d_trace),
-									   reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends, nullptr));
+    if (a16_use_cta())
+	ICB_LAUNCH(ctx, "align_dp",
+		   icb_k_align16_dp<<<unsigned(cnt), A16_THREADS, smem, st>>>(d_seq, ws.d_descs, reinterpret_cast<uint4*>(ws.d_trace),
+									       reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends, nullptr, a16_allow_plain()));
+    else
+	ICB_LAUNCH(ctx, "align_dp",
+		   icb_k_align16w_dp<<<unsigned(cnt), 32 * a16_warps(false), 0, st>>>(d_seq, ws.d_descs, reinterpret_cast<uint4*>(ws.d_trace),
+								    reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends, nullptr));
     ICB_LAUNCH(ctx, "align_trace",
 	       icb_k_align16_trace<<<unsigned((cnt + TB_WARPS - 1) / TB_WARPS), TB_WARPS * 32, 0, st>>>(
 		   d_seq, ws.d_descs, int(cnt), reinterpret_cast<const uint4*>(ws.d_trace), ws.d_ends, k, ws.d_out, nullptr, nullptr));
@@ -518,11 +933,63 @@ int icb_align16_run_dev(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_se
     if (max_pairs <= 0) return ICB_OK;
     cudaStream_t st = ctx->stream;
     const size_t smem = size_t(max_m + 1) * 4;
-    ICB_LAUNCH(ctx, "align_dp",
-	       icb_k_align16_dp<<<unsigned(max_pairs), A16_THREADS, smem, st>>>(d_seq, d_descs, reinterpret_cast<uint4*>(ws.d_trace),
-										 reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends, d_count));
+    // the worker's batch rank decides how its alignment kernels queue against those of the other batches in flight
+    if (a16_use_cta())
+	ICB_LAUNCH(ctx, "align_dp",
+		   ICB_CUDA(ctx, icb_launch_prio(icb_k_align16_dp, dim3(unsigned(max_pairs)), dim3(A16_THREADS), smem, st, ctx->aln_priority, d_seq,
+						 d_descs, reinterpret_cast<uint4*>(ws.d_trace), reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends,
+						 d_count, a16_allow_plain())));
+    else
+	ICB_LAUNCH(ctx, "align_dp",
+		   ICB_CUDA(ctx, icb_launch_prio(icb_k_align16w_dp, dim3(unsigned(max_pairs)), dim3(32 * a16_warps(ctx->aln_latency)), 0, st, ctx->aln_priority, d_seq, d_descs,
+						 reinterpret_cast<uint4*>(ws.d_trace), reinterpret_cast<uint32_t*>(ws.d_lines), ws.d_ends, d_count)));
     ICB_LAUNCH(ctx, "align_trace",
-	       icb_k_align16_trace<<<unsigned((max_pairs + TB_WARPS - 1) / TB_WARPS), TB_WARPS * 32, 0, st>>>(
-		   d_seq, d_descs, 0, reinterpret_cast<const uint4*>(ws.d_trace), ws.d_ends, k, nullptr, d_count, aln_out));
+	       ICB_CUDA(ctx, icb_launch_prio(icb_k_align16_trace, dim3(unsigned((max_pairs + TB_WARPS - 1) / TB_WARPS)), dim3(TB_WARPS * 32), 0, st,
+					     ctx->aln_priority, d_seq, d_descs, 0, reinterpret_cast<const uint4*>(ws.d_trace),
+					     static_cast<const IcbAlignEnd*>(ws.d_ends), k, static_cast<icb_align_result*>(nullptr), d_count, aln_out)));
     return ICB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ diagnostics
+extern "C" {
+
+int icb_debug_residency_start(icb_ctx* ctx, int64_t capacity)
+{
+    if (!ctx || capacity <= 0 || capacity > (int64_t(1) << 28)) return ICB_ERR_ARG;
+    IcbResidencyLog L;
+    ICB_CUDA(ctx, cudaMemcpyFromSymbol(&L, g_icb_residency, sizeof L));
+    if (L.rec) {
+	cudaFree(L.rec);
+	cudaFree(L.count);
+    }
+    ICB_CUDA(ctx, cudaMalloc(&L.rec, sizeof(uint4) * size_t(capacity)));
+    ICB_CUDA(ctx, cudaMalloc(&L.count, sizeof(unsigned int)));
+    ICB_CUDA(ctx, cudaMemset(L.count, 0, sizeof(unsigned int)));
+    L.cap = unsigned(capacity);
+    ICB_CUDA(ctx, cudaMemcpyToSymbol(g_icb_residency, &L, sizeof L));
+    ICB_CUDA(ctx, cudaDeviceSynchronize());
+    return ICB_OK;
+}
+
+// copies the records out (at most `capacity` of them; returns how many were written through *n_records), stops and frees the log
+int icb_debug_residency_dump(icb_ctx* ctx, uint32_t* records, int64_t capacity, int64_t* n_records)
+{
+    if (!ctx || !n_records) return ICB_ERR_ARG;
+    ICB_CUDA(ctx, cudaDeviceSynchronize());
+    IcbResidencyLog L;
+    ICB_CUDA(ctx, cudaMemcpyFromSymbol(&L, g_icb_residency, sizeof L));
+    if (!L.rec) return ctx->fail(ICB_ERR_STATE, "the residency log is not running");
+    unsigned int cnt = 0;
+    ICB_CUDA(ctx, cudaMemcpy(&cnt, L.count, sizeof cnt, cudaMemcpyDeviceToHost));
+    const int64_t have = std::min<int64_t>(cnt, L.cap);
+    const int64_t take = std::min<int64_t>(have, capacity);
+    if (records && take > 0) ICB_CUDA(ctx, cudaMemcpy(records, L.rec, sizeof(uint4) * size_t(take), cudaMemcpyDeviceToHost));
+    *n_records = take;
+    cudaFree(L.rec);
+    cudaFree(L.count);
+    L = IcbResidencyLog{nullptr, nullptr, 0u};
+    ICB_CUDA(ctx, cudaMemcpyToSymbol(g_icb_residency, &L, sizeof L));
+    return ICB_OK;
+}
+
+}  // extern "C"

@@ -134,7 +134,7 @@ struct icb_clusterer {
 	IcbDLoopView view;  // every pointer and parameter the kernels of the round take by value
 	const void* p[12];
 	size_t smem_f;
-	int nb_f, smem_cnt_f, iters, mode, max_m, k, spec;
+	int nb_f, smem_cnt_f, iters, mode, max_m, k, spec, aln_priority;
 	bool operator==(const RoundKey& o) const { return memcmp(this, &o, sizeof(RoundKey)) == 0; }
     };
     cudaGraphExec_t round_exec = nullptr;
@@ -1264,6 +1264,7 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
 	key.max_m = max_m;
 	key.k = k;
 	key.spec = V.spec_window * 8 + V.spec_pairs;
+	key.aln_priority = ctx->aln_priority * 2 + (ctx->aln_latency ? 1 : 0);
 	if (!round_exec || !(key == round_key)) {
 	    if (round_exec) cudaGraphExecDestroy(round_exec);
 	    round_exec = nullptr;
@@ -1566,6 +1567,21 @@ struct icb_tree_trace {
     std::vector<Job> jobs;
 };
 
+// launch priority of the alignment kernels of sorted batch b of n (see cluster_batches_impl)
+static int batch_aln_priority(const icb_ctx* c, int b, int n_batches)
+{
+    static const bool on = getenv("ICB_NO_BATCH_PRIORITY") == nullptr;
+    if (!on) return c->lo_priority;
+    return std::min(c->lo_priority, b == 0 ? c->hi_priority + 1 : (b <= n_batches / 8 ? c->hi_priority + 2 : c->lo_priority));
+}
+
+// how many of the first sorted batches take the latency-first alignment kernel (their chains of rounds are the longest)
+static int batch_latency_first()
+{
+    static const int v = getenv("ICB_LATENCY_BATCHES") ? atoi(getenv("ICB_LATENCY_BATCHES")) : 1;
+    return v;
+}
+
 void icb_worker_pool_release(icb_ctx* ctx)
 {
     for (size_t w = 0; w < ctx->pool_ctx.size(); w++) {
@@ -1656,6 +1672,7 @@ static int cluster_batches_impl(icb_readset* rs, const icb_cluster_params* param
 	if (rc) return ctx->fail(rc, c->last_error);
     }
     static const bool batch_log = getenv("ICB_BATCH_LOG") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
     auto work = [&](int w) {
 	icb_ctx* c = ctx->pool_ctx[w];
 	cudaSetDevice(c->device);
@@ -1667,15 +1684,21 @@ static int cluster_batches_impl(icb_readset* rs, const icb_cluster_params* param
 	    Stopwatch bw;
 	    rc = cl->reset();
 	    if (rc) break;
+	    // The batches of a sort hold its reads best first, and the better reads found more clusters per read: the first
+	    // batches need the most rounds (batch 0 of configs[1]: 405, the median batch 220).  With every batch in flight
+	    // at once the step ends when the longest chain does, so its alignment kernels go ahead of the others'.
+	    c->aln_priority = batch_aln_priority(c, b, n_batches);
+	    c->aln_latency = b < batch_latency_first();
 	    rc = icb_cluster_reads(cl, order + bounds[b], bounds[b + 1] - bounds[b], cluster_of + bounds[b], strand_of + bounds[b]);
 	    if (rc) break;
 	    const double bms = bw.lap();
 	    wstats[w].ms_batch_max = std::max(wstats[w].ms_batch_max, bms);
 	    if (batch_log) {
 		const icb_cluster_stats& q = cl->stats;
-		fprintf(stderr, "[icb] batch %d worker %d reads %lld: %.0f ms (query %.0f full %.0f align %.0f insert %.0f host %.0f order %.0f cpu %.0f) "
+		fprintf(stderr, "[icb] batch %d worker %d reads %lld: ends at %.0f, %.0f ms (query %.0f full %.0f align %.0f insert %.0f host %.0f order %.0f cpu %.0f) "
 				"chunks %lld rounds %lld pairs %lld ties %lld decisions %lld order_calls %lld clusters %zu\n",
-			b, w, (long long)(bounds[b + 1] - bounds[b]), bms, q.ms_query, q.ms_full, q.ms_align, q.ms_insert, q.ms_host, q.ms_order,
+			b, w, (long long)(bounds[b + 1] - bounds[b]),
+			std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), bms, q.ms_query, q.ms_full, q.ms_align, q.ms_insert, q.ms_host, q.ms_order,
 			q.ms_cpu, (long long)q.chunks, (long long)q.rounds, (long long)q.pairs_aligned, (long long)q.tie_fallbacks,
 			(long long)q.decisions, (long long)q.order_calls, cl->founder.size());
 	    }
@@ -1798,6 +1821,8 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
 		Node& nd = nodes[size_t(b)];
 		nd.worker = w;
 		nd.lo = nd.hi = b;
+		c->aln_priority = batch_aln_priority(c, b, n_batches);
+		c->aln_latency = b < batch_latency_first();
 		int rcw = clusterer_create_on(c, rs, params, &nd.cl);
 		if (!rcw)
 		    rcw = icb_cluster_reads(nd.cl, order + bounds[b], bounds[b + 1] - bounds[b], cluster_of + bounds[b], strand_of + bounds[b]);
@@ -1867,6 +1892,8 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
 		    }
 		const int64_t ne = int64_t(el_reps.size());
 		std::vector<int32_t> ec(static_cast<size_t>(ne)), es(static_cast<size_t>(ne));
+		c->aln_priority = c->lo_priority;
+		c->aln_latency = false;
 		const int rcw = icb_cluster_reads(L.cl, el_reps.data(), ne, ec.data(), es.data());
 		if (rcw) {
 		    fail_worker(w, rcw, c);

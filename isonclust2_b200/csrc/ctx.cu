@@ -100,6 +100,8 @@ icb_ctx* icb_ctx_create_child(icb_ctx* parent)
     ctx->device = parent->device;
     ctx->sm_count = parent->sm_count;
     ctx->hi_priority = parent->hi_priority;
+    ctx->lo_priority = parent->lo_priority;
+    ctx->aln_priority = parent->lo_priority;
     ctx->timing = parent->timing;
     ctx->trace_base = parent->trace_base;
     ctx->blocking_wait = true;
@@ -183,7 +185,10 @@ int icb_ctx_create(int device, icb_ctx** out)
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     {
 	int least = 0, greatest = 0;
-	if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) ctx->hi_priority = greatest;
+	if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) {
+	    ctx->hi_priority = greatest;
+	    ctx->lo_priority = ctx->aln_priority = least;
+	}
     }
     {
 	// memory returned to the stream-ordered pool stays cached in it (no trimming at synchronisation points)

@@ -24,6 +24,10 @@ struct icb_ctx {
     IcbAlignWorkspace* align_ws = nullptr;  // stage 3 buffers (align.cuh), created on first use
     int sm_count = ICB_SM_COUNT_FALLBACK;
     int hi_priority = 0;  // greatest launch priority of the device (cudaDeviceGetStreamPriorityRange)
+    int lo_priority = 0;  // least
+    int aln_priority = 0; // launch priority of this context's alignment kernels in the device loop (a worker's batch rank sets it)
+    bool aln_latency = false;  // device loop: this context's pairs go to the CTA-per-pair kernel (shortest time per pair) instead of
+			       // the warp-per-pair one (most pairs per second)
     cudaStream_t stream = nullptr;
     std::string last_error;
     bool timing = false;

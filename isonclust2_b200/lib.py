@@ -52,6 +52,8 @@ def load():
     L.icb_ctx_kernel_time.argtypes = [_p, C.c_char_p, C.POINTER(_i64), C.POINTER(_dbl)]
     L.icb_ctx_launch_count.argtypes = [_p]
     L.icb_ctx_launch_count.restype = _i64
+    L.icb_debug_residency_start.argtypes = [_p, _i64]
+    L.icb_debug_residency_dump.argtypes = [_p, _p, _i64, C.POINTER(_i64)]
     L.icb_readset_create.argtypes = [_p, _p, _p, _p, _i64, C.POINTER(_p)]
     L.icb_readset_destroy.argtypes = [_p]
     L.icb_readset_destroy.restype = None
