@@ -51,7 +51,11 @@ def digest_key(reads, seed, mode, batch_max_seq, n_genes):
     return f"reads={reads} seed={seed} genes={n_genes} k={K} w={W_} mode={mode} B={BATCH_KB} M={batch_max_seq} minq={MIN_QUAL}"
 
 
-INT_PIPE_PEAK_GCUPS = 148 * 4 * 16 * 1.965 / 7.5  # SMs x sub-partitions x ALU lanes/clk x GHz / ALU instructions per cell = 2482
+# Ceiling of the alignment kernel (integer class): SMs x sub-partitions x 16 ALU lanes per clock (every packed min / max, PRMT and
+# add of the kernel issues at 2 clocks per warp instruction and sub-partition: measured, tools/microbench/pipe_rates.cu) x GHz /
+# ALU-pipe instructions per cell (212 per 4 steps x 8 rows of a lane in the SASS of icb_k_align16w_dp's inner loop = 6.6) = 2820
+ALU_INSTR_PER_CELL = 212 / 32
+INT_PIPE_PEAK_GCUPS = 148 * 4 * 16 * 1.965 / ALU_INSTR_PER_CELL
 KERNELS = ("sketch_reads", "score_reads", "hpc_error_rate", "index_query", "index_query_pool", "index_query_full", "index_insert", "align_dp",
            "align_trace", "align_dp32", "classify_errors", "index_rehash", "sketch_reads_long", "sketch_reads_cta", "gather_minimizers",
            "dl_init", "dl_decide", "dl_order", "dl_order_large", "dl_commit", "dl_gather", "dl_finalize")
@@ -322,10 +326,10 @@ def run_ours(args):
     if mode == "fast":
         roofline = dict(index_probe)
     else:
-        # the dominant kernel: icb_k_align16_dp, integer-ALU class.  achieved = cells of the saturated replay / summed DP launch
+        # the dominant kernel: icb_k_align16w_dp, integer-ALU class.  achieved = cells of the saturated replay / summed DP launch
         # time on one stream; ceiling = ALU-pipe issue: 15 ALU-pipe instructions per packed update of 2 cells
-        roofline = {"bound": "int-alu", "kernel": "icb_k_align16_dp (align_dp)", "achieved": dp_sat["gcups"] if dp_sat else 0.0,
-                    "peak": INT_PIPE_PEAK_GCUPS, "peak_source": "148 SM x 4 x 16 lanes x 1.965 GHz / 7.5 ALU instr per cell",
+        roofline = {"bound": "int-alu", "kernel": "icb_k_align16w_dp (align_dp)", "achieved": dp_sat["gcups"] if dp_sat else 0.0,
+                    "peak": INT_PIPE_PEAK_GCUPS, "peak_source": "148 SM x 4 x 16 ALU lanes x 1.965 GHz / 6.6 ALU-pipe instr per cell (SASS; issue rates measured, tools/microbench/pipe_rates.cu)",
                     "unit": "GCUPS", "frac": (dp_sat["gcups"] / INT_PIPE_PEAK_GCUPS) if dp_sat else 0.0, "traffic": None,
                     "saturated_replay": dp_sat,
                     "in_step": {"cells_per_step": st["cells_aligned"], "pairs_per_step": st["pairs_aligned"],

@@ -420,7 +420,7 @@ int icb_align32_run_dev(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_se
 namespace {
 
 constexpr int64_t LIMIT16 = 8000;			  // align16: H + 2j + 64 must stay below 2^15
-constexpr int64_t TRACE_BUDGET_TILES = (int64_t(1) << 30) / 32;  // trace arena per launch (and per worker): 1 GiB
+constexpr int64_t TRACE_BUDGET_TILES = (int64_t(4) << 30) / 32;  // trace arena per launch of icb_align_pairs: 4 GiB (a few thousand read pairs: every SM full)
 
 struct Launch {
     std::vector<IcbPairDesc> descs;

@@ -578,6 +578,7 @@ __device__ __forceinline__ void stripw(Lane16& S, PassW& P, const uint8_t* __res
 	if (pass > 0) {
 	    const int need = (pass - 1) * 65536 + min(m, upto);
 	    while (s_prog[above] < need) __nanosleep(64);
+	    if (nwarps > 1) __threadfence_block();
 	}
 	v.x = (pass > 0 && c < m) ? __ldcg(line + c) : (uint32_t(2 * c + A16_BIAS) | 0x00010000u);
 	v.y = c < m ? (4u << (8 * (code5(icb_ref_char(seq, d, c)) & 3))) : 0u;
@@ -612,7 +613,7 @@ __device__ __forceinline__ void stripw(Lane16& S, PassW& P, const uint8_t* __res
 	    const int base = sl0 & ~(AW_GROUP - 1);
 	    const int c = base + lane - 63;
 	    if (c >= 0 && c < m && base + lane <= sl0 + 7) __stcg(line + c, s_out[lane]);
-	    if (nwarps > 1) __threadfence();  // the line is read by another warp, through L2
+	    if (nwarps > 1) __threadfence_block();  // the line is read by another warp of this CTA (both sides go to L2: .cg)
 	    __syncwarp();
 	    if (lane == 0) s_prog[warp] = pass * 65536 + (blk + 1 == nblk ? m : max(0, min(m, sl0 + 8 - 63)));
 	}

@@ -34,7 +34,7 @@ if has ncu_sketch; then
 fi
 if has ncu_align; then
     # the saturated launch (all pairs of 3000 reads in one call), bracketed by cudaProfilerStart/Stop inside the tool
-    timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:icb_k_align16_dp -c 1 -f -o $O/${tag}_align16 \
+    timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:icb_k_align16w?_dp -c 1 -f -o $O/${tag}_align16 \
         python tools/bench_align.py 3000 128 1 prof > $O/${tag}_ncu_align.log 2>&1
     ncu -i $O/${tag}_align16.ncu-rep --page raw --csv > $O/${tag}_align16_raw.csv 2>/dev/null
     echo "ncu align exit $?"

@@ -39,3 +39,19 @@ def coverage(mask, label):
 coverage(np.ones(len(rows), bool), "all kernels")
 for n in names:
     coverage(nm == n, n)
+
+# where the chain of ONE stream spends its time: kernels by name and the gaps between consecutive launches
+streams = collections.Counter(r[1] for r in rows)
+print("\nper-stream chains (the three streams with the most launches):")
+for sid, cnt in streams.most_common(3):
+    m = np.array([r[1] == sid for r in rows])
+    order = np.argsort(a[m])
+    sa, sb, sn = a[m][order], b[m][order], nm[m][order]
+    span = sb.max() - sa.min()
+    gaps = np.maximum(0.0, sa[1:] - np.maximum.accumulate(sb)[:-1])
+    print(f" stream {sid}: {cnt} launches over {span:.1f} ms; in kernels {np.sum(sb - sa):.1f} ms; gaps {gaps.sum():.1f} ms "
+          f"(gaps > 50 us: {np.sum(gaps > 0.05)} totalling {gaps[gaps > 0.05].sum():.1f} ms)")
+    for n in names:
+        k = sn == n
+        if k.any():
+            print(f"     {n:22s} {k.sum():6d} launches {np.sum(sb[k] - sa[k]):9.1f} ms  avg {np.mean(sb[k] - sa[k]) * 1e3:8.1f} us  p90 {np.percentile(sb[k] - sa[k], 90) * 1e3:8.1f} us")
