@@ -22,6 +22,7 @@
 #include <cstring>
 #include <numeric>
 
+#include "residency.cuh"
 #include "align.cuh"
 
 namespace {
@@ -456,6 +457,7 @@ int run_launch(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_seq, Launch
 int icb_align_pairs_on(icb_ctx* ctx, icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int kmer_size,
 		       icb_align_result* results)
 {
+    IcbRange nvtx_range("ParasailAlign batch (icb_align_pairs)");
     if (n_pairs == 0) return ICB_OK;
     if (!ctx->align_ws) ctx->align_ws = new IcbAlignWorkspace;
     IcbAlignWorkspace& ws = *ctx->align_ws;
@@ -598,3 +600,5 @@ int icb_align_pairs(icb_readset* rs, const icb_pair* pairs, int64_t n_pairs, int
 }
 
 }  // extern "C"
+
+cudaError_t icb_residency_set_align32(const IcbResidencyLog& L) { return icb_residency_set_here(L); }

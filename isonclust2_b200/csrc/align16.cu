@@ -28,30 +28,7 @@
 
 #include "align.cuh"
 
-// Diagnostics (icb_debug_residency_start / _dump): when enabled, every alignment CTA (DP) / warp (traceback) leaves one
-// record {kind | smid << 8, start, end, n | m << 16} with the times in units of 1.024 us of the global timer, from which
-// tools/residency.py rebuilds how many alignment CTAs each SM held over a step.
-struct IcbResidencyLog {
-    uint4* rec;
-    unsigned int* count;
-    unsigned int cap;
-};
-__device__ IcbResidencyLog g_icb_residency = {nullptr, nullptr, 0u};
-__device__ __forceinline__ unsigned int icb_res_now()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return static_cast<unsigned int>(t >> 10);
-}
-__device__ __forceinline__ void icb_res_record(int kind, unsigned int t0, int n, int m)
-{
-    const IcbResidencyLog L = g_icb_residency;
-    if (!L.rec) return;
-    unsigned int smid;
-    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    const unsigned int at = atomicAdd(L.count, 1u);
-    if (at < L.cap) L.rec[at] = make_uint4(unsigned(kind) | (smid << 8), t0, icb_res_now(), unsigned(n) | (unsigned(m) << 16));
-}
+#include "residency.cuh"
 
 namespace {
 
@@ -397,7 +374,7 @@ icb_k_align16_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict_
 	    }
 	    e.status = 0;
 	    ends[blockIdx.x] = e;
-	    icb_res_record(1, res_t0, n, m);
+	    icb_res_record(RES_DP_CTA, icb_res_tag(descs), res_t0, unsigned(n) | (unsigned(m) << 16));
 	}
     }
 }
@@ -629,6 +606,7 @@ __global__ void __launch_bounds__(32 * AW_MAXW, 3)
 icb_k_align16w_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict__ descs, uint4* __restrict__ trace,
 		  uint32_t* __restrict__ lines, IcbAlignEnd* __restrict__ ends, const int32_t* __restrict__ n_pairs_dev)
 {
+    icb_res_mark(RES_DP, descs);
     if (n_pairs_dev && int(blockIdx.x) >= *n_pairs_dev) return;  // device-built pair queue (dloop.cu): the grid is its capacity
     const unsigned int res_t0 = g_icb_residency.rec ? icb_res_now() : 0u;
     __shared__ uint2 s_feed[AW_MAXW][2 * AW_GROUP];
@@ -717,7 +695,7 @@ icb_k_align16w_dp(const uint8_t* __restrict__ seq, const IcbPairDesc* __restrict
 	}
 	e.status = 0;
 	ends[blockIdx.x] = e;
-	icb_res_record(1, res_t0, n, m);
+	icb_res_record(RES_DP_CTA, icb_res_tag(descs), res_t0, unsigned(n) | (unsigned(m) << 16));
     }
 }
 
@@ -788,6 +766,7 @@ icb_k_align16_trace(const uint8_t* __restrict__ seq, const IcbPairDesc* __restri
 		    const uint4* __restrict__ trace, const IcbAlignEnd* __restrict__ ends, int k,
 		    icb_align_result* __restrict__ out, const int32_t* __restrict__ n_pairs_dev, int32_t* __restrict__ aln_out)
 {
+    icb_res_mark(RES_TRACE, descs);
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * TB_WARPS + (threadIdx.x >> 5);
     if (n_pairs_dev) n_pairs = *n_pairs_dev;
@@ -866,7 +845,7 @@ icb_k_align16_trace(const uint8_t* __restrict__ seq, const IcbPairDesc* __restri
     }
     if (i < 0 && j >= 0) st.push_zeros(j + 1, lane);
     else if (j < 0 && i >= 0) st.push_zeros(i + 1, lane);
-    if (lane == 0) icb_res_record(2, res_t0, n, m);
+    if (lane == 0) icb_res_record(RES_TRACE_WARP, icb_res_tag(descs), res_t0, unsigned(n) | (unsigned(m) << 16));
     if (aln_out) {
 	if (lane == 0) aln_out[d.out] = st.pushed >= k ? st.aligned : 0;
 	return;
@@ -952,6 +931,18 @@ int icb_align16_run_dev(icb_ctx* ctx, IcbAlignWorkspace& ws, const uint8_t* d_se
 }
 
 // ------------------------------------------------------------------------------------------------ diagnostics
+cudaError_t icb_residency_set_dloop(const IcbResidencyLog& L);
+cudaError_t icb_residency_set_index(const IcbResidencyLog& L);
+cudaError_t icb_residency_set_align32(const IcbResidencyLog& L);
+static cudaError_t residency_set_everywhere(const IcbResidencyLog& L)
+{
+    cudaError_t e = icb_residency_set_here(L);
+    if (e == cudaSuccess) e = icb_residency_set_dloop(L);
+    if (e == cudaSuccess) e = icb_residency_set_index(L);
+    if (e == cudaSuccess) e = icb_residency_set_align32(L);
+    return e;
+}
+
 extern "C" {
 
 int icb_debug_residency_start(icb_ctx* ctx, int64_t capacity)
@@ -967,7 +958,7 @@ int icb_debug_residency_start(icb_ctx* ctx, int64_t capacity)
     ICB_CUDA(ctx, cudaMalloc(&L.count, sizeof(unsigned int)));
     ICB_CUDA(ctx, cudaMemset(L.count, 0, sizeof(unsigned int)));
     L.cap = unsigned(capacity);
-    ICB_CUDA(ctx, cudaMemcpyToSymbol(g_icb_residency, &L, sizeof L));
+    ICB_CUDA(ctx, residency_set_everywhere(L));
     ICB_CUDA(ctx, cudaDeviceSynchronize());
     return ICB_OK;
 }
@@ -989,7 +980,7 @@ int icb_debug_residency_dump(icb_ctx* ctx, uint32_t* records, int64_t capacity, 
     cudaFree(L.rec);
     cudaFree(L.count);
     L = IcbResidencyLog{nullptr, nullptr, 0u};
-    ICB_CUDA(ctx, cudaMemcpyToSymbol(g_icb_residency, &L, sizeof L));
+    ICB_CUDA(ctx, residency_set_everywhere(L));
     return ICB_OK;
 }
 

@@ -614,6 +614,7 @@ int icb_clusterer::upload_founders(int64_t from)
 int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of,
 				 int32_t* strand_of)
 {
+    IcbRange nvtx_range("chunk: host loop");
     cudaStream_t st = ctx->stream;
     const std::vector<int32_t>&nf = rs->h_nf, &nr = rs->h_nr, &hpc_len = rs->h_hpc_len;
     const std::vector<double>& raw_err = rs->h_err;
@@ -1109,6 +1110,7 @@ int icb_clusterer::process_chunk(const std::vector<int32_t>& chunk, const std::v
 int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const std::vector<int64_t>& slots, int32_t* cluster_of,
 					int32_t* strand_of, bool& handled)
 {
+    IcbRange nvtx_range("chunk: device loop");
     handled = false;
     cudaStream_t st = ctx->stream;
     const int N = int(chunk.size());
@@ -1208,6 +1210,7 @@ int icb_clusterer::process_chunk_device(const std::vector<int32_t>& chunk, const
     if (rc) return rc;
     rc = chunk_idx.reserve(tot);
     if (rc) return rc;
+    qa.res_tag = qf.res_tag = uint32_t((unsigned long long)(V.descs16) >> 8) & 0xfffffu;
     qa.chunk_idx = qf.chunk_idx = chunk_idx.v;
     qa.main_idx = qf.main_idx = main_idx.v;
     rc = icb_index_insert(ctx, chunk_idx, rs, d_chunk_reads, d_ids, N);
@@ -1633,6 +1636,7 @@ static int cluster_batches_impl(icb_readset* rs, const icb_cluster_params* param
 			int32_t n_batches, int32_t n_workers, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
 			icb_cluster_stats* stats)
 {
+    IcbRange nvtx_range("cluster of every batch (icb_cluster_batches)");
     if (!rs || !params || n_batches < 0 || (n_batches > 0 && (!order || !bounds || !cluster_of || !strand_of))) return ICB_ERR_ARG;
     icb_ctx* ctx = rs->ctx;
     ICB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1744,6 +1748,7 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
 		     int32_t n_workers, int32_t min_cls_size, int32_t* cluster_of, int32_t* strand_of, int64_t* n_clusters,
 		     icb_cluster_stats* stats, icb_tree_trace* trace)
 {
+    IcbRange nvtx_range("batches + merge tree (icb_cluster_tree)");
     if (!rs || !params || n_batches < 0 || (n_batches > 0 && (!order || !bounds || !cluster_of || !strand_of))) return ICB_ERR_ARG;
     icb_ctx* ctx = rs->ctx;
     ICB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1993,6 +1998,7 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
 
 int icb_cluster_reads(icb_clusterer* cl, const int32_t* order, int64_t n, int32_t* cluster_of, int32_t* strand_of)
 {
+    IcbRange nvtx_range("ClusterSortedReads (icb_cluster_reads)");
     if (!cl || n < 0 || (n > 0 && (!order || !cluster_of || !strand_of))) return ICB_ERR_ARG;
     icb_ctx* ctx = cl->ctx;
     ICB_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -289,6 +289,7 @@ static const int64_t PAD = 256;	 // slack after the byte buffers so 16-byte tile
 int icb_readset_create(icb_ctx* ctx, const char* seq, const char* qual, const int64_t* offs, int64_t n_reads,
 		       icb_readset** out)
 {
+    IcbRange nvtx_range("upload reads (icb_readset_create)");
     if (!ctx || !out || n_reads < 0 || (n_reads > 0 && (!seq || !qual || !offs))) return ICB_ERR_ARG;
     *out = nullptr;
     ICB_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 
+#include "residency.cuh"
 #include "dloop.cuh"
 #include "ref_order_hd.h"
 
@@ -459,6 +460,7 @@ __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_init(IcbDLoopView V, int 
 							      unsigned long long full_cap, unsigned long long tiles_cap,
 							      unsigned long long words_cap)
 {
+    icb_res_mark(RES_INIT, V.descs16);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
 	IcbDLoopState& s = *V.st;
@@ -507,6 +509,7 @@ __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_init(IcbDLoopView V, int 
 // one warp per chunk position
 __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_decide(IcbDLoopView V)
 {
+    icb_res_mark(RES_DECIDE, V.descs16);
     __shared__ IcbCand s_c[DL_WARPS][DL_CW];
     const volatile IcbDLoopState* st = V.st;
     if (st->done || st->fallback) return;
@@ -525,6 +528,7 @@ __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_decide(IcbDLoopView V)
 template <int NMAX>
 __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_order(IcbDLoopView V, const int32_t* __restrict__ list, const int32_t* __restrict__ n_list)
 {
+    icb_res_mark(NMAX == DL_NMAX_S ? RES_ORDER : RES_ORDER_L, V.descs16);
     extern __shared__ __align__(16) unsigned char dl_smem[];
     __shared__ DlShared S;
     const volatile IcbDLoopState* st = V.st;
@@ -584,6 +588,7 @@ __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_order(IcbDLoopView V, con
 // one warp walks the chunk from the commit frontier
 __global__ void __launch_bounds__(32) icb_k_dl_commit(IcbDLoopView V)
 {
+    icb_res_mark(RES_COMMIT, V.descs16);
     __shared__ IcbCand s_c[DL_CW];
     IcbDLoopState* st = V.st;
     const volatile IcbDLoopState* vst = V.st;
@@ -622,7 +627,7 @@ __global__ void __launch_bounds__(32) icb_k_dl_commit(IcbDLoopView V)
 		V.out_cls[pos] = V.dec_cls[pos];
 		V.out_strand[pos] = V.dec_strand[pos];
 	    }
-	    __threadfence();
+	    __threadfence_block();  // lane 0 -> the other lanes of this warp (the next read's decision); later kernels see it at the kernel boundary
 	}
 	__syncwarp();
 	pos++;
@@ -653,6 +658,7 @@ constexpr int GA_ITEMS = DL_MAXW * 32 / DL_THREADS;  // chunk positions per thre
 
 __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_gather(IcbDLoopView V, int max_pairs)
 {
+    icb_res_mark(RES_GATHER, V.descs16);
     typedef cub::BlockScan<long long, DL_THREADS> Scan;
     __shared__ typename Scan::TempStorage tmp;
     IcbDLoopState* st = V.st;
@@ -800,6 +806,7 @@ __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_gather(IcbDLoopView V, in
 // reads, and the chunk's query totals
 __global__ void __launch_bounds__(DL_THREADS) icb_k_dl_finalize(IcbDLoopView V, int* n_ins)
 {
+    icb_res_mark(RES_FINALIZE, V.descs16);
     IcbDLoopState* st = V.st;
     if (threadIdx.x == 0) *n_ins = 0;
     if (!st->done || st->fallback) return;
@@ -886,3 +893,5 @@ int icb_dl_finalize(icb_ctx* ctx, const IcbDLoopView& V, int* d_n_ins)
     ICB_LAUNCH(ctx, "dl_finalize", icb_k_dl_finalize<<<1, DL_THREADS, 0, ctx->stream>>>(V, d_n_ins));
     return ICB_OK;
 }
+
+cudaError_t icb_residency_set_dloop(const IcbResidencyLog& L) { return icb_residency_set_here(L); }

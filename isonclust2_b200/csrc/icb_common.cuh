@@ -1,5 +1,6 @@
 // Internal definitions shared by the CUDA translation units of libisonclust2_b200.so.
 #pragma once
+#include <nvtx3/nvToolsExt.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -64,6 +65,15 @@ inline cudaError_t icb_dfree(icb_ctx* ctx, void* p) { return p ? cudaFreeAsync(p
 	cudaError_t e__ = (call);                                             \
 	if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, #call, __FILE__, __LINE__); \
     } while (0)
+
+// NVTX range over a host-side phase of the path (header-only NVTX 3: a no-op unless a tool is attached); the names are the
+// reference's function names, so a timeline reads like its call stack.
+struct IcbRange {
+    explicit IcbRange(const char* name) { nvtxRangePushA(name); }
+    ~IcbRange() { nvtxRangePop(); }
+    IcbRange(const IcbRange&) = delete;
+    IcbRange& operator=(const IcbRange&) = delete;
+};
 
 // RAII-free launch bracket: ICB_LAUNCH(ctx, "name", kernel<<<...>>>(...));
 #define ICB_LAUNCH(ctx, name, ...)                                            \

@@ -17,6 +17,7 @@
 // chains), reported as hits/s; bytes per read = 12(M_f+M_r) + 8(M_f+M_r) + 8H + 16C.
 #include <mutex>
 
+#include "residency.cuh"
 #include "dloop.cuh"
 #include "index.cuh"
 
@@ -241,6 +242,8 @@ __global__ void __launch_bounds__(Q_THREADS) icb_k_query_ptr(const IcbQueryArgs*
 template <bool SMEM_CNT>
 __device__ __forceinline__ void icb_query_body(const IcbQueryArgs& a)
 {
+    if (g_icb_residency.rec && blockIdx.x == 0 && threadIdx.x == 0)
+	icb_res_record(a.mode == 2 ? RES_QUERY_POOL : RES_QUERY_FULL, a.res_tag, icb_res_now(), 0u);
     extern __shared__ uint32_t sm[];
     __shared__ int s_red[Q_THREADS / 32];
     __shared__ int s_red2[Q_THREADS / 32];
@@ -811,3 +814,5 @@ int icb_classify_errors(icb_ctx* ctx, const double* d_err, const int32_t* d_stat
     ICB_LAUNCH(ctx, "classify_errors", icb_k_classify<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(d_err, d_status, n, d_class));
     return ICB_OK;
 }
+
+cudaError_t icb_residency_set_index(const IcbResidencyLog& L) { return icb_residency_set_here(L); }

@@ -85,6 +85,7 @@ struct IcbQueryArgs {
     // device-resident loop (dloop.cuh): work lists and pools live on the device
     struct IcbDLoopState* dl_state;	// pool cursors, fallback flag; NULL on the host-loop path
     const int32_t* dl_n_list;		// number of entries of `list`, written by the gather kernel
+    uint32_t res_tag;			// diagnostics: the batch's tag in the residency log (residency.cuh)
     IcbCand* dl_pool;			// mode 2: candidate pool (records) ...
     int32_t* dl_pool_aln;		// ... and its alignment results, reset to "unknown"
     IcbCand* dl_full_pool;		// mode 2: full-list pool; reads whose best candidates are tied get their full list right away

@@ -210,6 +210,7 @@ extern "C" {
 
 int icb_score_reads(icb_readset* rs, int kmer_size, const double qualtab[129], const double qualtab_nomin[129])
 {
+    IcbRange nvtx_range("FillQualScores (icb_score_reads)");
     if (!rs || !qualtab || !qualtab_nomin) return ICB_ERR_ARG;
     icb_ctx* ctx = rs->ctx;
     if (kmer_size < 1 || kmer_size > 31) return ctx->fail(ICB_ERR_ARG, "kmer_size must be in [1,31]");

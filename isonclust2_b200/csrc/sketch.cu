@@ -934,6 +934,7 @@ extern "C" {
 int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const double qualtab_nomin[129],
 		     const uint8_t* skip)
 {
+    IcbRange nvtx_range("PrepareSortedBatch sketches (icb_sketch_reads)");
     if (!rs || !qualtab_nomin) return ICB_ERR_ARG;
     icb_ctx* ctx = rs->ctx;
     const int k = kmer_size, w = window_size;

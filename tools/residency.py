@@ -29,8 +29,8 @@ buf = np.zeros((cap, 4), dtype=np.uint32)
 got = C.c_int64()
 ctx.check(ctx.L.icb_debug_residency_dump(ctx.h, buf.ctypes.data, cap, C.byref(got)))
 rec = buf[: got.value]
-kind = rec[:, 0] & 0xFF
-sm = rec[:, 0] >> 8
+kind = rec[:, 0] & 0xF
+sm = (rec[:, 0] >> 4) & 0xFF
 t0 = rec[:, 1].astype(np.int64)
 t1 = rec[:, 2].astype(np.int64)
 base = t0.min()
