@@ -1010,6 +1010,347 @@ static int main_cluster(int argc, char** argv)
     return 0;
 }
 
+// ---------------------------------------------------------------- tree: every batch of a sort + the whole merge tree in one process
+// What the reference's pipeline runs as one `cluster` job per batch file and one `cluster -l A -r B` job per merge
+// (README.md:105-117), on ONE device context: the reads of all batches are uploaded, scored and sketched once, every
+// node's index and representatives stay resident between levels (icb_cluster_tree_traced), and the batches of the nodes —
+// cluster lists in the reference's order, MinDB, consensus chains — are rebuilt on the host from the decisions with the same
+// code that serves `cluster` (apply_decisions).  The root is written as the `.cer` the last merge job would write.
+struct CmdArgsTree {
+    bool Verbose = false, MinPurge = false, SeqPurge = false;
+    int MinClsSize = -1, Workers = 0;
+    std::string BatchDir, OutCereal;
+    int Mode = None;
+};
+
+static void print_help_tree()
+{
+    cerr << "Usage: isONclust2 tree [flags] -o root.cer <directory with the isONbatch_<i>.cer files of `sort`>\n"
+	 << "Clusters every sorted batch and merges them as a tree (what `cluster` does per file and per pair of files), in one process.\n"
+	 << "\t-x --mode\t\tClustering mode: sahlin, fast, furious.\n"
+	 << "\t-o --outfile\t\tOutput batch (the root of the tree).\n"
+	 << "\t-F --min-cls-size\tMinimum cluster size of merged right batches.\n"
+	 << "\t-w --workers\t\tBatches / merges in flight (default: library default).\n"
+	 << "\t-z --min-purge\t\tPurge the minimizer database of the output batch.\n"
+	 << "\t-j --keep-seq\t\tAs for cluster.\n"
+	 << "\t-v --verbose\t\tVerbose output.\n";
+}
+
+static CmdArgsTree parse_args_tree(int argc, char** argv)
+{
+    static const struct option longopts[] = {
+	{"verbose", no_argument, 0, 'v'},	   {"min-purge", no_argument, 0, 'z'},	 {"min-cls-size", required_argument, 0, 'F'},
+	{"keep-seq", no_argument, 0, 'j'},	   {"mode", required_argument, 0, 'x'},	 {"help", no_argument, 0, 'h'},
+	{"outfile", required_argument, 0, 'o'},	   {"workers", required_argument, 0, 'w'}, {0, 0, 0, 0},
+    };
+    CmdArgsTree res;
+    argc--;
+    argv++;
+    int iarg = 0, index;
+    while ((iarg = getopt_long(argc, argv, "hvo:x:zjF:w:", longopts, &index)) != -1) {
+	switch (iarg) {
+	    case 'h': print_help_tree(); exit(0);
+	    case 'o': res.OutCereal = optarg; break;
+	    case 'v': res.Verbose = true; break;
+	    case 'z': res.MinPurge = true; break;
+	    case 'j': res.SeqPurge = true; break;
+	    case 'F': res.MinClsSize = atoi(optarg); break;
+	    case 'w': res.Workers = atoi(optarg); break;
+	    case 'x':
+		if (!parse_mode(optarg, &res.Mode)) exit(1);
+		break;
+	    default: break;
+	}
+    }
+    if (optind >= argc) {
+	cerr << "The directory of the sorted batches is mandatory!" << endl;
+	print_help_tree();
+	exit(1);
+    }
+    res.BatchDir = argv[optind];
+    if (res.OutCereal == "") {
+	cerr << "Specifying output batch file is mandatory!" << endl;
+	print_help_tree();
+	exit(1);
+    }
+    return res;
+}
+
+static void fill_cluster_params(const CmdArgs& args, icb_cluster_params& P)
+{
+    memset(&P, 0, sizeof(P));
+    P.kmer_size = args.KmerSize;
+    P.window_size = args.WindowSize;
+    P.mode = args.Mode;
+    P.min_shared = args.MinShared;
+    P.mapped_threshold = args.MappedThreshold;
+    P.aligned_threshold = args.AlignedThreshold;
+    P.min_fraction = args.MinFraction;
+    P.min_prob_no_hits = args.MinProbNoHits;
+    P.min_qual = args.MinQual;
+    load_p_shared(args.KmerSize, args.WindowSize, P.p_shared);
+    const char* chunk = getenv("ICB_CHUNK");
+    P.chunk_size = chunk ? atoi(chunk) : 0;
+}
+
+// the per-batch preparation of main_cluster's single-batch case (main.cpp:286-303 of the reference)
+static std::unique_ptr<Batch> reset_for_single(Batch& left, int mode, int min_cls_size)
+{
+    auto right = create_pseudo_batch(left);
+    left.Cls.clear();
+    if (left.Depth > 0) left.Depth = -left.Depth;
+    left.NrCls = 0;
+    left.MinDB = MinimizerDB(MIN_DB_RESERVE, UnsignedHash());
+    if (left.SortArgs.Mode != mode) left.SortArgs.Mode = mode;
+    if (right->SortArgs.Mode != mode) right->SortArgs.Mode = mode;
+    if (min_cls_size > 0) left.SortArgs.MinClsSize = min_cls_size;
+    right->MinDB = MinimizerDB(0, UnsignedHash());
+    return right;
+}
+
+static int main_tree(int argc, char** argv)
+{
+    CmdArgsTree cmd = parse_args_tree(argc, argv);
+    VERBOSE = cmd.Verbose;
+    // ---- the sorted batches, in order
+    std::vector<std::unique_ptr<Batch>> nodes;
+    std::vector<std::string> names;
+    for (int b = 0;; b++) {
+	const std::string path = cmd.BatchDir + "/isONbatch_" + std::to_string(b) + ".cer";
+	FILE* f = fopen(path.c_str(), "rb");
+	if (!f) break;
+	fclose(f);
+	nodes.push_back(load_or_die(path));
+	names.push_back(path);
+    }
+    const int nb = int(nodes.size());
+    if (nb == 0) {
+	cerr << "No sorted batches (isONbatch_0.cer ...) in " << cmd.BatchDir << endl;
+	return 1;
+    }
+    for (int b = 0; b < nb; b++) {
+	Batch& B = *nodes[size_t(b)];
+	if (B.SortArgs.ConsMaxSize > 0) {
+	    cerr << "isONclust2 (B200): consensus generation (-c " << B.SortArgs.ConsMaxSize
+		 << ") is not part of this build; sort with the default -c (disabled)." << endl;
+	    return 1;
+	}
+	CmdArgs a = B.SortArgs, z = nodes[0]->SortArgs;
+	a.Mode = z.Mode = cmd.Mode;
+	if (!same_sort_args(a, z)) {
+	    cerr << "The batches have been sorted with different parameters! " << endl;
+	    return 1;
+	}
+    }
+    // ---- leaves: what `cluster -l isONbatch_b.cer` prepares; the reads the device sees are the eligible ones of every batch
+    std::vector<std::unique_ptr<Batch>> rights(static_cast<size_t>(nb));
+    std::vector<std::vector<size_t>> eligible(static_cast<size_t>(nb));
+    std::string seq, qual;
+    std::vector<int64_t> offs{0}, bounds{0};
+    for (int b = 0; b < nb; b++) {
+	Batch& L = *nodes[size_t(b)];
+	rights[size_t(b)] = reset_for_single(L, cmd.Mode, cmd.MinClsSize);
+	Batch& R = *rights[size_t(b)];
+	unsigned sf = 0;
+	for (size_t i = 0; i < R.Cls.size(); i++)
+	    if (right_is_eligible(L, R, i, &sf)) {
+		eligible[size_t(b)].push_back(i);
+		const SeqRec& s = *R.Cls[i]->at(0)->raw;
+		seq += s.seq;
+		qual += s.qual;
+		offs.push_back(int64_t(seq.size()));
+	    }
+	bounds.push_back(int64_t(offs.size()) - 1);
+    }
+    const CmdArgs args = nodes[0]->SortArgs;
+    const int64_t n = int64_t(offs.size()) - 1;
+    const int min_cls = args.MinClsSize;
+    std::vector<int32_t> leaf_c, leaf_s;
+    struct Job {
+	int32_t left, right;
+	std::vector<int32_t> cls, strand;
+    };
+    std::vector<Job> jobs;
+    if (args.Mode == None || n == 0) {
+	cerr << "isONclust2 (B200): tree needs a clustering mode (-x) and at least one eligible read" << endl;
+	return 1;
+    }
+    {
+	double qualTab[129], qualTabNomin[129];
+	icb_init_qual_tab(qualTab, 0);
+	icb_init_qual_tab(qualTabNomin, 1);
+	icb_ctx* ctx = open_device();
+	icb_readset* rs = nullptr;
+	ICB_DO(ctx, icb_readset_create(ctx, seq.data(), qual.data(), offs.data(), n, &rs));
+	ICB_DO(ctx, icb_score_reads(rs, args.KmerSize, qualTab, qualTabNomin));
+	ICB_DO(ctx, icb_sketch_reads(rs, args.KmerSize, args.WindowSize, qualTabNomin, nullptr));
+	{  // the sketches in the batch files must be the ones this k / w produce
+	    const size_t un = static_cast<size_t>(n);
+	    std::vector<int32_t> status(un, 0);
+	    std::vector<int64_t> mo(un + 1, 0), ro(un + 1, 0);
+	    int64_t nf = 0, nr = 0;
+	    ICB_DO(ctx, icb_sketch_sizes(rs, &nf, &nr));
+	    std::vector<Minimizer> mins(static_cast<size_t>(nf) + 1), rev(static_cast<size_t>(nr) + 1);
+	    ICB_DO(ctx, icb_sketch_download(rs, status.data(), nullptr, nullptr, nullptr, nullptr, reinterpret_cast<icb_minimizer*>(mins.data()),
+					    mo.data(), reinterpret_cast<icb_minimizer*>(rev.data()), ro.data()));
+	    int64_t r = 0;
+	    for (int b = 0; b < nb; b++)
+		for (size_t i : eligible[size_t(b)]) {
+		    const ProcSeq& p = *rights[size_t(b)]->Cls[i]->at(0);
+		    const bool same = status[r] == 1 && size_t(mo[r + 1] - mo[r]) == p.mins.size() && size_t(ro[r + 1] - ro[r]) == p.rev.size() &&
+				      (p.mins.empty() || memcmp(p.mins.data(), mins.data() + mo[r], p.mins.size() * sizeof(Minimizer)) == 0) &&
+				      (p.rev.empty() || memcmp(p.rev.data(), rev.data() + ro[r], p.rev.size() * sizeof(Minimizer)) == 0);
+		    if (!same) {
+			cerr << "isONclust2 (B200): the stored minimizers of " << p.id << " are not those of k=" << args.KmerSize
+			     << " w=" << args.WindowSize << " on its stored sequence; refusing to cluster an inconsistent batch." << endl;
+			exit(1);
+		    }
+		    r++;
+		}
+	}
+	icb_cluster_params P;
+	fill_cluster_params(args, P);
+	std::vector<int32_t> order(static_cast<size_t>(n)), cluster_of(static_cast<size_t>(n), -1), strand_of(static_cast<size_t>(n), 0);
+	for (int64_t r = 0; r < n; r++) order[size_t(r)] = int32_t(r);
+	std::vector<int64_t> ncl(static_cast<size_t>(nb), 0);
+	icb_cluster_stats st;
+	icb_tree_trace* tr = nullptr;
+	{
+	    int rc = icb_cluster_tree_traced(rs, &P, order.data(), bounds.data(), nb, cmd.Workers, min_cls, cluster_of.data(), strand_of.data(),
+					     ncl.data(), &st, &tr);
+	    if (rc == ICB_ERR_NO_PEMP) {
+		cerr << "terminate called after throwing an instance of 'std::invalid_argument'\n  what():  Empirical probability lookup failure!" << endl;
+		abort();
+	    }
+	    if (rc) die_icb(ctx, rc, "icb_cluster_tree_traced");
+	}
+	const int32_t *lc = nullptr, *ls = nullptr;
+	ICB_DO(ctx, icb_tree_trace_leaves(tr, &lc, &ls));
+	leaf_c.assign(lc, lc + n);
+	leaf_s.assign(ls, ls + n);
+	for (int32_t j = 0; j < icb_tree_trace_jobs(tr); j++) {
+	    Job J;
+	    int64_t nr = 0;
+	    const int32_t *jc = nullptr, *js = nullptr;
+	    ICB_DO(ctx, icb_tree_trace_job(tr, j, &J.left, &J.right, &nr, &jc, &js));
+	    J.cls.assign(jc, jc + nr);
+	    J.strand.assign(js, js + nr);
+	    jobs.push_back(std::move(J));
+	}
+	if (VERBOSE) {
+	    cerr << "Finished clustering " << nb << " batches and " << jobs.size() << " merges!" << endl;
+	    cerr << "Alignment invocation count: " << st.aln_invoked << endl;
+	}
+	icb_tree_trace_destroy(tr);
+	icb_readset_destroy(rs);
+	icb_ctx_destroy(ctx);
+    }
+    // A node the file-based tree writes and reads back is not the node it had in memory: the MinDB of a loaded batch is an
+    // unordered_map refilled in file order, and its iteration order decides the byte order of the next file.  The round trip
+    // is part of the reference's behaviour, so every rebuilt node takes it too (through a scratch file next to the output).
+    const std::string scratch = cmd.OutCereal + ".node.tmp";
+    auto round_trip = [&](std::unique_ptr<Batch>& node) {
+	save_batch(*node, scratch);
+	node = load_or_die(scratch);
+	remove(scratch.c_str());
+    };
+    // ---- rebuild the leaves
+    for (int b = 0; b < nb; b++) {
+	Batch& L = *nodes[size_t(b)];
+	Batch& R = *rights[size_t(b)];
+	std::vector<int32_t> best(R.Cls.size(), -2), strand(R.Cls.size(), 0);
+	int32_t ncls = 0;
+	int64_t t = bounds[size_t(b)];
+	for (size_t i : eligible[size_t(b)]) {
+	    const int32_t c = leaf_c[size_t(t)];
+	    if (c < 0) {
+		cerr << "isONclust2 (B200): device and host disagree on whether " << R.Cls[i]->at(0)->id << " is clustered" << endl;
+		exit(1);
+	    }
+	    if (c == ncls) {
+		best[i] = -1;
+		ncls++;
+	    }
+	    else {
+		best[i] = c;
+		strand[i] = leaf_s[size_t(t)];
+	    }
+	    t++;
+	}
+	apply_decisions(L, R, best, strand, cmd.SeqPurge);
+	L.LeftLeaf = names[size_t(b)];
+	L.RightLeaf = "";
+	rights[size_t(b)].reset();
+	if (nb > 1) round_trip(nodes[size_t(b)]);
+    }
+    // ---- replay the merges in the order a sequential driver runs them (level by level, left to right)
+    for (const Job& J : jobs) {
+	Batch& L = *nodes[size_t(J.left)];
+	if (!nodes[size_t(J.right)]) {
+	    cerr << "isONclust2 (B200): merge tree trace names a right node that was already merged" << endl;
+	    exit(1);
+	}
+	Batch& R = *nodes[size_t(J.right)];
+	R.MinDB = MinimizerDB(0, UnsignedHash());
+	if (cmd.MinClsSize > 0) L.SortArgs.MinClsSize = cmd.MinClsSize;
+	if (R.Depth > 0 && R.BatchStart != (L.BatchEnd + 1)) {
+	    cerr << "Trying to merge non-consecutive batches! Giving up!" << endl;
+	    exit(1);
+	}
+	if (L.Depth > 0 && R.Depth > L.Depth) {
+	    cerr << "The left input batch must have higher depth!" << endl;
+	    exit(1);
+	}
+	if (J.cls.size() != R.Cls.size()) {
+	    cerr << "isONclust2 (B200): merge of batches " << J.left << " and " << J.right << ": " << J.cls.size() << " decisions for " << R.Cls.size()
+		 << " clusters" << endl;
+	    exit(1);
+	}
+	unsigned sf = 0;
+	std::vector<int32_t> best(R.Cls.size(), -2), strand(R.Cls.size(), 0);
+	int32_t ncls = int32_t(L.Cls.size());
+	for (size_t i = 0; i < R.Cls.size(); i++) {
+	    const bool ok = right_is_eligible(L, R, i, &sf);
+	    const int32_t c = J.cls[i];
+	    if (ok != (c >= 0)) {
+		cerr << "isONclust2 (B200): device and host disagree on whether cluster " << i << " of the right batch takes part in the merge" << endl;
+		exit(1);
+	    }
+	    if (!ok) continue;
+	    if (c == ncls) {
+		best[i] = -1;
+		ncls++;
+	    }
+	    else {
+		best[i] = c;
+		strand[i] = J.strand[i];
+	    }
+	}
+	apply_decisions(L, R, best, strand, cmd.SeqPurge);
+	L.LeftLeaf = "tree:" + std::to_string(J.left);
+	L.RightLeaf = "tree:" + std::to_string(J.right);
+	nodes[size_t(J.right)].reset();
+	if (&J != &jobs.back()) round_trip(nodes[size_t(J.left)]);
+    }
+    Batch& root = *nodes[0];
+    for (int b = 1; b < nb; b++)
+	if (nodes[size_t(b)]) {
+	    cerr << "isONclust2 (B200): batch " << b << " was never merged" << endl;
+	    exit(1);
+	}
+    if (VERBOSE) {
+	cerr << "Output batch statistics:" << endl;
+	print_batch_info(root);
+    }
+    if (cmd.MinPurge) {
+	cerr << "Purging minimizer database in output batch!" << endl;
+	root.MinDB = MinimizerDB(0, UnsignedHash());
+    }
+    save_batch(root, cmd.OutCereal);
+    if (VERBOSE) cerr << "Output batch written to: " << cmd.OutCereal << endl;
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc == 1) {
@@ -1020,6 +1361,7 @@ int main(int argc, char** argv)
     try {
 	if (sub == "sort") return main_sort(argc, argv);
 	if (sub == "cluster") return main_cluster(argc, argv);
+	if (sub == "tree") return main_tree(argc, argv);
 	if (sub == "info") return main_info(argc, argv);
 	if (sub == "version") {
 	    std::cout << "isONclust2 version: " << ICB_VERSION << endl;

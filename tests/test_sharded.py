@@ -25,8 +25,10 @@ class HostShard:
         self.db = {}
 
     def add(self, cls, mins):
-        for m in mins:
-            self.db.setdefault(int(m["Min"]), []).append(int(cls))
+        for m in mins:  # a cluster enters a posting list once (minimizer.cpp:31-42: only if cls > back())
+            lst = self.db.setdefault(int(m["Min"]), [])
+            if not lst or int(cls) > lst[-1]:
+                lst.append(int(cls))
 
     def query_hits(self, mins, rev_mins):
         from isonclust2_b200.sharded import HIT_DT

@@ -121,3 +121,27 @@ def test_tree_through_the_cli_matches_reference_tree(tmp_path):
     b = _serial_tree(tmp_path / "our", OUR_BIN, n, "t")
     import cerfile
     assert cerfile.same_file_except_total_reads(str(tmp_path / "ref" / a.path), str(tmp_path / "our" / b.path))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["sahlin", "fast"])
+def test_tree_subcommand_equals_file_based_tree(tmp_path, mode):
+    """`isONclust2 tree` (every batch and every merge in one process, nodes resident on the device, batches rebuilt from the
+    decisions) writes the root `.cer` the file-based tree of `cluster` jobs writes — everything but the two leaf names."""
+    n = _sorted_batches(tmp_path, OUR_BIN, n_reads=1200, per_batch=200)
+    assert n == 6
+    from isonclust2_b200 import tree
+    os.makedirs(tmp_path / "t", exist_ok=True)
+
+    def runner(cmd, env):
+        r = subprocess.run(cmd, cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, (cmd, r.stderr[-1500:])
+    root = tree.run_tree(n, "srt/batches", "t", mode, runner=runner, cli=OUR_BIN)
+    r = subprocess.run([OUR_BIN, "tree", "-x", mode, "-v", "-o", "root.cer", "srt/batches"], cwd=tmp_path, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert _same_from_mindb(str(tmp_path / root.path), str(tmp_path / "root.cer"))
+    if os.path.exists(REF_BIN):  # and the reference's own tree over the same sorted batches
+        os.makedirs(tmp_path / "r", exist_ok=True)
+        rroot = tree.run_tree(n, "srt/batches", "r", mode, runner=runner, cli=REF_BIN)
+        assert _same_from_mindb(str(tmp_path / rroot.path), str(tmp_path / "root.cer"))
