@@ -868,6 +868,14 @@ static int main_cluster(int argc, char** argv)
 	     << ") is not part of this build; sort with the default -c (disabled)." << endl;
 	exit(1);
     }
+    if (!SINGLE && left->Cls.size() > 0 && left->MinDB.size() == 0) {
+	// The reference queries the left batch's MinDB AS LOADED: a left batch written with -z (--min-purge) has none, its
+	// clusters are invisible to the merge and every right read founds a new cluster.  This build seeds the device index from
+	// the representatives instead, which would find them — a different output.  Refuse rather than differ.
+	cerr << "isONclust2 (B200): the left batch has " << left->Cls.size() << " clusters but an empty minimizer database (written with "
+	     << "-z / --min-purge?); merging into it is not supported — re-create it without -z." << endl;
+	exit(1);
+    }
     if (left->MinDB.size() == 0) left->MinDB = MinimizerDB(MIN_DB_RESERVE, UnsignedHash());
     right->MinDB = MinimizerDB(0, UnsignedHash());
 

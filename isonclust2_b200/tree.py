@@ -63,9 +63,11 @@ def job_command(node, batch_dir, mode, cli=CLI, extra=()):
     return [cli, "cluster", "-x", mode, "-l", node.left.path, "-r", node.right.path, "-o", node.path, *extra]
 
 
-def run_tree(n_batches, batch_dir, workdir, mode="sahlin", rank=0, world=1, barrier=None, runner=None, cli=CLI, device=None, extra=()):
-    """Runs this rank's share of every level; `barrier()` separates levels; `runner(cmd, env)` executes one job
-    (default: subprocess with ICB_DEVICE set to this rank's GPU).  Returns the root node."""
+def run_tree(n_batches, batch_dir, workdir, mode="sahlin", rank=0, world=1, barrier=None, runner=None, cli=CLI, device=None, extra=(), agree=None,
+             cwd=None):
+    """Runs this rank's share of every level; `barrier()` separates levels (or `agree(ok)`, which also tells every rank
+    whether all of them succeeded); `runner(cmd, env)` executes one job (default: subprocess with ICB_DEVICE set to this
+    rank's GPU) in directory `cwd` (where relative job outputs live; default: the current one).  Returns the root node."""
     levels, root = plan(n_batches, workdir)
     env = dict(os.environ)
     if device is not None:
@@ -86,11 +88,42 @@ def run_tree(n_batches, batch_dir, workdir, mode="sahlin", rank=0, world=1, barr
 
     runner = runner or default_runner
     for jobs in levels:
+        # A failed job must not leave the other ranks waiting in the barrier, nor a half-written output for the next level:
+        # every job writes to a temporary name that is renamed on success, and the ranks agree on the level's outcome
+        # (`agree(ok) -> bool`, an all-reduce of a status flag) in place of a bare barrier.
+        error = None
         for node in shard(jobs, rank, world):
-            runner(job_command(node, batch_dir, mode, cli, extra), env)
-        if barrier is not None:
-            barrier()
+            final = node.path
+            node.path = final + ".partial"
+            try:
+                runner(job_command(node, batch_dir, mode, cli, extra), env)
+                os.replace(os.path.join(cwd or "", node.path), os.path.join(cwd or "", final))
+            except BaseException as e:  # noqa: BLE001 - reported on every rank below
+                error = e
+                break
+            finally:
+                node.path = final
+        if agree is not None:
+            if not agree(error is None):
+                raise RuntimeError(f"merge tree: a job of this level failed on {'this' if error else 'another'} rank") from error
+        else:
+            if error is not None:
+                raise error
+            if barrier is not None:
+                barrier()
     return root
+
+
+def make_agree(dist, device):
+    """`agree(ok)`: True on every rank iff every rank passed True — the barrier between tree levels that also carries the
+    outcome (one MIN all-reduce of a flag), so that no rank waits for a rank that has already given up."""
+    import torch
+
+    def agree(ok):
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+    return agree
 
 
 def count_batches(batch_dir):
@@ -110,7 +143,7 @@ def main(argv=None):
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    barrier = None
+    agree = None
     dist = None
     if world > 1:
         import torch
@@ -119,19 +152,24 @@ def main(argv=None):
         if backend == "nccl":
             torch.cuda.set_device(local)
         dist.init_process_group(backend)
-        barrier = dist.barrier
+        agree = make_agree(dist, torch.device("cuda", local) if backend == "nccl" else torch.device("cpu"))
     sort_dir = os.path.join(args.out, "sorted")
+    ok = True
     if rank == 0:
         os.makedirs(args.out, exist_ok=True)
         env = dict(os.environ, ICB_DEVICE=str(local))
         r = subprocess.run([CLI, "sort", "-o", sort_dir, *args.sort_flags, args.fastq], env=env, stderr=subprocess.PIPE, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stderr)
-            raise SystemExit(r.returncode)
-    if barrier:
-        barrier()
+            ok = False
+    if agree:
+        ok = agree(ok)
+    if not ok:
+        if dist is not None:
+            dist.destroy_process_group()
+        raise SystemExit(1)
     batch_dir = os.path.join(sort_dir, "batches")
-    root = run_tree(count_batches(batch_dir), batch_dir, args.out, args.mode, rank, world, barrier, device=local)
+    root = run_tree(count_batches(batch_dir), batch_dir, args.out, args.mode, rank, world, device=local, agree=agree)
     if rank == 0:
         print(root.path if root else "")
     if dist is not None:

@@ -50,7 +50,9 @@ def runner(cmd, env):
     log.append(" ".join(cmd[1:]))
     r = subprocess.run(cmd, cwd={cwd!r}, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, (cmd, r.stderr[-1500:])
-root = tree.run_tree({n}, "srt/batches", "par", "sahlin", rank, world, dist.barrier, runner=runner, cli={cli!r})
+import torch
+root = tree.run_tree({n}, "srt/batches", "par", "sahlin", rank, world, runner=runner, cli={cli!r}, cwd={cwd!r},
+                     agree=tree.make_agree(dist, torch.device("cpu")))
 gathered = [None] * world
 dist.all_gather_object(gathered, log)
 if rank == 0:
@@ -78,7 +80,7 @@ def _serial_tree(tmp_path, exe, n, outdir):
     def runner(cmd, env):
         r = subprocess.run(cmd, cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert r.returncode == 0, (cmd, r.stderr[-1500:])
-    return tree.run_tree(n, "srt/batches", outdir, "sahlin", runner=runner, cli=exe)
+    return tree.run_tree(n, "srt/batches", outdir, "sahlin", runner=runner, cli=exe, cwd=str(tmp_path))
 
 
 def _same_from_mindb(a, b):
@@ -136,12 +138,67 @@ def test_tree_subcommand_equals_file_based_tree(tmp_path, mode):
     def runner(cmd, env):
         r = subprocess.run(cmd, cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert r.returncode == 0, (cmd, r.stderr[-1500:])
-    root = tree.run_tree(n, "srt/batches", "t", mode, runner=runner, cli=OUR_BIN)
+    root = tree.run_tree(n, "srt/batches", "t", mode, runner=runner, cli=OUR_BIN, cwd=str(tmp_path))
     r = subprocess.run([OUR_BIN, "tree", "-x", mode, "-v", "-o", "root.cer", "srt/batches"], cwd=tmp_path, stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert _same_from_mindb(str(tmp_path / root.path), str(tmp_path / "root.cer"))
     if os.path.exists(REF_BIN):  # and the reference's own tree over the same sorted batches
         os.makedirs(tmp_path / "r", exist_ok=True)
-        rroot = tree.run_tree(n, "srt/batches", "r", mode, runner=runner, cli=REF_BIN)
+        rroot = tree.run_tree(n, "srt/batches", "r", mode, runner=runner, cli=REF_BIN, cwd=str(tmp_path))
         assert _same_from_mindb(str(tmp_path / rroot.path), str(tmp_path / "root.cer"))
+
+
+FAIL_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch
+import torch.distributed as dist
+from isonclust2_b200 import tree
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+def runner(cmd, env):
+    out = cmd[cmd.index("-o") + 1]
+    if rank == 1 and "c_1.cer" in out:
+        raise RuntimeError("job failed on purpose")
+    open(os.path.join({cwd!r}, out), "w").write("x")
+try:
+    tree.run_tree(4, "b", "w", "sahlin", rank, world, runner=runner, cli="none", cwd={cwd!r}, agree=tree.make_agree(dist, torch.device("cpu")))
+    sys.stdout.write("RANK%d-FINISHED\n" % rank)
+except RuntimeError as e:
+    sys.stdout.write("RANK%d-STOPPED: %s\n" % (rank, e))
+sys.stdout.flush()
+dist.destroy_process_group()
+"""
+
+
+def test_failed_job_stops_every_rank(tmp_path):
+    """A job that fails on one rank ends the tree on ALL ranks at the end of that level (no rank is left in a barrier), and the
+    failed job leaves no output behind for a later level to pick up."""
+    os.makedirs(tmp_path / "w")
+    script = tmp_path / "worker.py"
+    script.write_text(FAIL_WORKER.format(root=ROOT, cwd=str(tmp_path)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29633", str(script)], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "RANK0-STOPPED" in r.stdout and "RANK1-STOPPED" in r.stdout and "FINISHED" not in r.stdout
+    assert os.path.exists(tmp_path / "w" / "c_0.cer") and not os.path.exists(tmp_path / "w" / "c_1.cer")
+    assert not [f for f in os.listdir(tmp_path / "w") if f.startswith("m_")]  # no merge level ran
+
+
+def test_merge_into_purged_left_batch_is_refused(tmp_path):
+    """A left batch written with -z has clusters but no MinDB: the reference would not see them, this build would — it refuses
+    (before any device work) instead of writing a different merge."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/isONclust2 not built (needs /root/reference)")
+    n = _sorted_batches(tmp_path, REF_BIN, n_reads=400, per_batch=200)
+    assert n == 2
+    for b, extra in ((0, ["-z"]), (1, [])):
+        r = subprocess.run([REF_BIN, "cluster", "-x", "sahlin", *extra, "-l", f"srt/batches/isONbatch_{b}.cer", "-o", f"c_{b}.cer"], cwd=tmp_path,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+    r = subprocess.run([OUR_BIN, "cluster", "-x", "sahlin", "-l", "c_0.cer", "-r", "c_1.cer", "-o", "m.cer"], cwd=tmp_path, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "empty minimizer database" in r.stderr, r.stderr[-1500:]
+    assert not os.path.exists(tmp_path / "m.cer")
