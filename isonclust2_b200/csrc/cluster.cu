@@ -1570,6 +1570,13 @@ struct icb_tree_trace {
     std::vector<Job> jobs;
 };
 
+// batches (and merges of one tree level) in flight per GPU
+static int default_workers()
+{
+    static const int v = getenv("ICB_WORKERS") ? std::max(1, atoi(getenv("ICB_WORKERS"))) : 48;
+    return v;
+}
+
 // launch priority of the alignment kernels of sorted batch b of n (see cluster_batches_impl)
 static int batch_aln_priority(const icb_ctx* c, int b, int n_batches)
 {
@@ -1649,8 +1656,10 @@ static int cluster_batches_impl(icb_readset* rs, const icb_cluster_params* param
     int rc = icb_readset_prepare_host(rs);
     if (rc) return rc;
     ICB_CUDA(ctx, ctx->wait());  // scores / sketches are complete before other streams read them
-    // a worker mostly sleeps on its stream (icb_ctx::wait), so several batches per host core are kept in flight
-    int nw = n_workers > 0 ? n_workers : std::min(std::max(8, 3 * icb_host_cores()), 48);
+    // A worker sleeps on its stream (icb_ctx::wait) but for 0.6 core-seconds per million reads: how many batches are kept
+    // in flight is a matter of filling the GPU, not of host cores (round 1 sized it by the cores, 3 per core, and a rank with
+    // 4 of a node's 32 cores then ran 12 of its 35 batches at a time).  ICB_WORKERS overrides.
+    int nw = n_workers > 0 ? n_workers : default_workers();
     nw = std::min(nw, int(n_batches));
     std::atomic<int> next(0), first_err(0);
     std::vector<icb_cluster_stats> wstats(nw);
@@ -1762,7 +1771,7 @@ static int cluster_tree_impl(icb_readset* rs, const icb_cluster_params* params, 
     int rc = icb_readset_prepare_host(rs);
     if (rc) return rc;
     ICB_CUDA(ctx, ctx->wait());
-    int nw = n_workers > 0 ? n_workers : std::min(std::max(8, 3 * icb_host_cores()), 48);
+    int nw = n_workers > 0 ? n_workers : default_workers();
     nw = std::min(nw, int(n_batches));
     while (int(ctx->pool_ctx.size()) < nw) {
 	icb_ctx* kid = icb_ctx_create_child(ctx);
