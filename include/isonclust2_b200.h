@@ -79,6 +79,17 @@ int icb_sort_by_score(const double* score, int64_t n, int32_t* order);
  * Uploads the flat reads to the device (the only copy of the inputs the device stages need). */
 int icb_readset_create(icb_ctx* ctx, const char* seq, const char* qual, const int64_t* offs, int64_t n_reads,
 		       icb_readset** rs);
+/* The same with room behind the uploaded reads for extra_reads reads / extra_bases bases appended later, none longer than
+ * extra_max_len: the consensus representatives of `sort -c <positive>` clustering (cluster.cpp:263-303), which replace a
+ * cluster's representative sequence while the batch is being clustered. */
+int icb_readset_create_reserve(icb_ctx* ctx, const char* seq, const char* qual, const int64_t* offs, int64_t n_reads, int64_t extra_reads,
+			       int64_t extra_bases, int64_t extra_max_len, icb_readset** rs);
+/* Appends read `read` of the scored and sketched read set `src` (same context, same k / w) to `rs` — raw sequence,
+ * compressed sequence and both sketches are copied on the device — with the error rates the reference gives a consensus
+ * representative instead of the ones its quality string would give: UpdateClusterConsensus (consensus.cpp:57-63, 96-124)
+ * sets RawSeq's error rate and score and HpcSeq's error rate to weighted means of the cluster's and the joining read's.
+ * *index = the read's index in rs (usable with icb_clusterer_update_representative, icb_align_pairs).  rs must be sketched. */
+int icb_readset_append_from(icb_readset* rs, icb_readset* src, int64_t read, double raw_err, double raw_score, double hpc_err, int64_t* index);
 void icb_readset_destroy(icb_readset* rs);
 int64_t icb_readset_n_reads(const icb_readset* rs);
 int64_t icb_readset_n_bases(const icb_readset* rs);
@@ -290,6 +301,31 @@ int icb_align_traceback(icb_readset* rs, const icb_pair* pair, int kmer_size, ic
 /* InitMinSharedMap (p_emp_prob.cpp:22-47) as the 15 x 15 grid icb_cluster_params wants: path NULL = $ICB_PEMP_TABLE, else
  * data/p_emp_prob.bin next to this library.  Cells without a row are NaN. */
 int icb_load_p_shared(const char* path, int kmer_size, int window_size, double p_shared[225]);
+
+/* ------------------------------------------------------------------ consensus (host side of the path)
+ * The partial-order alignment the reference gets from its vendored spoa 4.0.9 (AVX2 build), restated bit for bit on the
+ * host (csrc/poa.cpp; north_star keeps spoa on the host): engine parameters of main.cpp:284-324 (match 4, mismatch -8,
+ * convex gaps -8/-4, -20/-1), algo = the reference's `-A`: 0 local (kSW), 1 global (kNW), 2 semi-global (kOV, args.h:53).
+ * A graph handle is a spoa::Graph.  None of these calls touches the device. */
+typedef struct icb_poa_graph icb_poa_graph;
+int icb_poa_graph_create(icb_poa_graph** graph);
+void icb_poa_graph_destroy(icb_poa_graph* graph);
+/* spoa::Graph::load / save through cereal's binary archive (graph.hpp:188-276): the ConsGs blobs of a `.cer`.  save writes
+ * *n bytes if cap allows and always returns the size in *n. */
+int icb_poa_graph_load(const void* bytes, int64_t n, icb_poa_graph** graph);
+int icb_poa_graph_save(icb_poa_graph* graph, void* out, int64_t cap, int64_t* n);
+/* sequences().size(), nodes().size(), edges().size() */
+int icb_poa_graph_sizes(const icb_poa_graph* graph, int64_t* n_sequences, int64_t* n_nodes, int64_t* n_edges);
+/* Graph::Clear (graph.cpp:648-657) */
+int icb_poa_graph_clear(icb_poa_graph* graph);
+/* AlignmentEngine::Align (simd_alignment_engine_implementation.hpp:703-780, 1586-2131): pairs (node id or -1, sequence
+ * position or -1); *n_out pairs exist, written if cap allows. */
+int icb_poa_align(icb_poa_graph* graph, const char* seq, int64_t len, int algo, int32_t* node_ids, int32_t* positions, int64_t cap,
+		  int64_t* n_out, int32_t* score);
+/* AddSeqToGraph (consensus.cpp:15-22): Align, then Graph::AddAlignment with one weight for every base */
+int icb_poa_graph_add(icb_poa_graph* graph, const char* seq, int64_t len, uint32_t weight, int algo);
+/* Graph::GenerateConsensus (graph.cpp:368-375): heaviest bundle with branch completion */
+int icb_poa_graph_consensus(icb_poa_graph* graph, char* out, int64_t cap, int64_t* len);
 
 #ifdef __cplusplus
 }

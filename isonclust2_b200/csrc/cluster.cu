@@ -1375,13 +1375,14 @@ int icb_readset_prepare_host(icb_readset* rs)
     icb_ctx* ctx = rs->ctx;
     if (rs->host_ready) return ICB_OK;
     const int64_t n = rs->n_reads;
+    const int64_t cap = std::max(rs->n_reads, rs->cap_reads);  // room for appended reads (icb_readset_append_from)
     cudaStream_t st = ctx->stream;
-    rs->h_status.resize(n);
-    rs->h_hpc_len.resize(n);
-    rs->h_nf.resize(n);
-    rs->h_nr.resize(n);
-    rs->h_score.resize(n);
-    rs->h_err.resize(n);
+    rs->h_status.assign(cap, 0);
+    rs->h_hpc_len.assign(cap, 0);
+    rs->h_nf.assign(cap, 0);
+    rs->h_nr.assign(cap, 0);
+    rs->h_score.assign(cap, 0.0);
+    rs->h_err.assign(cap, 0.0);
     if (n) {
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_status.data(), rs->d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_hpc_len.data(), rs->d_hpc_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
@@ -1390,17 +1391,23 @@ int icb_readset_prepare_host(icb_readset* rs)
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_score.data(), rs->d_score, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->h_err.data(), rs->d_err, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     }
-    if (!rs->d_class) ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&rs->d_class, n + 16));
-    if (!rs->d_bkt) ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&rs->d_bkt, sizeof(uint32_t) * (n + 16)));
+    if (!rs->d_class) ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&rs->d_class, cap + 16));
+    if (!rs->d_bkt) ICB_CUDA(ctx, icb_dmalloc(ctx, (void**)&rs->d_bkt, sizeof(uint32_t) * (cap + 16)));
     int rc0 = icb_classify_errors(ctx, rs->d_hpc_err, rs->d_status, n, rs->d_class);
     if (rc0) return rc0;
     ICB_CUDA(ctx, ctx->wait());
     rs->max_m = 0;
     for (int64_t i = 0; i < n; i++) rs->max_m = std::max(rs->max_m, std::max(rs->h_nf[i], rs->h_nr[i]));
+    if (cap > n && rs->sk_w >= rs->sk_k) {
+	// appended reads are as long as max_len at most: leave their sketches the expected density and a third on top (the
+	// clusterers size their bitmaps and tables by max_m; icb_readset_append_from refuses a sketch above it)
+	const int64_t est = rs->max_len * 2 / (rs->sk_w - rs->sk_k + 2) * 4 / 3 + 64;
+	rs->max_m = int(std::min<int64_t>(32767, std::max<int64_t>(rs->max_m, est)));
+    }
     // bucket count of the reference's hit map per read: unordered_map(20 * (|mins| + |revMins|)) (minimizer.cpp:48) asks the
     // HOST libstdc++ for the next prime; the device loop's candidate-order emulation reads it from this table
     {
-	rs->h_bkt.resize(size_t(n));
+	rs->h_bkt.assign(size_t(cap), 0);
 	std::__detail::_Prime_rehash_policy pol;
 	size_t last_hint = ~size_t(0), last_bkt = 0;
 	for (int64_t i = 0; i < n; i++) {
@@ -1416,6 +1423,93 @@ int icb_readset_prepare_host(icb_readset* rs)
     }
     rs->host_ready = true;
     return ICB_OK;
+}
+
+// A sketched read of another read set becomes read n_reads of this one (see the header).  Everything the clusterers read
+// about a read is filled in: raw and compressed bases, both sketches (appended to the arena), the per-read scalars with the
+// caller's error rates, the error class, the hit map's bucket count, the host mirrors.
+extern "C" int icb_readset_append_from(icb_readset* rs, icb_readset* src, int64_t read, double raw_err, double raw_score, double hpc_err,
+				       int64_t* index)
+{
+    if (!rs || !src || !index || rs == src) return ICB_ERR_ARG;
+    icb_ctx* ctx = rs->ctx;
+    try {
+	ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (src->ctx != ctx) return ctx->fail(ICB_ERR_ARG, "append: both read sets must belong to one context");
+	if (!rs->sketched || !src->sketched || rs->sk_k != src->sk_k || rs->sk_w != src->sk_w)
+	    return ctx->fail(ICB_ERR_STATE, "append: both read sets must be sketched with the same k and w");
+	if (read < 0 || read >= src->n_reads) return ctx->fail(ICB_ERR_ARG, "append: no such read in the source read set");
+	int rc = icb_readset_prepare_host(rs);
+	if (rc) return rc;
+	cudaStream_t st = ctx->stream;
+	// the source read's scalars
+	int32_t sc[4] = {0, 0, 0, 0};  // status, hpc_len, nf, nr
+	int64_t smo = 0;
+	ICB_CUDA(ctx, cudaMemcpyAsync(&sc[0], src->d_status + read, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(&sc[1], src->d_hpc_len + read, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(&sc[2], src->d_nf + read, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(&sc[3], src->d_nr + read, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(&smo, src->d_min_off + read, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+	ICB_CUDA(ctx, ctx->wait());
+	if (sc[0] != 1) return ctx->fail(ICB_ERR_STATE, "append: the source read has no sketch (too short after compression?)");
+	const int64_t so = src->h_offs[size_t(read)], L = src->h_offs[size_t(read) + 1] - so;
+	const int64_t idx = rs->n_reads, base = rs->h_offs[size_t(idx)];
+	const int64_t nm = int64_t(sc[2]) + int64_t(sc[3]);
+	if (idx >= rs->cap_reads || base + L > rs->cap_bases)
+	    return ctx->fail(ICB_ERR_NOMEM, "append: the read set's reserve is used up (icb_readset_create_reserve)");
+	if (rs->arena_used + nm > rs->mins_capacity) return ctx->fail(ICB_ERR_NOMEM, "append: the minimizer arena's reserve is used up");
+	if (L > rs->max_len) return ctx->fail(ICB_ERR_ARG, "append: the read is longer than the reserve's extra_max_len");
+	if (sc[2] > rs->max_m || sc[3] > rs->max_m) return ctx->fail(ICB_ERR_ARG, "append: the read has more minimizers than the read set was prepared for");
+	// bases and sketches, device to device
+	if (L > 0) {
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_seq + base, src->d_seq + so, size_t(L), cudaMemcpyDeviceToDevice, st));
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_qual + base, src->d_qual + so, size_t(L), cudaMemcpyDeviceToDevice, st));
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_hpc_seq + base, src->d_hpc_seq + so, size_t(sc[1]), cudaMemcpyDeviceToDevice, st));
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_hpc_qual + base, src->d_hpc_qual + so, size_t(sc[1]), cudaMemcpyDeviceToDevice, st));
+	}
+	if (nm > 0)
+	    ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_mins + rs->arena_used, src->d_mins + smo, sizeof(icb_minimizer) * size_t(nm),
+					  cudaMemcpyDeviceToDevice, st));
+	// per-read scalars (pageable sources: each copy is staged before the call returns)
+	const int64_t end = base + L, mo = rs->arena_used;
+	const int32_t one = 1;
+	std::__detail::_Prime_rehash_policy pol;
+	const uint32_t bkt = uint32_t(std::min<size_t>(pol._M_next_bkt(20 * (size_t(sc[2]) + size_t(sc[3]))), 0xffffffffu));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_offs + idx + 1, &end, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_status + idx, &one, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_hpc_len + idx, &sc[1], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_nf + idx, &sc[2], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_nr + idx, &sc[3], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_min_off + idx, &mo, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_hpc_err + idx, &hpc_err, sizeof(double), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_err + idx, &raw_err, sizeof(double), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_score + idx, &raw_score, sizeof(double), cudaMemcpyHostToDevice, st));
+	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_bkt + idx, &bkt, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	rc = icb_classify_errors(ctx, rs->d_hpc_err + idx, rs->d_status + idx, 1, rs->d_class + idx);
+	if (rc) return rc;
+	ICB_CUDA(ctx, ctx->wait());
+	// host side
+	rs->h_offs.push_back(end);
+	rs->h_status[size_t(idx)] = 1;
+	rs->h_hpc_len[size_t(idx)] = sc[1];
+	rs->h_nf[size_t(idx)] = sc[2];
+	rs->h_nr[size_t(idx)] = sc[3];
+	rs->h_score[size_t(idx)] = raw_score;
+	rs->h_err[size_t(idx)] = raw_err;
+	rs->h_bkt[size_t(idx)] = bkt;
+	rs->n_reads = idx + 1;
+	rs->n_bases = end;
+	rs->arena_used += nm;
+	rs->total_f = rs->total_r = -1;
+	*index = idx;
+	return ICB_OK;
+    }
+    catch (const std::bad_alloc&) {
+	return ctx->fail(ICB_ERR_NOMEM, "append: out of host memory");
+    }
+    catch (...) {
+	return ctx->fail(ICB_ERR_STATE, "append: unexpected exception");
+    }
 }
 
 // The candidate-order emulation (ref_order.h, ref_order_hd.h and their device form in dloop.cu) restates what THIS

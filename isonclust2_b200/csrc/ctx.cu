@@ -289,13 +289,21 @@ static const int64_t PAD = 256;	 // slack after the byte buffers so 16-byte tile
 int icb_readset_create(icb_ctx* ctx, const char* seq, const char* qual, const int64_t* offs, int64_t n_reads,
 		       icb_readset** out)
 {
+    return icb_readset_create_reserve(ctx, seq, qual, offs, n_reads, 0, 0, 0, out);
+}
+
+int icb_readset_create_reserve(icb_ctx* ctx, const char* seq, const char* qual, const int64_t* offs, int64_t n_reads, int64_t extra_reads,
+			       int64_t extra_bases, int64_t extra_max_len, icb_readset** out)
+{
     IcbRange nvtx_range("upload reads (icb_readset_create)");
-    if (!ctx || !out || n_reads < 0 || (n_reads > 0 && (!seq || !qual || !offs))) return ICB_ERR_ARG;
+    if (!ctx || !out || n_reads < 0 || (n_reads > 0 && (!seq || !qual || !offs)) || extra_reads < 0 || extra_bases < 0 || extra_max_len < 0)
+	return ICB_ERR_ARG;
     *out = nullptr;
     ICB_CUDA(ctx, cudaSetDevice(ctx->device));
     auto rs = new icb_readset;
     rs->ctx = ctx;
     rs->n_reads = n_reads;
+    rs->h_offs.reserve(size_t(n_reads + extra_reads + 1));
     rs->h_offs.assign(offs, offs + n_reads + 1);
     if (n_reads == 0) rs->h_offs.assign(1, 0);
     for (int64_t i = 0; i < n_reads; i++) {
@@ -311,22 +319,25 @@ int icb_readset_create(icb_ctx* ctx, const char* seq, const char* qual, const in
 	delete rs;
 	return ctx->fail(ICB_ERR_ARG, "offs[0] must be 0");
     }
-    int64_t nb = rs->n_bases;
+    rs->cap_reads = n_reads + extra_reads;
+    rs->cap_bases = rs->n_bases + extra_bases;
+    if (extra_reads > 0 && extra_max_len > rs->max_len) rs->max_len = extra_max_len;  // alignment workspaces are sized by it
+    const int64_t nb = rs->n_bases, cb = rs->cap_bases, cr = rs->cap_reads;
     cudaError_t e;
 #define RS_ALLOC(ptr, bytes)                                           \
     if ((e = icb_dmalloc(ctx, (void**)&(ptr), (size_t)(bytes))) != cudaSuccess) { \
 	icb_readset_destroy(rs);                                       \
 	return ctx->fail_cuda(e, "cudaMalloc " #ptr, __FILE__, __LINE__);  \
     }
-    RS_ALLOC(rs->d_seq, nb + PAD);
-    RS_ALLOC(rs->d_qual, nb + PAD);
-    RS_ALLOC(rs->d_offs, sizeof(int64_t) * (n_reads + 1));
-    RS_ALLOC(rs->d_score, sizeof(double) * (n_reads + 1));
-    RS_ALLOC(rs->d_err, sizeof(double) * (n_reads + 1));
+    RS_ALLOC(rs->d_seq, cb + PAD);
+    RS_ALLOC(rs->d_qual, cb + PAD);
+    RS_ALLOC(rs->d_offs, sizeof(int64_t) * (cr + 1));
+    RS_ALLOC(rs->d_score, sizeof(double) * (cr + 1));
+    RS_ALLOC(rs->d_err, sizeof(double) * (cr + 1));
     RS_ALLOC(rs->d_counters, sizeof(unsigned long long) * 8);
 #undef RS_ALLOC
-    ICB_CUDA(ctx, cudaMemsetAsync(rs->d_seq + nb, 0, PAD, ctx->stream));
-    ICB_CUDA(ctx, cudaMemsetAsync(rs->d_qual + nb, 0, PAD, ctx->stream));
+    ICB_CUDA(ctx, cudaMemsetAsync(rs->d_seq + nb, 0, size_t(cb - nb + PAD), ctx->stream));
+    ICB_CUDA(ctx, cudaMemsetAsync(rs->d_qual + nb, 0, size_t(cb - nb + PAD), ctx->stream));
     if (nb > 0) {
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_seq, seq, nb, cudaMemcpyHostToDevice, ctx->stream));
 	ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_qual, qual, nb, cudaMemcpyHostToDevice, ctx->stream));

@@ -109,6 +109,10 @@ struct icb_readset {
     int64_t n_reads = 0;
     int64_t n_bases = 0;
     int64_t max_len = 0;
+    // room behind the uploaded reads for reads appended later (icb_readset_append_from: consensus representatives); every
+    // per-read / per-base array is allocated for cap_reads / cap_bases
+    int64_t cap_reads = 0, cap_bases = 0;
+    int64_t arena_used = 0;	  // minimizer arena entries in use (after icb_sketch_reads)
     std::vector<int64_t> h_offs;  // host copy of the offsets
     // inputs
     uint8_t* d_seq = nullptr;

@@ -941,7 +941,8 @@ int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const doub
     if (k < 1 || k > 31 || w < k) return ctx->fail(ICB_ERR_ARG, "need 1 <= k <= 31 and k <= w");
     if (w - k + 1 > MAX_W) return ctx->fail(ICB_ERR_ARG, "w - k + 1 above 64 is not supported");
     ICB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int64_t n = rs->n_reads, nb = rs->n_bases;
+    // per-read / per-base arrays are allocated for the read set's capacity (reads appended later: icb_readset_append_from)
+    const int64_t n = std::max(rs->n_reads, rs->cap_reads), nb = std::max(rs->n_bases, rs->cap_bases);
     cudaError_t e;
 #define SK_ALLOC(ptr, bytes)                                              \
     if (!(ptr) && (e = icb_dmalloc(ctx, (void**)&(ptr), (size_t)(bytes))) != cudaSuccess) \
@@ -956,9 +957,9 @@ int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const doub
     SK_ALLOC(rs->d_nr, sizeof(int32_t) * (n + 1));
     SK_ALLOC(rs->d_long_list, sizeof(int32_t) * 2 * (n + 1));  // list 1 and list 2
     uint8_t* d_skip = nullptr;
-    if (skip && n > 0) {
-	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_skip, n, ctx->stream));
-	ICB_CUDA(ctx, cudaMemcpyAsync(d_skip, skip, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (skip && rs->n_reads > 0) {
+	ICB_CUDA(ctx, cudaMallocAsync((void**)&d_skip, rs->n_reads, ctx->stream));
+	ICB_CUDA(ctx, cudaMemcpyAsync(d_skip, skip, rs->n_reads, cudaMemcpyHostToDevice, ctx->stream));
     }
     // minimizer arena: expected density 2/(W+1) per compressed base and strand; grow and rerun on overflow
     const int W = w - k + 1;
@@ -983,8 +984,10 @@ int icb_sketch_reads(icb_readset* rs, int kmer_size, int window_size, const doub
 	    if (d_skip) cudaFreeAsync(d_skip, ctx->stream);
 	    return ctx->fail(ICB_ERR_INVALID_BASE, "Invalid base encountered");
 	}
+	rs->arena_used = int64_t(c[0]);
 	if (int64_t(c[0]) <= rs->mins_capacity) break;
-	want = int64_t(c[0]) + 1024;  // exact need is known now
+	// exact need is known now; appended reads get the expected density of their bases on top
+	want = int64_t(c[0]) + 1024 + int64_t(double(nb - rs->n_bases) * (2.0 * 2.0 / (W + 1)) * 1.1);
     }
     if (d_skip) ICB_CUDA(ctx, cudaFreeAsync(d_skip, ctx->stream));
     // CalcErrorRate on the compressed qualities (qualscore.cpp:78): FP64 chain per read, thread per read

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -573,4 +574,58 @@ int64_t ref_mindb_after_updates(const uint32_t* clsMins, const int64_t* clsOffs,
     return int64_t(ks.size());
 }
 
+// ---------------------------------------------------------------- spoa (vendor/spoa 4.0.9), as consensus.cpp drives it
+// A graph handle is a spoa::Graph; ref_poa_add = AddSeqToGraph (consensus.cpp:15-22), ref_poa_consensus =
+// Graph::GenerateConsensus (graph.cpp:368-375), ref_poa_save / ref_poa_load = the cereal binary archive of the graph alone
+// (graph.hpp:188-276), ref_poa_align = AlignmentEngine::Align without adding.
+void* ref_poa_new() { return new spoa::Graph(); }
+void ref_poa_free(void* g) { delete static_cast<spoa::Graph*>(g); }
+void ref_poa_clear(void* g) { static_cast<spoa::Graph*>(g)->Clear(); }
+int64_t ref_poa_num_sequences(void* g) { return int64_t(static_cast<spoa::Graph*>(g)->sequences().size()); }
+int64_t ref_poa_num_nodes(void* g) { return int64_t(static_cast<spoa::Graph*>(g)->nodes().size()); }
+void ref_poa_add(void* g, const char* seq, int n, unsigned weight, int algo)
+{
+    ensureSpoa(algo);
+    AddSeqToGraph(std::string(seq, size_t(n)), static_cast<spoa::Graph*>(g), SpoaEngine.get(), weight);
+}
+int64_t ref_poa_align(void* g, const char* seq, int n, int algo, int32_t* nodes, int32_t* pos, int64_t cap, int32_t* score)
+{
+    ensureSpoa(algo);
+    std::int32_t sc = 0;
+    auto a = SpoaEngine->Align(std::string(seq, size_t(n)), *static_cast<spoa::Graph*>(g), &sc);
+    if (score) *score = sc;
+    if (int64_t(a.size()) <= cap)
+	for (size_t i = 0; i < a.size(); i++) {
+	    nodes[i] = a[i].first;
+	    pos[i] = a[i].second;
+	}
+    return int64_t(a.size());
+}
+int64_t ref_poa_consensus(void* g, char* out, int64_t cap)
+{
+    std::string c = static_cast<spoa::Graph*>(g)->GenerateConsensus();
+    if (int64_t(c.size()) <= cap) memcpy(out, c.data(), c.size());
+    return int64_t(c.size());
+}
+int64_t ref_poa_save(void* g, char* out, int64_t cap)
+{
+    std::ostringstream os(std::ios::binary);
+    {
+	cereal::BinaryOutputArchive ar(os);
+	ar(*static_cast<spoa::Graph*>(g));
+    }
+    const std::string s = os.str();
+    if (int64_t(s.size()) <= cap) memcpy(out, s.data(), s.size());
+    return int64_t(s.size());
+}
+void* ref_poa_load(const char* bytes, int64_t n)
+{
+    std::istringstream is(std::string(bytes, size_t(n)), std::ios::binary);
+    auto g = new spoa::Graph();
+    cereal::BinaryInputArchive ar(is);
+    ar(*g);
+    return g;
+}
+
 }  // extern "C"
+
