@@ -90,6 +90,10 @@ int icb_readset_create_reserve(icb_ctx* ctx, const char* seq, const char* qual, 
  * sets RawSeq's error rate and score and HpcSeq's error rate to weighted means of the cluster's and the joining read's.
  * *index = the read's index in rs (usable with icb_clusterer_update_representative, icb_align_pairs).  rs must be sketched. */
 int icb_readset_append_from(icb_readset* rs, icb_readset* src, int64_t read, double raw_err, double raw_score, double hpc_err, int64_t* index);
+/* Replaces the per-read error rates / scores computed by icb_score_reads and icb_sketch_reads (n_reads doubles each, NULL =
+ * keep): a batch loaded from a `.cer` carries the values the reference clusters with, and for consensus representatives
+ * those are not functions of the quality string.  Call before the first clusterer is created on rs. */
+int icb_readset_set_errors(icb_readset* rs, const double* raw_err, const double* raw_score, const double* hpc_err);
 void icb_readset_destroy(icb_readset* rs);
 int64_t icb_readset_n_reads(const icb_readset* rs);
 int64_t icb_readset_n_bases(const icb_readset* rs);

@@ -2,9 +2,12 @@
 // (SURVEY App. C#13).
 #include "cer.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
+#include <iterator>
+#include <set>
 
 namespace icb {
 
@@ -570,81 +573,110 @@ bool right_is_eligible(const Batch& left, const Batch& right, size_t i, unsigned
     return true;
 }
 
-void apply_decisions(Batch& left, Batch& right, const std::vector<int32_t>& best_of, const std::vector<int32_t>& strand_of, bool seq_purge)
+void apply_decision(Batch& left, Batch& right, size_t i, int best, int strand, bool seq_purge)
 {
     auto& cls = left.Cls;
     auto& reads = right.Cls;
-    left.ConsGs.reserve(cls.size());
-    for (size_t i = 0; i < reads.size(); i++) {
-	const int best = best_of[i];
-	if (best == -2) continue;
-	if (best == -1) {  // cluster.cpp:177-223
-	    const unsigned newId = unsigned(cls.size());
-	    const size_t nrReads = reads[i]->size();
-	    add_minimizers(reads[i]->at(0)->mins, newId, left.MinDB);
-	    if (nrReads == 1) {
-		const auto& rep = reads[i]->at(0);
-		auto nrep = std::make_shared<ProcSeq>();
-		nrep->raw.reset(new SeqRec(*rep->raw));
-		nrep->hpc.reset(new SeqRec(*rep->hpc));
-		nrep->mins = rep->mins;
-		nrep->rev = rep->rev;
-		nrep->strand = rep->strand;
-		nrep->id = rep->id;
-		const std::string repName = "rep_" + std::to_string(left.BatchNr) + "_" + std::to_string(newId);
-		nrep->raw->name = repName;
-		nrep->hpc->name = repName;
-		reads[i]->insert(reads[i]->begin(), 1, std::move(nrep));
-	    }
-	    left.ConsGs.emplace_back();
-	    left.ConsGsValid.push_back(1);
-	    chain_graph(reads[i]->at(0)->raw->seq, left.ConsGs.back());
-	    cls.emplace_back(reads[i]);
-	    if (nrReads == 1 && cls[newId]->size() != 2) {
-		std::cerr << "Inconsistent initial cluster size " << cls[newId]->size() << " for read: " << cls[newId]->at(0)->raw->name
-			  << std::endl;
-		std::cerr << "Aborting clustering!" << std::endl;
-		exit(1);
-	    }
-	    left.NrCls++;
-	    if (right.ConsGs.size() > 0 && right.ConsGsValid[i]) {
-		right.ConsGsValid[i] = 0;
-		right.ConsGs[i].clear();
-	    }
+    if (best == -2) return;
+    if (best == -1) {  // cluster.cpp:177-223
+	const unsigned newId = unsigned(cls.size());
+	const size_t nrReads = reads[i]->size();
+	add_minimizers(reads[i]->at(0)->mins, newId, left.MinDB);
+	if (nrReads == 1) {
+	    const auto& rep = reads[i]->at(0);
+	    auto nrep = std::make_shared<ProcSeq>();
+	    nrep->raw.reset(new SeqRec(*rep->raw));
+	    nrep->hpc.reset(new SeqRec(*rep->hpc));
+	    nrep->mins = rep->mins;
+	    nrep->rev = rep->rev;
+	    nrep->strand = rep->strand;
+	    nrep->id = rep->id;
+	    const std::string repName = "rep_" + std::to_string(left.BatchNr) + "_" + std::to_string(newId);
+	    nrep->raw->name = repName;
+	    nrep->hpc->name = repName;
+	    reads[i]->insert(reads[i]->begin(), 1, std::move(nrep));
 	}
-	else {	// cluster.cpp:224-257 (consMaxSize <= 0 continues at :259)
-	    auto& dst = *cls[size_t(best)];
-	    dst.reserve(dst.size() + reads[i]->size());
-	    for (size_t j = 0; j < reads[i]->size(); j++) {
-		auto& s = reads[i]->at(j);
-		if (!s) {
-		    std::cerr << "Null pointer at position " << j << " in read array " << i << " of size: " << reads[i]->size() << std::endl;
-		    exit(1);
-		}
-		if (strand_of[i] == -1) {
-		    if (s->strand == 1)
-			s->strand = -1;
-		    else if (s->strand == -1)
-			s->strand = 1;
-		    else
-			throw std::runtime_error("Invalid match strand!");
-		}
-		s->mins.clear();
-		s->mins.shrink_to_fit();
-		s->rev.clear();
-		s->rev.shrink_to_fit();
-		if (!seq_purge) {
-		    s->raw.reset();
-		    s->hpc.reset();
-		}
-	    }
-	    size_t first = reads[i]->size() > 1 ? 1 : 0;
-	    for (size_t j = first; j < reads[i]->size(); j++) dst.emplace_back(std::move(reads[i]->at(j)));
+	left.ConsGs.emplace_back();
+	left.ConsGsValid.push_back(1);
+	chain_graph(reads[i]->at(0)->raw->seq, left.ConsGs.back());
+	cls.emplace_back(reads[i]);
+	if (nrReads == 1 && cls[newId]->size() != 2) {
+	    std::cerr << "Inconsistent initial cluster size " << cls[newId]->size() << " for read: " << cls[newId]->at(0)->raw->name
+		      << std::endl;
+	    std::cerr << "Aborting clustering!" << std::endl;
+	    exit(1);
+	}
+	left.NrCls++;
+	if (right.ConsGs.size() > 0 && right.ConsGsValid[i]) {
+	    right.ConsGsValid[i] = 0;
+	    right.ConsGs[i].clear();
 	}
     }
+    else {  // cluster.cpp:224-261 (what follows :263 is the caller's: consensus)
+	auto& dst = *cls[size_t(best)];
+	dst.reserve(dst.size() + reads[i]->size());
+	for (size_t j = 0; j < reads[i]->size(); j++) {
+	    auto& s = reads[i]->at(j);
+	    if (!s) {
+		std::cerr << "Null pointer at position " << j << " in read array " << i << " of size: " << reads[i]->size() << std::endl;
+		exit(1);
+	    }
+	    if (strand == -1) {
+		if (s->strand == 1)
+		    s->strand = -1;
+		else if (s->strand == -1)
+		    s->strand = 1;
+		else
+		    throw std::runtime_error("Invalid match strand!");
+	    }
+	    s->mins.clear();
+	    s->mins.shrink_to_fit();
+	    s->rev.clear();
+	    s->rev.shrink_to_fit();
+	    if (!seq_purge) {
+		s->raw.reset();
+		s->hpc.reset();
+	    }
+	}
+	size_t first = reads[i]->size() > 1 ? 1 : 0;
+	for (size_t j = first; j < reads[i]->size(); j++) dst.emplace_back(std::move(reads[i]->at(j)));
+    }
+}
+
+void finish_decisions(Batch& left, Batch& right)  // cluster.cpp:319-321
+{
     left.Depth++;
     left.BatchEnd = right.BatchEnd;
     left.BatchBases = left.BatchBases + right.BatchBases;
+}
+
+void apply_decisions(Batch& left, Batch& right, const std::vector<int32_t>& best_of, const std::vector<int32_t>& strand_of, bool seq_purge)
+{
+    left.ConsGs.reserve(left.Cls.size());
+    for (size_t i = 0; i < right.Cls.size(); i++) apply_decision(left, right, i, best_of[i], strand_of[i], seq_purge);
+    finish_decisions(left, right);
+}
+
+// UpdateMinDB (minimizer.cpp:124-160) on the batch's own container: operator[] creates the entries the reference creates,
+// so the map's iteration order — the order of the `.cer` — stays the reference's
+void update_min_db(unsigned best, const std::vector<Minimizer>& old_mins, const std::vector<Minimizer>& new_mins, MinimizerDB& db)
+{
+    std::set<unsigned> oldSet, newSet, toIns, toDel;
+    for (const auto& m : old_mins) oldSet.insert(m.Min);
+    for (const auto& m : new_mins) newSet.insert(m.Min);
+    std::set_difference(oldSet.begin(), oldSet.end(), newSet.begin(), newSet.end(), std::inserter(toDel, toDel.begin()));
+    std::set_difference(newSet.begin(), newSet.end(), oldSet.begin(), oldSet.end(), std::inserter(toIns, toIns.begin()));
+    for (unsigned m : toDel) {
+	auto& mins = db[m];
+	std::set<unsigned> tmp(mins.begin(), mins.end());
+	tmp.erase(best);
+	mins.assign(tmp.begin(), tmp.end());
+    }
+    for (unsigned m : toIns) {
+	auto& tv = db[m];
+	tv.push_back(best);
+	std::sort(tv.begin(), tv.end());
+    }
 }
 
 }  // namespace icb

@@ -219,6 +219,12 @@ bool right_is_eligible(const Batch& left, const Batch& right, size_t i, unsigned
 // Applies the per-read decisions to the batches exactly as the reference's loop does: best[i] = cluster id read i joins,
 // -1 = founds a new cluster, -2 = skipped; strand[i] = matched strand of a join.  seq_purge = `-j` (cluster.cpp:249-252).
 void apply_decisions(Batch& left, Batch& right, const std::vector<int32_t>& best, const std::vector<int32_t>& strand, bool seq_purge);
+// one read of that loop / the three assignments behind it (cluster.cpp:319-321): for a caller that interleaves its own work
+// between the reads (consensus, cluster.cpp:263-309)
+void apply_decision(Batch& left, Batch& right, size_t i, int best, int strand, bool seq_purge);
+void finish_decisions(Batch& left, Batch& right);
+// UpdateMinDB (minimizer.cpp:124-160)
+void update_min_db(unsigned best, const std::vector<Minimizer>& old_mins, const std::vector<Minimizer>& new_mins, MinimizerDB& db);
 // AddMinimizers (minimizer.cpp:31-42)
 void add_minimizers(const std::vector<Minimizer>& mins, unsigned cls, MinimizerDB& db);
 // CreatePseudoBatch (serialize.cpp:29-43)

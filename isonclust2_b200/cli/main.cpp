@@ -18,6 +18,7 @@
 #include <cstring>
 #include <iostream>
 #include <limits>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -805,6 +806,252 @@ static void load_p_shared(int k, int w, double out[225])
 }
 
 // ---------------------------------------------------------------- cluster (main.cpp:238-392 + cluster.cpp:67-322)
+// ---------------------------------------------------------------- cluster with consensus (`sort -c <positive>`)
+// cluster.cpp:263-309 + consensus.cpp:34-137.  The partial-order alignment and the heaviest-bundle consensus stay on the host
+// (icb_poa_*, bit-exact to the reference's spoa); what a new consensus means for the clustering runs on the device: the
+// consensus is sketched (icb_sketch_reads on a one-read set), appended to the read set with the reference's weighted error
+// rates (icb_readset_append_from) and made the cluster's representative — UpdateMinDB on the device index and the
+// sequence later reads are aligned with (icb_clusterer_update_representative).
+// A representative that changes under read t invalidates every decision taken for later reads, so the device clusters
+// the right reads in sub-batches that END where the first change can happen: a join only yields a consensus once the
+// cluster's graph holds consMinSize sequences, so `need` = consMinSize - sequences joins are safe for every cluster.
+struct ConsensusRun {
+    Batch& left;
+    Batch& right;
+    const std::vector<size_t>& eligible;
+    size_t nl;
+    icb_ctx* ctx;
+    icb_readset* rs;
+    icb_clusterer* cl;
+    const int32_t* ids;
+    const CmdArgs& args;
+    int algo;
+    bool seqPurge;
+    std::vector<icb_poa_graph*> graphs;	 // live graph per left cluster (parsed from / written back to left.ConsGs)
+    std::vector<int32_t> nseq;		 // sequences in the cluster's graph, -1 = not known yet (blob not parsed)
+    std::vector<uint8_t> blocked;	 // leaf: the cluster outgrew ConsPeriod (cluster.cpp:267-271), for good
+    unsigned consInvoked;
+    double qualTab[129], qualTabNomin[129];
+};
+
+static icb_poa_graph* cons_graph(ConsensusRun& R, size_t c)
+{
+    if (R.graphs.size() < R.left.ConsGs.size()) R.graphs.resize(R.left.ConsGs.size(), nullptr);
+    if (!R.graphs[c]) {
+	if (c >= R.left.ConsGs.size() || !R.left.ConsGsValid[c]) {
+	    cerr << "isONclust2 (B200): cluster " << c << " has no consensus graph in the left batch" << endl;
+	    exit(1);
+	}
+	int rc = icb_poa_graph_load(R.left.ConsGs[c].data(), int64_t(R.left.ConsGs[c].size()), &R.graphs[c]);
+	if (rc) {
+	    cerr << "isONclust2 (B200): cannot read the consensus graph of cluster " << c << endl;
+	    exit(1);
+	}
+    }
+    return R.graphs[c];
+}
+
+static int64_t graph_sequences(icb_poa_graph* g)
+{
+    int64_t n = 0;
+    icb_poa_graph_sizes(g, &n, nullptr, nullptr);
+    return n;
+}
+
+// UpdateClusterConsensus (consensus.cpp:34-126) and what cluster.cpp:289-303 does with its result
+static void consensus_step(ConsensusRun& R, size_t i, int best, int matchStrand, const std::string& readSeq, double readRawErr, double readHpcErr)
+{
+    const CmdArgs& args = R.args;
+    Batch& left = R.left;
+    Batch& right = R.right;
+    Cluster& cls = *left.Cls[size_t(best)];
+    const bool leaf = left.Depth == -1;
+    if (leaf && args.ConsPeriod > 0 && int(cls.size()) > args.ConsPeriod) {  // cluster.cpp:267-271
+	R.blocked[size_t(best)] = 1;
+	return;
+    }
+    icb_poa_graph* g = cons_graph(R, size_t(best));
+    const bool haveRight = right.ConsGs.size() > 0 && right.ConsGsValid[i];
+    const std::string consName = "cons_" + std::to_string(left.BatchNr) + "_" + std::to_string(i);
+    const int consMinSize = leaf ? args.ConsMinSize : 2;
+    const int k = args.KmerSize, w = args.WindowSize;
+
+    const size_t leftSize = size_t(graph_sequences(g));
+    size_t rightSize = 1;
+    if (haveRight) {
+	icb_poa_graph* rg = nullptr;
+	if (icb_poa_graph_load(right.ConsGs[i].data(), int64_t(right.ConsGs[i].size()), &rg)) {
+	    cerr << "isONclust2 (B200): cannot read the consensus graph of right cluster " << i << endl;
+	    exit(1);
+	}
+	rightSize = size_t(graph_sequences(rg));
+	icb_poa_graph_destroy(rg);
+    }
+    const std::string rs = matchStrand == -1 ? rev_comp_or_die(readSeq) : readSeq;
+    ProcSeq& rep = *cls.at(0);
+    const double hpcErr = (rep.hpc->err * double(leftSize) + readHpcErr * double(rightSize)) / double(leftSize + rightSize);
+    const double rawErr = (rep.raw->err * double(leftSize) + readRawErr * double(rightSize)) / double(leftSize + rightSize);
+    int rc = icb_poa_graph_add(g, rs.data(), int64_t(rs.size()), uint32_t(haveRight ? rightSize : 1), R.algo);
+    if (rc) {
+	cerr << "isONclust2 (B200): partial-order alignment failed [" << rc << "] for " << consName << endl;
+	exit(1);
+    }
+    R.nseq[size_t(best)] = int32_t(leftSize + 1);
+    auto drop_right_graph = [&]() {  // cluster.cpp:305-308
+	if (right.ConsGs.size() > 0 && right.ConsGsValid[i]) {
+	    right.ConsGsValid[i] = 0;
+	    right.ConsGs[i].clear();
+	}
+    };
+    if (int(leftSize + 1) < consMinSize) {
+	drop_right_graph();
+	return;
+    }
+    int64_t clen = 0;
+    icb_poa_graph_consensus(g, nullptr, 0, &clen);
+    std::string cons(size_t(clen), '\0');
+    if (icb_poa_graph_consensus(g, &cons[0], clen, &clen)) {
+	cerr << "isONclust2 (B200): consensus generation failed for " << consName << endl;
+	exit(1);
+    }
+    if (!(cons.length() > unsigned(2 * k) || cons.length() >= unsigned(w))) {
+	cerr << "isONclust2 (B200): the consensus " << consName << " is shorter than 2k and the window (" << cons.length() << " bases); not supported" << endl;
+	exit(1);
+    }
+    const std::vector<Minimizer> oldMins = rep.mins;
+    rep.raw->seq = cons;
+    rep.raw->name = consName;
+    rep.raw->err = rawErr;
+    rep.raw->score = rawErr * double(cons.length());
+    const char fixedQualRaw = std::to_string(int(-10 * log10(rawErr)) + 33)[0];	 // consensus.cpp:98-99: the first character
+    rep.raw->qual = std::string(cons.length(), fixedQualRaw);
+
+    // ---- the consensus on the device: sketch, append, new representative
+    icb_readset* one = nullptr;
+    const int64_t o2[2] = {0, int64_t(cons.size())};
+    ICB_DO(R.ctx, icb_readset_create(R.ctx, cons.data(), rep.raw->qual.data(), o2, 1, &one));
+    ICB_DO(R.ctx, icb_score_reads(one, k, R.qualTab, R.qualTabNomin));
+    ICB_DO(R.ctx, icb_sketch_reads(one, k, w, R.qualTabNomin, nullptr));
+    int32_t status = 0, hpcLen = 0;
+    int64_t nf = 0, nr = 0, mo[2] = {0, 0}, ro[2] = {0, 0};
+    ICB_DO(R.ctx, icb_sketch_sizes(one, &nf, &nr));
+    std::string hs(cons.size() + 1, '\0'), hq(cons.size() + 1, '\0');
+    std::vector<Minimizer> mins(size_t(nf) + 1), rev(size_t(nr) + 1);
+    double devHpcErr = 0.0;
+    ICB_DO(R.ctx, icb_sketch_download(one, &status, &hpcLen, &devHpcErr, &hs[0], &hq[0], reinterpret_cast<icb_minimizer*>(mins.data()), mo,
+				      reinterpret_cast<icb_minimizer*>(rev.data()), ro));
+    if (status != 1) {
+	// consensus.cpp:110-116 keeps such a representative with score -1; it can never be matched again
+	cerr << "isONclust2 (B200): the consensus " << consName << " is too short after homopolymer compression (" << hpcLen << " bases); not supported" << endl;
+	exit(1);
+    }
+    hs.resize(size_t(hpcLen));
+    hq.resize(size_t(hpcLen));
+    mins.resize(size_t(nf));
+    rev.resize(size_t(nr));
+    std::unique_ptr<SeqRec> hpc(new SeqRec);  // HomopolymerCompressObj (hpc.cpp:34-62): name and qualities of the raw consensus
+    hpc->name = consName;
+    hpc->seq = hs;
+    hpc->qual = hq;
+    hpc->err = hpcErr;
+    hpc->score = hpcErr * double(hs.length());
+    rep.hpc = std::move(hpc);
+    rep.mins = mins;
+    rep.rev = rev;
+    int64_t idx = -1;
+    ICB_DO(R.ctx, icb_readset_append_from(R.rs, one, 0, rawErr, rep.raw->score, hpcErr, &idx));
+    ICB_DO(R.ctx, icb_clusterer_update_representative(R.cl, int32_t(best), int32_t(idx)));
+    icb_readset_destroy(one);
+    R.consInvoked++;
+    update_min_db(unsigned(best), oldMins, rep.mins, left.MinDB);
+
+    if (int(leftSize + 1) > args.ConsMaxSize) {	 // ConsPurge (consensus.cpp:128-137)
+	const uint32_t wgt = uint32_t(leftSize + 1);
+	icb_poa_graph_clear(g);
+	if (icb_poa_graph_add(g, cons.data(), int64_t(cons.size()), wgt, R.algo)) {
+	    cerr << "isONclust2 (B200): cannot rebuild the consensus graph of " << consName << endl;
+	    exit(1);
+	}
+	R.nseq[size_t(best)] = 1;
+    }
+    drop_right_graph();
+}
+
+static void cluster_with_consensus(ConsensusRun& R, std::vector<int32_t>& best, std::vector<int32_t>& strand)
+{
+    Batch& left = R.left;
+    Batch& right = R.right;
+    const CmdArgs& args = R.args;
+    const bool leaf = left.Depth == -1;
+    const int consMinSize = leaf ? args.ConsMinSize : 2;
+    const int64_t ne = int64_t(R.eligible.size());
+    R.graphs.assign(left.ConsGs.size(), nullptr);
+    R.nseq.assign(left.Cls.size(), -1);
+    R.blocked.assign(left.Cls.size(), 0);
+    left.ConsGs.reserve(left.Cls.size() + size_t(ne));
+    // joins that are safe for every cluster: a cluster whose graph size is unknown (a loaded left batch) may change at once
+    auto safe_joins = [&]() -> int64_t {
+	int64_t d = std::max(1, consMinSize - 1) + 1;  // a cluster founded inside the sub-batch: its founder + need joins
+	for (size_t c = 0; c < R.nseq.size(); c++) {
+	    if (R.blocked[c]) continue;
+	    const int64_t need = R.nseq[c] < 0 ? 1 : std::max<int64_t>(1, int64_t(consMinSize) - R.nseq[c]);
+	    if (need < d) d = need;
+	    if (d == 1) break;
+	}
+	return d;
+    };
+    std::vector<int32_t> cluster_of, strand_of;
+    int32_t ncls = int32_t(R.nl);
+    size_t next_right = 0;	// right reads below this index have been applied
+    int64_t pos = 0;
+    while (pos < ne) {
+	const int64_t nsub = std::min<int64_t>(std::min<int64_t>(safe_joins(), ne - pos), 4096);
+	cluster_of.assign(size_t(nsub), -1);
+	strand_of.assign(size_t(nsub), 0);
+	ICB_DO(R.ctx, icb_cluster_reads(R.cl, R.ids + R.nl + pos, nsub, cluster_of.data(), strand_of.data()));
+	for (int64_t t = 0; t < nsub; t++) {
+	    const size_t i = R.eligible[size_t(pos + t)];
+	    const int32_t c = cluster_of[size_t(t)];
+	    if (c < 0) {
+		cerr << "isONclust2 (B200): device and host disagree on whether " << right.Cls[i]->at(0)->id << " is clustered" << endl;
+		exit(1);
+	    }
+	    next_right = i + 1;
+	    const ProcSeq& r0 = *right.Cls[i]->at(0);
+	    const std::string readSeq = r0.raw->seq;  // cluster.cpp:170-175
+	    const double readRawErr = r0.raw->err, readHpcErr = r0.hpc->err;
+	    if (c == ncls) {
+		best[i] = -1;
+		ncls++;
+		apply_decision(left, right, i, -1, 0, R.seqPurge);
+		R.nseq.push_back(1);
+		R.blocked.push_back(0);
+	    }
+	    else {
+		best[i] = c;
+		strand[i] = strand_of[size_t(t)];
+		apply_decision(left, right, i, c, strand[i], R.seqPurge);
+		consensus_step(R, i, c, strand[i], readSeq, readRawErr, readHpcErr);
+	    }
+	}
+	pos += nsub;
+    }
+    (void)next_right;
+    finish_decisions(left, right);
+    for (size_t c = 0; c < R.graphs.size(); c++)
+	if (R.graphs[c]) {
+	    int64_t nb = 0;
+	    icb_poa_graph_save(R.graphs[c], nullptr, 0, &nb);
+	    left.ConsGs[c].resize(size_t(nb));
+	    if (icb_poa_graph_save(R.graphs[c], &left.ConsGs[c][0], nb, &nb)) {
+		cerr << "isONclust2 (B200): cannot serialize the consensus graph of cluster " << c << endl;
+		exit(1);
+	    }
+	    icb_poa_graph_destroy(R.graphs[c]);
+	    R.graphs[c] = nullptr;
+	}
+}
+
 static int main_cluster(int argc, char** argv)
 {
     CmdArgsCluster cmd = parse_args_cluster(argc, argv);
@@ -836,7 +1083,9 @@ static int main_cluster(int argc, char** argv)
     }
     if (left->SortArgs.Mode != cmd.Mode) left->SortArgs.Mode = cmd.Mode;
     if (right->SortArgs.Mode != cmd.Mode) right->SortArgs.Mode = cmd.Mode;
-    if (VERBOSE && left->SortArgs.ConsMaxSize > 0) cerr << "Generating consensus using spoa algorithm: " << cmd.SpoaAlgo << endl;
+    if (VERBOSE && left->SortArgs.ConsMaxSize > 0)  // main.cpp:304-320
+	cerr << "Generating consensus using spoa algorithm: " << (cmd.SpoaAlgo == 0 ? "local" : cmd.SpoaAlgo == 1 ? "global" : cmd.SpoaAlgo == 2 ? "semi-global" : "")
+	     << endl;
     if (cmd.MinClsSize > 0) left->SortArgs.MinClsSize = cmd.MinClsSize;
     if (VERBOSE) {
 	cerr << "Clustering mode: ";
@@ -863,11 +1112,8 @@ static int main_cluster(int argc, char** argv)
 	cerr << "The left input batch must have higher depth!" << endl;
 	exit(1);
     }
-    if (args.ConsMaxSize > 0) {
-	cerr << "isONclust2 (B200): consensus generation (-c " << args.ConsMaxSize
-	     << ") is not part of this build; sort with the default -c (disabled)." << endl;
-	exit(1);
-    }
+    const bool CONS = args.ConsMaxSize > 0;  // cluster.cpp:263-265
+    unsigned consInvoked = 0;
     if (!SINGLE && left->Cls.size() > 0 && left->MinDB.size() == 0) {
 	// The reference queries the left batch's MinDB AS LOADED: a left batch written with -z (--min-purge) has none, its
 	// clusters are invisible to the merge and every right read founds a new cluster.  This build seeds the device index from
@@ -915,9 +1161,32 @@ static int main_cluster(int argc, char** argv)
 	icb_init_qual_tab(qualTabNomin, 1);
 	icb_ctx* ctx = open_device();
 	icb_readset* rs = nullptr;
-	ICB_DO(ctx, icb_readset_create(ctx, seq.data(), qual.data(), offs.data(), n, &rs));
+	if (CONS) {
+	    // room for the consensus representatives (one per join at most, cluster.cpp:263-303), each the length of a
+	    // cluster's transcript: twice the right batch's bases, none longer than twice the longest read
+	    int64_t maxLen = 0, rightBases = 0;
+	    for (int64_t r = 0; r < n; r++) maxLen = std::max(maxLen, offs[size_t(r) + 1] - offs[size_t(r)]);
+	    rightBases = offs[size_t(n)] - offs[nl];
+	    ICB_DO(ctx, icb_readset_create_reserve(ctx, seq.data(), qual.data(), offs.data(), n, int64_t(eligible.size()), 2 * rightBases + (1 << 20),
+						   2 * maxLen + 1024, &rs));
+	}
+	else {
+	    ICB_DO(ctx, icb_readset_create(ctx, seq.data(), qual.data(), offs.data(), n, &rs));
+	}
 	ICB_DO(ctx, icb_score_reads(rs, args.KmerSize, qualTab, qualTabNomin));
 	ICB_DO(ctx, icb_sketch_reads(rs, args.KmerSize, args.WindowSize, qualTabNomin, nullptr));
+	if (CONS) {
+	    // A consensus representative carries error rates that are weighted means (consensus.cpp:57-63), not functions of
+	    // its quality string: cluster with the values stored in the batches, as the reference does.
+	    std::vector<double> rawErr(static_cast<size_t>(n)), rawScore(static_cast<size_t>(n)), hpcErr(static_cast<size_t>(n));
+	    for (int64_t r = 0; r < n; r++) {
+		const ProcSeq& p = size_t(r) < nl ? *left->Cls[size_t(r)]->at(0) : *right->Cls[eligible[size_t(r) - nl]]->at(0);
+		rawErr[size_t(r)] = p.raw->err;
+		rawScore[size_t(r)] = p.raw->score;
+		hpcErr[size_t(r)] = p.hpc->err;
+	    }
+	    ICB_DO(ctx, icb_readset_set_errors(rs, rawErr.data(), rawScore.data(), hpcErr.data()));
+	}
 	{  // the sketches in the batch files must be the ones this k / w produce (they are what the reference would query)
 	    const size_t un = static_cast<size_t>(n);
 	    std::vector<int32_t> status(un, 0);
@@ -967,9 +1236,18 @@ static int main_cluster(int argc, char** argv)
 	if (nl) ICB_DO(ctx, icb_clusterer_seed(cl, ids.data(), int64_t(nl)));
 	const int64_t ne = int64_t(eligible.size());
 	std::vector<int32_t> cluster_of(static_cast<size_t>(ne), -1), strand_of(static_cast<size_t>(ne), 0);
-	ICB_DO(ctx, icb_cluster_reads(cl, ids.data() + nl, ne, cluster_of.data(), strand_of.data()));
+	if (CONS) {
+	    ConsensusRun run{*left, *right, eligible, nl, ctx, rs, cl, ids.data(), args, cmd.SpoaAlgo, cmd.SeqPurge, {}, {}, {}, 0};
+	    memcpy(run.qualTab, qualTab, sizeof qualTab);
+	    memcpy(run.qualTabNomin, qualTabNomin, sizeof qualTabNomin);
+	    cluster_with_consensus(run, best, strand);
+	    consInvoked = run.consInvoked;
+	}
+	else {
+	    ICB_DO(ctx, icb_cluster_reads(cl, ids.data() + nl, ne, cluster_of.data(), strand_of.data()));
+	}
 	int32_t ncls = int32_t(nl);
-	for (int64_t t = 0; t < ne; t++) {
+	for (int64_t t = 0; !CONS && t < ne; t++) {
 	    const int32_t c = cluster_of[size_t(t)];
 	    if (c < 0) {
 		cerr << "isONclust2 (B200): device and host disagree on whether " << right->Cls[eligible[size_t(t)]]->at(0)->id << " is clustered" << endl;
@@ -989,13 +1267,14 @@ static int main_cluster(int argc, char** argv)
 	    icb_clusterer_stats(cl, &st);
 	    cerr << "Finished clustering!" << endl;
 	    cerr << "Alignment invocation count: " << st.aln_invoked << " (" << (nright ? 100.0 * double(st.aln_invoked) / double(nright) : 0.0) << "%)" << endl;
-	    cerr << "Consensus invocation count: 0 (0%)" << endl;
+	    cerr << "Consensus invocation count: " << consInvoked << " (" << (consInvoked && nright ? double(consInvoked) / double(nright) * 100 : 0.0)
+		 << "%)" << endl;
 	}
 	icb_clusterer_destroy(cl);
 	icb_readset_destroy(rs);
 	icb_ctx_destroy(ctx);
     }
-    apply_decisions(*left, *right, best, strand, cmd.SeqPurge);
+    if (!(CONS && args.Mode != None && !eligible.empty())) apply_decisions(*left, *right, best, strand, cmd.SeqPurge);
     if (VERBOSE) {
 	std::cout << std::endl;	 // cluster.cpp:312
 	if (left->SortArgs.MinClsSize > 1)

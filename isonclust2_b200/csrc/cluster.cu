@@ -1425,6 +1425,24 @@ int icb_readset_prepare_host(icb_readset* rs)
     return ICB_OK;
 }
 
+// The stored error rates of a loaded batch instead of the ones the quality strings give (see the header)
+extern "C" int icb_readset_set_errors(icb_readset* rs, const double* raw_err, const double* raw_score, const double* hpc_err)
+{
+    if (!rs) return ICB_ERR_ARG;
+    icb_ctx* ctx = rs->ctx;
+    ICB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!rs->scored || !rs->sketched) return ctx->fail(ICB_ERR_STATE, "set_errors needs scored and sketched reads");
+    const size_t bytes = sizeof(double) * size_t(rs->n_reads);
+    if (bytes) {
+	if (raw_err) ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_err, raw_err, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (raw_score) ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_score, raw_score, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (hpc_err) ICB_CUDA(ctx, cudaMemcpyAsync(rs->d_hpc_err, hpc_err, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ICB_CUDA(ctx, ctx->wait());
+    rs->host_ready = false;  // host mirrors and error classes are rebuilt by the next clusterer
+    return ICB_OK;
+}
+
 // A sketched read of another read set becomes read n_reads of this one (see the header).  Everything the clusterers read
 // about a read is filled in: raw and compressed bases, both sketches (appended to the arena), the per-read scalars with the
 // caller's error rates, the error class, the hit map's bucket count, the host mirrors.

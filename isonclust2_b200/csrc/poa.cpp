@@ -25,6 +25,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -445,7 +446,10 @@ PoaAlignment poa_align(const unsigned char* seq, uint32_t len, const PoaGraph& G
     const size_t S = W * N;			 // lanes per row
     const size_t rows = G.nodes.size() + 1;
     const auto& rank_to_node = G.rank_to_node;
-    auto wrap = [](int64_t v) { return T(v); };	 // lane arithmetic wraps (paddw / paddd)
+    typedef typename std::make_unsigned<T>::type U;
+    auto wrap = [](int64_t v) { return T(v); };				       // lane arithmetic wraps (paddw / paddd)
+    auto add = [](T a, T b) -> T { return T(U(U(a) + U(b))); };		       // the same in the lane's own width
+    auto sub = [](T a, T b) -> T { return T(U(U(a) - U(b))); };
 
     if (Wk.H.size() < rows * S) {
 	const size_t want = rows * S + rows * S / 4;
@@ -526,56 +530,68 @@ PoaAlignment poa_align(const unsigned char* seq, uint32_t len, const PoaGraph& G
 	if (node.in.empty()) preds.push_back(0);
 	for (uint32_t e : node.in) preds.push_back(Wk.rank_of[G.edges[e].tail] + 1);
 	for (size_t p = 0; p < preds.size(); p++) {
-	    const T* Hp = H + size_t(preds[p]) * S;
-	    const T* Fp = F + size_t(preds[p]) * S;
-	    const T* Op = O + size_t(preds[p]) * S;
+	    const T* __restrict Hp = H + size_t(preds[p]) * S;
+	    const T* __restrict Fp = F + size_t(preds[p]) * S;
+	    const T* __restrict Op = O + size_t(preds[p]) * S;
+	    T* __restrict Hw = Hr;
+	    T* __restrict Fw = Fr;
+	    T* __restrict Ow = Or;
 	    const T x0 = T(fc[preds[p]]);
 	    if (p == 0) {
 		for (size_t j = 0; j < S; j++) {
-		    Fr[j] = wrap(int64_t(std::max(wrap(int64_t(Hp[j]) + gme), Fp[j])) + ve);
-		    Or[j] = wrap(int64_t(std::max(wrap(int64_t(Hp[j]) + qmc), Op[j])) + vc);
+		    Fw[j] = add(std::max(add(Hp[j], gme), Fp[j]), ve);
+		    Ow[j] = add(std::max(add(Hp[j], qmc), Op[j]), vc);
 		}
-		Hr[0] = wrap(int64_t(x0) + pr[0]);
-		for (size_t j = 1; j < S; j++) Hr[j] = wrap(int64_t(Hp[j - 1]) + pr[j]);
+		Hw[0] = add(x0, pr[0]);
+		for (size_t j = 1; j < S; j++) Hw[j] = add(Hp[j - 1], pr[j]);
 	    }
 	    else {
 		for (size_t j = 0; j < S; j++) {
-		    Fr[j] = std::max(Fr[j], wrap(int64_t(std::max(wrap(int64_t(Hp[j]) + gme), Fp[j])) + ve));
-		    Or[j] = std::max(Or[j], wrap(int64_t(std::max(wrap(int64_t(Hp[j]) + qmc), Op[j])) + vc));
+		    Fw[j] = std::max(Fw[j], add(std::max(add(Hp[j], gme), Fp[j]), ve));
+		    Ow[j] = std::max(Ow[j], add(std::max(add(Hp[j], qmc), Op[j]), vc));
 		}
-		Hr[0] = std::max(Hr[0], wrap(int64_t(x0) + pr[0]));
-		for (size_t j = 1; j < S; j++) Hr[j] = std::max(Hr[j], wrap(int64_t(Hp[j - 1]) + pr[j]));
+		Hw[0] = std::max(Hw[0], add(x0, pr[0]));
+		for (size_t j = 1; j < S; j++) Hw[j] = std::max(Hw[j], add(Hp[j - 1], pr[j]));
 	    }
 	}
 	T xl = T(fc[i]), yl = T(fc[i]);
 	T best[N];
 	for (int k = 0; k < N; k++) best[k] = 0;
 	for (size_t b = 0; b < W; b++) {
-	    T* h = Hr + b * N;
-	    T a[N], q[N], t[N];
-	    for (int k = 0; k < N; k++) h[k] = std::max(h[k], std::max(Fr[b * N + k], Or[b * N + k]));
-	    a[0] = wrap(int64_t(wrap(int64_t(xl) + gme)) + ve);
-	    q[0] = wrap(int64_t(wrap(int64_t(yl) + qmc)) + vc);
+	    T* __restrict h = Hr + b * N;
+	    const T* __restrict fb = Fr + b * N;
+	    const T* __restrict ob = Or + b * N;
+	    T* __restrict eb = Er + b * N;
+	    T* __restrict qb = Qr + b * N;
+	    T a[N], q[N], t[N], u[N];
+	    for (int k = 0; k < N; k++) h[k] = std::max(h[k], std::max(fb[k], ob[k]));
+	    a[0] = add(add(xl, gme), ve);
+	    q[0] = add(add(yl, qmc), vc);
 	    for (int k = 1; k < N; k++) {
-		a[k] = wrap(int64_t(wrap(int64_t(h[k - 1]) + gme)) + ve);
-		q[k] = wrap(int64_t(wrap(int64_t(h[k - 1]) + qmc)) + vc);
+		a[k] = add(add(h[k - 1], gme), ve);
+		q[k] = add(add(h[k - 1], qmc), vc);
 	    }
+#pragma GCC unroll 4
 	    for (int s = 0; s < LOGN; s++) {  // _mmxxx_prefix_max (:107-114, :142-148)
 		const int sh = 1 << s;
-		for (int k = 0; k < N; k++) t[k] = k >= sh ? wrap(int64_t(a[k - sh]) + pen_e[s]) : kNegInf;
-		for (int k = 0; k < N; k++) a[k] = std::max(a[k], t[k]);
-		for (int k = 0; k < N; k++) t[k] = k >= sh ? wrap(int64_t(q[k - sh]) + pen_c[s]) : kNegInf;
-		for (int k = 0; k < N; k++) q[k] = std::max(q[k], t[k]);
+		for (int k = 0; k < N; k++) {
+		    t[k] = k >= sh ? add(a[k >= sh ? k - sh : 0], pen_e[s]) : kNegInf;
+		    u[k] = k >= sh ? add(q[k >= sh ? k - sh : 0], pen_c[s]) : kNegInf;
+		}
+		for (int k = 0; k < N; k++) {
+		    a[k] = std::max(a[k], t[k]);
+		    q[k] = std::max(q[k], u[k]);
+		}
 	    }
 	    for (int k = 0; k < N; k++) h[k] = std::max(h[k], std::max(a[k], q[k]));
-	    xl = std::max(h[N - 1], wrap(int64_t(a[N - 1]) - gme));
-	    yl = std::max(h[N - 1], wrap(int64_t(q[N - 1]) - qmc));
+	    xl = std::max(h[N - 1], sub(a[N - 1], gme));
+	    yl = std::max(h[N - 1], sub(q[N - 1], qmc));
 	    if (P.type == 0)
 		for (int k = 0; k < N; k++) h[k] = std::max(h[k], T(0));
 	    for (int k = 0; k < N; k++) {
 		best[k] = std::max(best[k], h[k]);
-		Er[b * N + k] = a[k];
-		Qr[b * N + k] = q[k];
+		eb[k] = a[k];
+		qb[k] = q[k];
 	    }
 	}
 	if (P.type == 0 || (P.type == 2 && node.out.empty())) {
