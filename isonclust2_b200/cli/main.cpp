@@ -887,7 +887,10 @@ static void consensus_step(ConsensusRun& R, size_t i, int best, int matchStrand,
 	rightSize = size_t(graph_sequences(rg));
 	icb_poa_graph_destroy(rg);
     }
-    const std::string rs = matchStrand == -1 ? rev_comp_or_die(readSeq) : readSeq;
+    // consensus.cpp:47-49 calls RevComp(rs) for a read matched on the reverse strand and DROPS the result (RevComp returns a
+    // new string, util.cpp:13-38): the read goes into the graph as it is, after the same validity check of its bases
+    if (matchStrand == -1) (void)rev_comp_or_die(readSeq);
+    const std::string& rs = readSeq;
     ProcSeq& rep = *cls.at(0);
     const double hpcErr = (rep.hpc->err * double(leftSize) + readHpcErr * double(rightSize)) / double(leftSize + rightSize);
     const double rawErr = (rep.raw->err * double(leftSize) + readRawErr * double(rightSize)) / double(leftSize + rightSize);
@@ -1162,13 +1165,15 @@ static int main_cluster(int argc, char** argv)
 	icb_ctx* ctx = open_device();
 	icb_readset* rs = nullptr;
 	if (CONS) {
-	    // room for the consensus representatives (one per join at most, cluster.cpp:263-303), each the length of a
-	    // cluster's transcript: twice the right batch's bases, none longer than twice the longest read
+	    // room for the consensus representatives (one per join at most, cluster.cpp:263-303).  A consensus is about as long
+	    // as its cluster's transcript, but reads matched on the reverse strand enter the graph unturned (consensus_step)
+	    // and the semi-global alignment then hangs them on an end, so it can be several reads long: four times the right
+	    // batch's bases in all, none longer than eight times the longest read
 	    int64_t maxLen = 0, rightBases = 0;
 	    for (int64_t r = 0; r < n; r++) maxLen = std::max(maxLen, offs[size_t(r) + 1] - offs[size_t(r)]);
 	    rightBases = offs[size_t(n)] - offs[nl];
-	    ICB_DO(ctx, icb_readset_create_reserve(ctx, seq.data(), qual.data(), offs.data(), n, int64_t(eligible.size()), 2 * rightBases + (1 << 20),
-						   2 * maxLen + 1024, &rs));
+	    ICB_DO(ctx, icb_readset_create_reserve(ctx, seq.data(), qual.data(), offs.data(), n, int64_t(eligible.size()), 4 * rightBases + (1 << 20),
+						   8 * maxLen + 1024, &rs));
 	}
 	else {
 	    ICB_DO(ctx, icb_readset_create(ctx, seq.data(), qual.data(), offs.data(), n, &rs));
