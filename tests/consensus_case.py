@@ -16,9 +16,17 @@ STEPS = [("c0.cer", ["cluster", "-x", "sahlin", "-l", "srt/batches/isONbatch_0.c
          ("a1.cer", ["cluster", "-x", "sahlin", "-A", "1", "-l", "srt/batches/isONbatch_0.cer", "-o", "a1.cer"])]
 
 
-def write_input(d):
+# second case: one batch of four large clusters with the whole life of a consensus graph — 15 sequences before the first
+# consensus (ConsMinSize: sub-batches of several reads), restarted above 40 (ConsPurge), abandoned above 60 reads (ConsPeriod)
+P_SORT_ARGS = ["sort", "-B", "50000", "-M", "300", "-c", "40", "-g", "15", "-P", "60", "-o", "srt", "reads.fq"]
+P_READS = dict(n_reads=300, seed=9, reads_per_gene=75, max_len=1200)
+P_STEPS = [("p0.cer", ["cluster", "-x", "sahlin", "-l", "srt/batches/isONbatch_0.cer", "-o", "p0.cer"])]
+
+
+def write_input(d, reads=None):
     from isonclust2_b200 import synth
-    seq, qual, offs = synth.make_reads(N_READS, seed=SEED, reads_per_gene=READS_PER_GENE)
+    kw = reads or dict(n_reads=N_READS, seed=SEED, reads_per_gene=READS_PER_GENE)
+    seq, qual, offs = synth.make_reads(kw.pop("n_reads"), **kw)
     synth.write_fastq(os.path.join(d, "reads.fq"), seq, qual, offs)
 
 
@@ -27,12 +35,12 @@ def digest(path):
     return hashlib.sha256(d[:28] + b"\0\0\0\0" + d[32:]).hexdigest()
 
 
-def run_pipeline(exe, d, steps=STEPS, timeout=1500):
-    """Runs sort + every step in directory d; returns {file: digest} and the stderr of the verbose last merge."""
+def run_pipeline(exe, d, steps=STEPS, timeout=1500, sort_args=SORT_ARGS, n_batches=3):
+    """Runs sort + every step in directory d; returns {file: digest}."""
     out = {}
-    r = subprocess.run([exe] + SORT_ARGS, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    r = subprocess.run([exe] + sort_args, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     assert r.returncode == 0, r.stderr[-2000:]
-    for i in range(3):
+    for i in range(n_batches):
         out[f"isONbatch_{i}.cer"] = digest(os.path.join(d, "srt", "batches", f"isONbatch_{i}.cer"))
     for name, args in steps:
         r = subprocess.run([exe] + args, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)

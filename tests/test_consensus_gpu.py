@@ -40,6 +40,17 @@ def test_consensus_pipeline_matches_reference(tmp_path):
             assert cerfile.same_file_except_total_reads(str(d / name), str(r / name)), name
 
 
+def test_consensus_graph_life_cycle(tmp_path):
+    """ConsMinSize 15 / ConsMaxSize 40 / ConsPeriod 60 on four clusters of 75 reads: several reads per device call while no graph
+    is near ConsMinSize, ConsPurge restarts, clusters that stop updating for good (cluster.cpp:267-271)"""
+    with open(os.path.join(ROOT, "tests", "golden", "consensus_v1.json")) as f:
+        gold = json.load(f)["period_case"]
+    assert gold["sort_args"] == cc.P_SORT_ARGS and gold["reads"] == cc.P_READS
+    cc.write_input(str(tmp_path), dict(cc.P_READS))
+    ours = cc.run_pipeline(OUR_BIN, str(tmp_path), steps=cc.P_STEPS, sort_args=cc.P_SORT_ARGS, n_batches=1)
+    assert ours == gold["digests"]
+
+
 def test_consensus_counts_are_reported(tmp_path):
     """-v prints the reference's counters (main.cpp:355-359); consensus must have been invoked and the spoa line names the algorithm"""
     import subprocess
