@@ -233,14 +233,62 @@ class Context:
     def launch_count(self):
         return self.L.icb_ctx_launch_count(self.h)
 
-    def upload(self, seq, qual, offs):
-        return ReadSet(self, seq, qual, offs)
+    def upload(self, seq, qual, offs, reserve=None):
+        return ReadSet(self, seq, qual, offs, reserve=reserve)
+
+
+class PoaGraph:
+    """spoa::Graph + the reference's alignment engine on the HOST (csrc/poa.cpp, bit-exact to the vendored spoa 4.0.9): the
+    consensus side of `sort -c <positive>` clustering (consensus.cpp:15-137).  algo: 0 local, 1 global, 2 semi-global."""
+
+    def __init__(self, blob=None):
+        self.L = _lib.load()
+        self.h = C.c_void_p()
+        rc = self.L.icb_poa_graph_create(C.byref(self.h)) if blob is None else self.L.icb_poa_graph_load(blob, len(blob), C.byref(self.h))
+        if rc:
+            raise IcbError(rc, "cannot create / load a POA graph")
+
+    def close(self):
+        if self.h:
+            self.L.icb_poa_graph_destroy(self.h)
+            self.h = None
+
+    def _check(self, rc, what):
+        if rc:
+            raise IcbError(rc, what)
+
+    def add(self, seq, weight=1, algo=2):  # AddSeqToGraph
+        self._check(self.L.icb_poa_graph_add(self.h, bytes(seq), len(seq), int(weight), int(algo)), "icb_poa_graph_add")
+
+    def consensus(self):  # Graph::GenerateConsensus
+        n = C.c_int64()
+        self._check(self.L.icb_poa_graph_consensus(self.h, None, 0, C.byref(n)), "icb_poa_graph_consensus")
+        buf = C.create_string_buffer(max(1, n.value))
+        self._check(self.L.icb_poa_graph_consensus(self.h, buf, n.value, C.byref(n)), "icb_poa_graph_consensus")
+        return buf.raw[:n.value]
+
+    def save(self):  # the ConsGs blob of a `.cer`
+        n = C.c_int64()
+        self._check(self.L.icb_poa_graph_save(self.h, None, 0, C.byref(n)), "icb_poa_graph_save")
+        buf = C.create_string_buffer(max(1, n.value))
+        self._check(self.L.icb_poa_graph_save(self.h, buf, n.value, C.byref(n)), "icb_poa_graph_save")
+        return buf.raw[:n.value]
+
+    @property
+    def n_sequences(self):
+        n = C.c_int64()
+        self._check(self.L.icb_poa_graph_sizes(self.h, C.byref(n), None, None), "icb_poa_graph_sizes")
+        return n.value
+
+    def clear(self):
+        self._check(self.L.icb_poa_graph_clear(self.h), "icb_poa_graph_clear")
 
 
 class ReadSet:
-    """Device-resident flat reads + their scores and sketches."""
+    """Device-resident flat reads + their scores and sketches.  reserve = (extra_reads, extra_bases, extra_max_len): room for
+    reads appended later with append_from (consensus representatives)."""
 
-    def __init__(self, ctx, seq, qual, offs):
+    def __init__(self, ctx, seq, qual, offs, reserve=None):
         self.ctx = ctx
         L = ctx.L
         seq = np.ascontiguousarray(seq, dtype=np.uint8) if not isinstance(seq, np.ndarray) else seq
@@ -249,8 +297,24 @@ class ReadSet:
         self.n = len(self.offs) - 1
         self.n_bases = int(self.offs[-1])
         h = C.c_void_p()
-        ctx.check(L.icb_readset_create(ctx.h, seq.ctypes.data, qual.ctypes.data, self.offs.ctypes.data, self.n, C.byref(h)))
+        if reserve is None:
+            ctx.check(L.icb_readset_create(ctx.h, seq.ctypes.data, qual.ctypes.data, self.offs.ctypes.data, self.n, C.byref(h)))
+        else:
+            er, eb, el = (int(v) for v in reserve)
+            ctx.check(L.icb_readset_create_reserve(ctx.h, seq.ctypes.data, qual.ctypes.data, self.offs.ctypes.data, self.n, er, eb, el, C.byref(h)))
         self.h = h
+
+    def append_from(self, src, read, raw_err, raw_score, hpc_err):
+        """Read `read` of the sketched read set `src` becomes the next read of this one, with the given error rates
+        (UpdateClusterConsensus' weighted means, consensus.cpp:57-63).  Returns its index."""
+        idx = C.c_int64()
+        self.ctx.check(self.ctx.L.icb_readset_append_from(self.h, src.h, int(read), float(raw_err), float(raw_score), float(hpc_err), C.byref(idx)))
+        return idx.value
+
+    def set_errors(self, raw_err=None, raw_score=None, hpc_err=None):
+        """Stored error rates / scores of a loaded batch instead of the computed ones (before the first Clusterer)."""
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (raw_err, raw_score, hpc_err)]
+        self.ctx.check(self.ctx.L.icb_readset_set_errors(self.h, *[None if a is None else a.ctypes.data for a in arrs]))
 
     def close(self):
         if self.h:

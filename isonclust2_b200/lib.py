@@ -57,6 +57,19 @@ def load():
     L.icb_readset_create.argtypes = [_p, _p, _p, _p, _i64, C.POINTER(_p)]
     L.icb_readset_destroy.argtypes = [_p]
     L.icb_readset_destroy.restype = None
+    L.icb_readset_create_reserve.argtypes = [_p, _p, _p, _p, _i64, _i64, _i64, _i64, C.POINTER(_p)]
+    L.icb_readset_append_from.argtypes = [_p, _p, _i64, _dbl, _dbl, _dbl, C.POINTER(_i64)]
+    L.icb_readset_set_errors.argtypes = [_p, _p, _p, _p]
+    L.icb_poa_graph_create.argtypes = [C.POINTER(_p)]
+    L.icb_poa_graph_destroy.argtypes = [_p]
+    L.icb_poa_graph_destroy.restype = None
+    L.icb_poa_graph_load.argtypes = [_p, _i64, C.POINTER(_p)]
+    L.icb_poa_graph_save.argtypes = [_p, _p, _i64, C.POINTER(_i64)]
+    L.icb_poa_graph_sizes.argtypes = [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]
+    L.icb_poa_graph_clear.argtypes = [_p]
+    L.icb_poa_align.argtypes = [_p, C.c_char_p, _i64, _i32, _p, _p, _i64, C.POINTER(_i64), C.POINTER(C.c_int32)]
+    L.icb_poa_graph_add.argtypes = [_p, C.c_char_p, _i64, C.c_uint32, _i32]
+    L.icb_poa_graph_consensus.argtypes = [_p, _p, _i64, C.POINTER(_i64)]
     L.icb_readset_n_reads.argtypes = [_p]
     L.icb_readset_n_reads.restype = _i64
     L.icb_readset_n_bases.argtypes = [_p]

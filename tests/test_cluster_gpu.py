@@ -280,6 +280,65 @@ def test_update_representative_vs_oracle(port, ctx, mode):
         rs.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_appended_representatives_vs_oracle(port, ctx, mode):
+    """icb_readset_append_from (the consensus path's way of giving a cluster a NEW representative sequence): the same swaps as
+    above, but every new representative is a read of a SECOND read set appended to the reserve of the first — the device copies
+    its bases and sketches, the caller states its error rates — and the clustering that follows equals the oracle's."""
+    k, w = 11, 15
+    seq, qual, offs = synth.make_reads(400, seed=291 + mode, reads_per_gene=8, min_len=300, max_len=900)
+    score, err = port.fill_scores(qual, offs, k)
+    order = port.sort_order(score)
+    sk = port.sketch_batch(seq, qual, offs, k, w)
+    status = sk["status"].copy()
+    for i in range(len(err)):
+        if port.L.orc_quality_filtered(err[i], 7.0):
+            status[i] = 0
+    good = [int(r) for r in order if status[r] == 1]
+    reps = good[0:40:2]
+    upd = [(3, good[41]), (7, good[43]), (3, good[45]), (11, good[47]), (19, good[49]), (5, good[51])]
+    used = set(reps) | {r for _, r in upd}
+    queries = np.array([r for r in good if r not in used], np.int32)
+    pc = port.cluster_seeded(seq, offs, sk, score, err, reps, upd, queries, k, w, mode, pemp.load_p_shared(k, w), status=status)
+    # the second read set: the replacement reads only
+    src_ids = [r for _, r in upd]
+    s_offs = np.zeros(len(src_ids) + 1, np.int64)
+    s_offs[1:] = np.cumsum([offs[r + 1] - offs[r] for r in src_ids])
+    s_seq = np.concatenate([seq[offs[r]:offs[r + 1]] for r in src_ids])
+    s_qual = np.concatenate([qual[offs[r]:offs[r + 1]] for r in src_ids])
+    rs = ctx.upload(seq, qual, offs, reserve=(len(src_ids), int(s_offs[-1]) + 64, 1000))
+    src = ctx.upload(s_seq, s_qual, s_offs)
+    try:
+        s2, e2 = rs.score(k)
+        rs.sketch_async(k, w, skip=api.quality_filtered(e2, 7.0))
+        src.score(k)
+        src.sketch_async(k, w)
+        cl = api.Clusterer(rs, k, w, mode=mode, chunk_size=32)
+        try:
+            cl.seed(reps)
+            new_id = {}
+            for j, (c, r) in enumerate(upd):
+                idx = rs.append_from(src, j, err[r], score[r], sk["hpc_err"][r])
+                assert idx == len(offs) - 1 + j
+                new_id[idx] = r
+                cl.update_representative(c, idx)
+            c1, s1 = cl.cluster(queries)
+            assert cl.n_clusters == pc["n_clusters"]
+            assert (c1 == pc["cluster"]).all(), np.flatnonzero(c1 != pc["cluster"])[:10]
+            assert (s1 == pc["strand"]).all()
+            f = np.array([new_id.get(int(x), int(x)) for x in cl.founders()])
+            assert (f == pc["founder"]).all()
+            assert cl.stats()["aln_invoked"] == pc["n_aligned"]
+            assert np.isin(c1, [3, 7, 19, 5]).any()
+            with pytest.raises(api.IcbError):  # the reserve is used up
+                rs.append_from(src, 0, err[upd[0][1]], score[upd[0][1]], sk["hpc_err"][upd[0][1]])
+        finally:
+            cl.close()
+    finally:
+        src.close()
+        rs.close()
+
+
 def _per_slot(rc, order):
     """(cluster, strand) per sorted slot from the reference's member lists; -1 / 0 for reads it skipped."""
     slot_of = np.empty(len(order), np.int64)
