@@ -286,7 +286,7 @@ def test_appended_representatives_vs_oracle(port, ctx, mode):
     above, but every new representative is a read of a SECOND read set appended to the reserve of the first — the device copies
     its bases and sketches, the caller states its error rates — and the clustering that follows equals the oracle's."""
     k, w = 11, 15
-    seq, qual, offs = synth.make_reads(400, seed=291 + mode, reads_per_gene=8, min_len=300, max_len=900)
+    seq, qual, offs = synth.make_reads(400, seed=191 + mode, reads_per_gene=8, min_len=300, max_len=900)
     score, err = port.fill_scores(qual, offs, k)
     order = port.sort_order(score)
     sk = port.sketch_batch(seq, qual, offs, k, w)
