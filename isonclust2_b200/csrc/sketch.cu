@@ -58,6 +58,14 @@ struct SketchArgs {
     uint8_t* long_scratch;	   // GLOBAL variant: per-CTA scratch
     int64_t long_scratch_stride;
     int64_t lmax;		   // capacity (bases) of the per-read buffers
+    // 1 << (32 - 2k), handed to the warp kernel as DATA: a k-mer in the low 2k bits of a word (anything above it) times this
+    // is the k-mer in the top 2k bits, one IMAD on the FMA pipe.  Computed in the kernel the compiler sees a power of two and
+    // emits a shift and an add on the ALU pipe, the pipe this kernel is bound by.
+    uint32_t key_mul;
+    // The same for the "argmin changed" flags: minus_one = 0xffffffff and bit[t] = 1 << t as data, so that key - previous key and
+    // flag * bit + mask are IMADs (a compare, a select and an add per window on the ALU pipe otherwise).
+    uint32_t minus_one;
+    uint32_t bit[16];
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt()
@@ -449,6 +457,16 @@ __device__ __forceinline__ uint32_t sw_prmt(uint32_t a, uint32_t b, uint32_t s)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
     return d;
 }
+// acc + (x != y) * bit as IMAD (x - y), VIMNMX (min with 1), IMAD: PTX, because the compiler turns the C form into a compare, a
+// select and an add, all three on the ALU pipe (minus_one = 0xffffffff and bit come in as data, SketchArgs)
+__device__ __forceinline__ uint32_t sw_flag_acc(uint32_t x, uint32_t y, uint32_t minus_one, uint32_t bit, uint32_t acc)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(y), "r"(minus_one), "r"(x));
+    asm("min.u32 %0, %0, 1;" : "+r"(d));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(d), "r"(bit));
+    return acc;
+}
 // bit i of the result = byte i of x is non-zero
 __device__ __forceinline__ uint32_t sw_nonzero_bytes(uint32_t x)
 {
@@ -456,7 +474,8 @@ __device__ __forceinline__ uint32_t sw_nonzero_bytes(uint32_t x)
     return (t * 0x00204081u) >> 28;
 }
 
-template <int W, int SW_LMAX, int MIN_CTAS>
+// KC: k as a compile-time constant (0 = run-time k): which word pair a forward k-mer sits in is then known per unrolled step
+template <int W, int SW_LMAX, int MIN_CTAS, int KC>
 __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(SketchArgs a)
 {
     constexpr int SW_HBUF = SwShape<SW_LMAX>::HBUF, SW_NWORD = SwShape<SW_LMAX>::NWORD, SW_LIST = SwShape<SW_LMAX>::LIST,
@@ -467,9 +486,9 @@ __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(Sketch
     uint8_t* hq = hs + SW_HBUF;
     uint32_t* Fs = reinterpret_cast<uint32_t*>(hq + SW_HBUF);
     uint32_t* Rs = Fs + SW_NWORD;
-    const int k = a.k;
+    const int k = KC ? KC : a.k;
     const uint32_t kmask = (1u << (2 * k)) - 1u;
-    const uint32_t krmul = 1u << (32 - 2 * k);
+    const uint32_t krmul = a.key_mul;  // 1 << (32 - 2k), opaque to the compiler (see SketchArgs)
 
     for (;;) {
 	long long t0 = 0;
@@ -683,10 +702,20 @@ __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(Sketch
 		    uint32_t kf[16 + W - 1], kr[16 + W - 1];
 #pragma unroll
 		    for (int o = 0; o < 16 + W - 1; o++) {
-			const uint32_t y = o == 0 ? fB : (o < 16 ? __funnelshift_l(fC, fB, 2 * o) : (o == 16 ? fC : __funnelshift_l(fD, fC, 2 * (o - 16))));
-			const uint32_t vf = y >> (32 - 2 * k);
 			const uint32_t z = o == 0 ? rB : (o < 16 ? __funnelshift_r(rB, rC, 2 * o) : (o == 16 ? rC : __funnelshift_r(rC, rD, 2 * (o - 16))));
-			kf[o] = vf * 32u + uint32_t(o + 1);	   // smallest key = smallest value, leftmost position
+			if (KC != 0) {
+			    // forward k-mer into the LOW 2k bits of a word (whatever lies above it is multiplied away): one
+			    // shift of the word, or one funnel shift of the pair, that holds it — known per step for a constant k
+			    const uint32_t hi = o < 16 ? fB : fC, lo = o < 16 ? fC : fD;
+			    const int sh = 64 - 2 * (o & 15) - 2 * KC;  // right shift of hi:lo that brings the last base to bit 0
+			    const uint32_t yl = sh >= 32 ? (hi >> (sh - 32)) : __funnelshift_r(lo, hi, sh);
+			    kf[o] = yl * krmul + uint32_t(o + 1);  // value in the top 2k bits, position in the low 5
+			}
+			else {
+			    const uint32_t y = o == 0 ? fB : (o < 16 ? __funnelshift_l(fC, fB, 2 * o) : (o == 16 ? fC : __funnelshift_l(fD, fC, 2 * (o - 16))));
+			    const uint32_t vf = y >> (32 - 2 * k);
+			    kf[o] = vf * 32u + uint32_t(o + 1);	   // smallest key = smallest value, leftmost position
+			}
 			// reverse strand: leftmost there = rightmost here.  The multiplication drops the bits above the k-mer
 			// (mod 2^32): value in the top 2k bits, position in the low 5 of the 32 - 2k below — one IMAD, no mask
 			kr[o] = z * krmul + uint32_t(31 - (o + 1));
@@ -725,8 +754,9 @@ __global__ void __launch_bounds__(SW_THREADS, MIN_CTAS) icb_k_sketch_warp(Sketch
 		    for (int t = 0; t < 16; t++) {
 			const uint32_t bf = t == 0 ? pf : mf[t - 1];
 			const uint32_t br = t == 0 ? pr : mr[t - 1];
-			ff += min(mf[t] ^ bf, 1u) << t;	 // keys differ <=> argmin positions differ
-			fr += min(mr[t] ^ br, 1u) << t;
+			// keys differ <=> argmin positions differ: difference and accumulation on the FMA pipe (SketchArgs::bit)
+			ff = sw_flag_acc(mf[t], bf, a.minus_one, a.bit[t], ff);
+			fr = sw_flag_acc(mr[t], br, a.minus_one, a.bit[t], fr);
 		    }
 		    {
 			// forward: windows q0+t in [0, nwin), window 0 always; reverse (bit t <-> window q0+t-1): windows in [1, nwin],
@@ -870,6 +900,9 @@ int icb_launch_sketch(icb_readset* rs, int k, int w, const uint8_t* d_skip)
     a.long_scratch = nullptr;
     a.long_scratch_stride = 0;
     a.lmax = LMAX_FAST;
+    a.key_mul = (2 * k <= 31) ? (1u << (32 - 2 * k)) : 0u;  // only the warp kernel (2k + 5 <= 32) reads it
+    a.minus_one = 0xffffffffu;
+    for (int t = 0; t < 16; t++) a.bit[t] = 1u << t;
     if (rs->n_reads == 0) return ICB_OK;
     cudaStream_t st = ctx->stream;
     const int W = w - k + 1;
@@ -882,8 +915,12 @@ int icb_launch_sketch(icb_readset* rs, int k, int w, const uint8_t* d_skip)
 	    return e && atoi(e) == 3 ? 3 : 4;
 	}();
 	const size_t smem = size_t(SW_WARPS) * (want_ctas == 3 ? SwShape<3072>::PER_WARP : SwShape<2688>::PER_WARP);
-	auto kern = want_ctas == 3 ? (W == 5 ? icb_k_sketch_warp<5, 3072, 3> : icb_k_sketch_warp<8, 3072, 3>)
-				   : (W == 5 ? icb_k_sketch_warp<5, 2688, 4> : icb_k_sketch_warp<8, 2688, 4>);
+	// compile-time k for the two usual sketches: k 11 / w 15 (the reference's defaults, args.h:13-16) and k 13 / w 20
+	const int kc = (k == 11 && W == 5) ? 11 : (k == 13 && W == 8) ? 13 : 0;
+	auto kern = want_ctas == 3 ? (W == 5 ? (kc ? icb_k_sketch_warp<5, 3072, 3, 11> : icb_k_sketch_warp<5, 3072, 3, 0>)
+					     : (kc ? icb_k_sketch_warp<8, 3072, 3, 13> : icb_k_sketch_warp<8, 3072, 3, 0>))
+				   : (W == 5 ? (kc ? icb_k_sketch_warp<5, 2688, 4, 11> : icb_k_sketch_warp<5, 2688, 4, 0>)
+					     : (kc ? icb_k_sketch_warp<8, 2688, 4, 13> : icb_k_sketch_warp<8, 2688, 4, 0>));
 	ICB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 	int per_sm = 0;
 	ICB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SW_THREADS, smem));
