@@ -12,7 +12,8 @@
 //                       does not fit int16, :718-776), a block's E only sees the cells of its own block BEFORE the
 //                       horizontal states were folded in, arithmetic wraps in the lane type, the row maximum of a sink
 //                       row starts at 0, and the backtrack compares in int.  All of that decides ties, so it is emulated
-//                       lane by lane (the lane loops are written for the compiler's vectoriser).
+//                       lane by lane: the per-predecessor pass as plain loops the compiler vectorises, the block pass on
+//                       GCC vectors (PoaVec).  Host-only file, compiled by g++ (not through nvcc).
 //   linear / affine gap modes (other engine parameters) are not built: the reference hard-codes the convex parameters.
 //
 // No CUDA in this file; it is part of the library so that the CLI and the tests reach it through the C ABI (icb_poa_*).
@@ -430,6 +431,28 @@ int64_t worst_case_score(const PoaParams& P, int64_t i, int64_t j)
     return std::min(-1 * (P.m * std::min(i, j) + gap(std::llabs(i - j))), gap(i) + gap(j));
 }
 
+// N lanes of T as one GCC vector; up<SH>(v, fill): lane k takes v[k - SH], the lanes below SH take fill[0]
+template <typename T, int N>
+struct PoaVec {
+    typedef T V __attribute__((vector_size(sizeof(T) * N)));
+    typedef typename std::make_unsigned<T>::type U;
+    typedef U VU __attribute__((vector_size(sizeof(T) * N)));
+    static inline __attribute__((always_inline)) V add(V x, V y) { return (V)((VU)x + (VU)y); }  // wraps like paddw / paddd
+    static inline __attribute__((always_inline)) V sub(V x, V y) { return (V)((VU)x - (VU)y); }
+    static inline __attribute__((always_inline)) V max(V x, V y) { return x > y ? x : y; }
+    static inline __attribute__((always_inline)) V splat(T x) { return x - V{}; }
+    template <int SH, size_t... K>
+    static inline __attribute__((always_inline)) V up_impl(V v, V fill, std::index_sequence<K...>)
+    {
+	return __builtin_shufflevector(v, fill, (int(K) >= SH ? int(K) - SH : N)...);
+    }
+    template <int SH>
+    static inline __attribute__((always_inline)) V up(V v, V fill)
+    {
+	return up_impl<SH>(v, fill, std::make_index_sequence<N>{});
+    }
+};
+
 // work arrays kept between calls (SimdAlignmentEngine::Realloc, :424-516); every cell read by a call is written by it first
 template <typename T>
 struct PoaWork {
@@ -439,7 +462,7 @@ struct PoaWork {
 };
 
 template <typename T, int N, int LOGN>
-PoaAlignment poa_align(const unsigned char* seq, uint32_t len, const PoaGraph& G, const PoaParams& P, PoaWork<T>& Wk, int32_t* score_out)
+__attribute__((always_inline)) inline PoaAlignment poa_align(const unsigned char* seq, uint32_t len, const PoaGraph& G, const PoaParams& P, PoaWork<T>& Wk, int32_t* score_out)
 {
     const T kNegInf = T(std::numeric_limits<T>::min() + 1024);
     const size_t W = (size_t(len) + N - 1) / N;	 // matrix_width in vectors
@@ -449,7 +472,6 @@ PoaAlignment poa_align(const unsigned char* seq, uint32_t len, const PoaGraph& G
     typedef typename std::make_unsigned<T>::type U;
     auto wrap = [](int64_t v) { return T(v); };				       // lane arithmetic wraps (paddw / paddd)
     auto add = [](T a, T b) -> T { return T(U(U(a) + U(b))); };		       // the same in the lane's own width
-    auto sub = [](T a, T b) -> T { return T(U(U(a) - U(b))); };
 
     if (Wk.H.size() < rows * S) {
 	const size_t want = rows * S + rows * S / 4;
@@ -554,49 +576,50 @@ PoaAlignment poa_align(const unsigned char* seq, uint32_t len, const PoaGraph& G
 		for (size_t j = 1; j < S; j++) Hw[j] = std::max(Hw[j], add(Hp[j - 1], pr[j]));
 	    }
 	}
+	// One register of the reference = one vector here (PoaVec below: GCC vector extensions with constant shuffles, the
+	// compiler picks the instructions — 2 x SSE2 for a plain x86-64 build).
+	typedef PoaVec<T, N> PV;
+	typedef typename PV::V V;
+	const V vninf = PV::splat(kNegInf), vgme = PV::splat(gme), vqmc = PV::splat(qmc), vve = PV::splat(ve), vvc = PV::splat(vc), vzero = V{};
+	V vpe[LOGN], vpc[LOGN];
+	for (int sidx = 0; sidx < LOGN; sidx++) {
+	    vpe[sidx] = PV::splat(pen_e[sidx]);
+	    vpc[sidx] = PV::splat(pen_c[sidx]);
+	}
 	T xl = T(fc[i]), yl = T(fc[i]);
-	T best[N];
-	for (int k = 0; k < N; k++) best[k] = 0;
+	V best = vzero;
 	for (size_t b = 0; b < W; b++) {
-	    T* __restrict h = Hr + b * N;
-	    const T* __restrict fb = Fr + b * N;
-	    const T* __restrict ob = Or + b * N;
-	    T* __restrict eb = Er + b * N;
-	    T* __restrict qb = Qr + b * N;
-	    T a[N], q[N], t[N], u[N];
-	    for (int k = 0; k < N; k++) h[k] = std::max(h[k], std::max(fb[k], ob[k]));
-	    a[0] = add(add(xl, gme), ve);
-	    q[0] = add(add(yl, qmc), vc);
-	    for (int k = 1; k < N; k++) {
-		a[k] = add(add(h[k - 1], gme), ve);
-		q[k] = add(add(h[k - 1], qmc), vc);
+	    V h, fb, ob;
+	    memcpy(&h, Hr + b * N, sizeof h);
+	    memcpy(&fb, Fr + b * N, sizeof fb);
+	    memcpy(&ob, Or + b * N, sizeof ob);
+	    h = PV::max(h, PV::max(fb, ob));
+	    V a = PV::add(PV::add(PV::template up<1>(h, PV::splat(xl)), vgme), vve);
+	    V q = PV::add(PV::add(PV::template up<1>(h, PV::splat(yl)), vqmc), vvc);
+	    // _mmxxx_prefix_max (:107-114, :142-148): lanes move up by 1, 2, 4 (, 8), the vacated ones read -infinity
+	    a = PV::max(a, PV::template up<1>(PV::add(a, vpe[0]), vninf));
+	    q = PV::max(q, PV::template up<1>(PV::add(q, vpc[0]), vninf));
+	    a = PV::max(a, PV::template up<2>(PV::add(a, vpe[1]), vninf));
+	    q = PV::max(q, PV::template up<2>(PV::add(q, vpc[1]), vninf));
+	    a = PV::max(a, PV::template up<4>(PV::add(a, vpe[2]), vninf));
+	    q = PV::max(q, PV::template up<4>(PV::add(q, vpc[2]), vninf));
+	    if (LOGN > 3) {
+		a = PV::max(a, PV::template up<(N > 8 ? 8 : 1)>(PV::add(a, vpe[LOGN - 1]), vninf));
+		q = PV::max(q, PV::template up<(N > 8 ? 8 : 1)>(PV::add(q, vpc[LOGN - 1]), vninf));
 	    }
-#pragma GCC unroll 4
-	    for (int s = 0; s < LOGN; s++) {  // _mmxxx_prefix_max (:107-114, :142-148)
-		const int sh = 1 << s;
-		for (int k = 0; k < N; k++) {
-		    t[k] = k >= sh ? add(a[k >= sh ? k - sh : 0], pen_e[s]) : kNegInf;
-		    u[k] = k >= sh ? add(q[k >= sh ? k - sh : 0], pen_c[s]) : kNegInf;
-		}
-		for (int k = 0; k < N; k++) {
-		    a[k] = std::max(a[k], t[k]);
-		    q[k] = std::max(q[k], u[k]);
-		}
-	    }
-	    for (int k = 0; k < N; k++) h[k] = std::max(h[k], std::max(a[k], q[k]));
-	    xl = std::max(h[N - 1], sub(a[N - 1], gme));
-	    yl = std::max(h[N - 1], sub(q[N - 1], qmc));
-	    if (P.type == 0)
-		for (int k = 0; k < N; k++) h[k] = std::max(h[k], T(0));
-	    for (int k = 0; k < N; k++) {
-		best[k] = std::max(best[k], h[k]);
-		eb[k] = a[k];
-		qb[k] = q[k];
-	    }
+	    h = PV::max(h, PV::max(a, q));
+	    const V xs = PV::max(h, PV::sub(a, vgme)), ys = PV::max(h, PV::sub(q, vqmc));
+	    xl = xs[N - 1];
+	    yl = ys[N - 1];
+	    if (P.type == 0) h = PV::max(h, vzero);
+	    best = PV::max(best, h);
+	    memcpy(Hr + b * N, &h, sizeof h);
+	    memcpy(Er + b * N, &a, sizeof a);
+	    memcpy(Qr + b * N, &q, sizeof q);
 	}
 	if (P.type == 0 || (P.type == 2 && node.out.empty())) {
 	    T row_max = 0;  // _mmxxx_max_value starts at 0 (:254)
-	    for (int k = 0; k < N; k++) row_max = std::max(row_max, best[k]);
+	    for (int k = 0; k < N; k++) row_max = std::max(row_max, T(best[k]));
 	    if (max_score < row_max) {
 		max_score = row_max;
 		max_i = int32_t(i);
@@ -754,13 +777,24 @@ struct icb_poa_graph {
 namespace {
 
 // SimdAlignmentEngine::Align (:703-780)
+// The engine twice: compiled for AVX2 and for the build's baseline, picked when the library is loaded (GCC function
+// multi-versioning) — the lane shuffles of the block pass are one instruction each with AVX2 and a dozen with SSE2.
+__attribute__((target_clones("avx2", "default"))) PoaAlignment poa_align_i16(const unsigned char* seq, uint32_t len, const PoaGraph& G, const PoaParams& P, PoaWork<int16_t>& Wk, int32_t* score)
+{
+    return poa_align<int16_t, 16, 4>(seq, len, G, P, Wk, score);
+}
+__attribute__((target_clones("avx2", "default"))) PoaAlignment poa_align_i32(const unsigned char* seq, uint32_t len, const PoaGraph& G, const PoaParams& P, PoaWork<int32_t>& Wk, int32_t* score)
+{
+    return poa_align<int32_t, 8, 3>(seq, len, G, P, Wk, score);
+}
+
 PoaAlignment poa_align_any(icb_poa_graph* h, const unsigned char* seq, uint32_t len, const PoaParams& P, int32_t* score)
 {
     if (h->g.nodes.empty() || len == 0) return PoaAlignment();
     const int64_t worst = worst_case_score(P, int64_t(len) + 8, int64_t(h->g.nodes.size()));
     if (worst < int64_t(std::numeric_limits<int32_t>::min()) + 1024) throw std::invalid_argument("possible overflow");
-    if (worst < int64_t(std::numeric_limits<int16_t>::min()) + 1024) return poa_align<int32_t, 8, 3>(seq, len, h->g, P, h->w32, score);
-    return poa_align<int16_t, 16, 4>(seq, len, h->g, P, h->w16, score);
+    if (worst < int64_t(std::numeric_limits<int16_t>::min()) + 1024) return poa_align_i32(seq, len, h->g, P, h->w32, score);
+    return poa_align_i16(seq, len, h->g, P, h->w16, score);
 }
 
 bool poa_params(int algo, PoaParams& P)

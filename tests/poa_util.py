@@ -11,7 +11,8 @@ _p, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int
 
 
 def ours():
-    L = C.CDLL(os.path.join(ROOT, "isonclust2_b200", "libisonclust2_b200.so"))
+    # ICB_POA_LIB: another build of csrc/poa.cpp (e.g. one without the AVX2 clone) under the same tests
+    L = C.CDLL(os.environ.get("ICB_POA_LIB") or os.path.join(ROOT, "isonclust2_b200", "libisonclust2_b200.so"))
     L.icb_poa_graph_create.argtypes = [C.POINTER(_p)]
     L.icb_poa_graph_destroy.argtypes = [_p]
     L.icb_poa_graph_destroy.restype = None
