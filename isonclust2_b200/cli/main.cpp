@@ -1005,7 +1005,6 @@ static void cluster_with_consensus(ConsensusRun& R, std::vector<int32_t>& best, 
     };
     std::vector<int32_t> cluster_of, strand_of;
     int32_t ncls = int32_t(R.nl);
-    size_t next_right = 0;	// right reads below this index have been applied
     int64_t pos = 0;
     while (pos < ne) {
 	const int64_t nsub = std::min<int64_t>(std::min<int64_t>(safe_joins(), ne - pos), 4096);
@@ -1019,7 +1018,6 @@ static void cluster_with_consensus(ConsensusRun& R, std::vector<int32_t>& best, 
 		cerr << "isONclust2 (B200): device and host disagree on whether " << right.Cls[i]->at(0)->id << " is clustered" << endl;
 		exit(1);
 	    }
-	    next_right = i + 1;
 	    const ProcSeq& r0 = *right.Cls[i]->at(0);
 	    const std::string readSeq = r0.raw->seq;  // cluster.cpp:170-175
 	    const double readRawErr = r0.raw->err, readHpcErr = r0.hpc->err;
@@ -1039,7 +1037,6 @@ static void cluster_with_consensus(ConsensusRun& R, std::vector<int32_t>& best, 
 	}
 	pos += nsub;
     }
-    (void)next_right;
     finish_decisions(left, right);
     for (size_t c = 0; c < R.graphs.size(); c++)
 	if (R.graphs[c]) {
