@@ -416,6 +416,22 @@ struct PoaGraph {
 	for (uint32_t v : consensus)
 	    if (v >= nn) throw std::runtime_error("graph consensus leaves the node table");
 	if (o != n) throw std::runtime_error("bytes behind the graph");
+	// the alignment walks rows in rank order and reads the rows of a node's predecessors: the stored order must be a
+	// permutation of the nodes with every edge pointing forward (spoa trusts the file; a damaged one must not index outside
+	// the matrices here)
+	if (nr != nn) throw std::runtime_error("graph ranks are not a permutation of its nodes");
+	std::vector<uint32_t> rank_of(nn, 0xffffffffu);
+	for (size_t i = 0; i < nr; i++) {
+	    if (rank_of[rank_to_node[i]] != 0xffffffffu) throw std::runtime_error("graph ranks are not a permutation of its nodes");
+	    rank_of[rank_to_node[i]] = uint32_t(i);
+	}
+	for (const auto& e : edges)
+	    if (rank_of[e.tail] >= rank_of[e.head]) throw std::runtime_error("graph edge points backwards in the stored order");
+	for (uint32_t c = 0; c < num_codes && c < 256; c++)
+	    if (decoder[c] < 0 || decoder[c] > 255) throw std::runtime_error("graph decoder entry outside a byte");
+	if (num_codes > 256) throw std::runtime_error("graph with more than 256 codes");
+	for (const auto& nd : nodes)
+	    if (nd.code >= num_codes) throw std::runtime_error("graph node with an unknown code");
     }
 };
 

@@ -110,3 +110,16 @@ def test_poa_load_rejects_garbage(L):
     blob = good.save()
     assert L.icb_poa_graph_load(blob[:-3], len(blob) - 3, C.byref(h)) != 0
     assert L.icb_poa_graph_load(blob + b"\0", len(blob) + 1, C.byref(h)) != 0
+    # a stored order that is not a forward permutation of the nodes (spoa would walk outside its matrices)
+    import struct
+    n_nodes = good.sizes()[1]
+    tail = 8 + 4 * n_nodes + 8  # rank_to_node_id (count + ids) + the empty consensus vector
+    ranks = list(struct.unpack_from(f"<{n_nodes}I", blob, len(blob) - tail + 8))
+    assert sorted(ranks) == list(range(n_nodes))
+    for bad in ([ranks[0]] * n_nodes, ranks[::-1]):
+        b2 = bytearray(blob)
+        struct.pack_into(f"<{n_nodes}I", b2, len(blob) - tail + 8, *bad)
+        assert L.icb_poa_graph_load(bytes(b2), len(b2), C.byref(h)) != 0
+    b3 = bytearray(blob)
+    struct.pack_into("<I", b3, 4 + 2 * 1032 + 8 + 1 + 4, 77)  # first node's code
+    assert L.icb_poa_graph_load(bytes(b3), len(b3), C.byref(h)) != 0
