@@ -180,3 +180,27 @@ def test_dump_argument_errors(refrun):
         assert r.returncode == 1 and "Specifying output directory is mandatory!" in r.stderr
         r = subprocess.run([exe, "dump", "-o", "dump_bad", "-i", "nope.cer", "m012.cer"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert r.returncode == 1 and "Failed to load index nope.cer" in r.stderr
+
+
+def test_dump_and_info_of_consensus_batches(tmp_path):
+    """`.cer` files of a consensus-on run (`sort -c 12 -g 4`: representatives named cons_<batch>_<read>, graphs with many
+    sequences, a MinDB with emptied posting lists): `dump` and `info` of this build read them like the reference binary."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/isONclust2 not built (needs /root/reference)")
+    import consensus_case as cc
+    d = tmp_path
+    cc.write_input(str(d))
+    cc.run_pipeline(REF_BIN, str(d), steps=cc.STEPS[:5])
+    m = cerfile.parse(str(d / "m012.cer"))
+    assert any(c[0]["raw"]["name"].startswith(b"cons_") for c in m["cls"])
+    for name in ("c0.cer", "m012.cer"):
+        tag = name.replace(".cer", "")
+        run([REF_BIN, "dump", "-i", "srt/sorted_reads_idx.cer", "-o", f"dump_ref_{tag}", name], cwd=d)
+        run([OUR_BIN, "dump", "-i", "srt/sorted_reads_idx.cer", "-o", f"dump_our_{tag}", name], cwd=d)
+        a, b = _tree(d / f"dump_ref_{tag}"), _tree(d / f"dump_our_{tag}")
+        assert sorted(a) == sorted(b) and len(a) > 4
+        for k in a:
+            assert a[k] == b[k], (name, k)
+        ra = subprocess.run([REF_BIN, "info", name], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        rb = subprocess.run([OUR_BIN, "info", name], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert ra.returncode == rb.returncode == 0 and ra.stdout == rb.stdout and ra.stderr == rb.stderr
