@@ -123,3 +123,24 @@ def test_poa_load_rejects_garbage(L):
     b3 = bytearray(blob)
     struct.pack_into("<I", b3, 4 + 2 * 1032 + 8 + 1 + 4, 77)  # first node's code
     assert L.icb_poa_graph_load(bytes(b3), len(b3), C.byref(h)) != 0
+
+
+def test_python_mirror(L):
+    """api.PoaGraph (the ctypes mirror the Python host side uses) over the same entry points"""
+    from isonclust2_b200 import api
+    reads = pu.family(31, 300, 6)
+    g, og = api.PoaGraph(), pu.OurGraph(L)
+    try:
+        for s, w in reads:
+            g.add(s, w, 2)
+            og.add(s, w, 2)
+        assert g.n_sequences == 6 and g.consensus() == og.consensus() and g.save() == og.save()
+        g2 = api.PoaGraph(g.save())
+        assert g2.save() == g.save()
+        g2.clear()
+        assert g2.n_sequences == 0
+        g2.close()
+        with pytest.raises(api.IcbError):
+            api.PoaGraph(b"not a graph")
+    finally:
+        g.close()
